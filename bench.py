@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""Headline benchmark: Mrays/s rendering RGB + 256-d SAM features at 800x800 (BASELINE.json), 1/2/4/8 B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \\
+        bench.py --gpus N --steps K --warmup W
+
+One "step" = one 800x800 frame of the `samnerf_distill` model (SURVEY.md 8 d config 3): 640 000 rays, every ray
+rendered to rgb / median depth / accumulation / proposal depth AND the 256-d SAM feature (k = 16 top samples,
+sharpening 10, patch 1), in the reference's chunks of 32 768 rays, through `libsnrf` (C ABI).  With N > 1 the frame is
+cut into N contiguous row blocks ("screen tiles"), one per rank, followed by one NCCL all-gather of the rendered tiles:
+total work is fixed, so scaling is "strong".  Synthetic scene-like parameters (seed 0), synthetic orbit camera.
+
+`--impl reference` times the reference's own CPU path: the reference is Python + the CUDA-only tinycudann, so its CPU
+implementation is the oracle port (oracle/samnerf_oracle.py, validated against the reference's own modules by
+oracle/make_golden.py), all host threads, on a bounded sample of the same frame per step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+H = W = 800
+BYTES_PER_RAY = {"proposal": 10240, "field": 16384, "sam": 49152}  # SURVEY.md 8 d / BASELINE.md section 3
+METRIC = "Mrays/s rendering RGB+256-d SAM features at 800x800"
+WORKLOAD = "samnerf_distill 800x800 RGB+256-d SAM (k=16, p=1): 640000 rays in chunks of 32768"
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason samples taken DURING the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.path = index, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, reasons, mx = [], set(), None
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    mx = float(f[2])
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            sm.sort()
+            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def frame_rays():
+    from samnerf_b200.synthetic import orbit_rays
+
+    o, d = orbit_rays(H, W, 800.0)
+    return o.reshape(-1, 3).contiguous(), d.reshape(-1, 3).contiguous()
+
+
+def cpu_reference_rate(n_rays: int, repeats: int, cfg, params):
+    """Oracle port on a strided sample of the frame, all host threads.  Returns (Mrays/s best, cores, sample text)."""
+    from oracle.samnerf_oracle import Oracle
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    orc = Oracle(cfg, params)
+    o, d = frame_rays()
+    idx = (torch.arange(n_rays) * (o.shape[0] // n_rays)).long()
+    o, d = o[idx].contiguous(), d[idx].contiguous()
+    best = float("inf")
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            orc.render_rays(o, d, get_feature=("sam",))
+        best = min(best, time.perf_counter() - t0)
+    return n_rays / best / 1e6, cores, f"{n_rays} rays strided over the 800x800 frame, best of {repeats}, torch CPU fp32"
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from samnerf_b200 import SAMNeRFConfig, make_synthetic_params
+    from oracle.samnerf_oracle import Oracle
+
+    cfg = SAMNeRFConfig.distill(clipseg=False, patch_size=1)
+    params = make_synthetic_params(cfg, args.regime, 0)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    orc = Oracle(cfg, params)
+    o, d = frame_rays()
+    n = args.ref_rays
+    times = []
+    for step in range(args.warmup + args.steps):
+        idx = ((torch.arange(n) * (o.shape[0] // n)) + step) % o.shape[0]
+        oo, dd = o[idx].contiguous(), d[idx].contiguous()
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            orc.render_rays(oo, dd, get_feature=("sam",))
+        dt = time.perf_counter() - t0
+        if step >= args.warmup:
+            times.append(dt)
+    total = sum(times)
+    value = n * len(times) / total / 1e6
+    sample = f"{n} rays strided over the 800x800 frame per step (bounded sample of the 640000-ray frame)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "regime": args.regime, "note": "reference CPU path = oracle port (tinycudann is CUDA-only)"},
+        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_native(args):
+    import torch.distributed as dist
+
+    from samnerf_b200 import SAMNeRFConfig, make_synthetic_params
+    from samnerf_b200.renderer import Renderer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus N > 1 must be launched with torch.distributed.run (one rank per GPU)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    cfg = SAMNeRFConfig.distill(clipseg=False, patch_size=1)
+    params = make_synthetic_params(cfg, args.regime, 0)
+    r = Renderer(cfg, device=local, engine=args.engine)
+    r.load_params(params)
+    o_all, d_all = frame_rays()
+    n_all = o_all.shape[0]
+    assert H % world == 0
+    n_loc = n_all // world
+    lo = rank * n_loc
+    o_host = o_all[lo:lo + n_loc].contiguous().pin_memory()
+    d_host = d_all[lo:lo + n_loc].contiguous().pin_memory()
+    o_dev, d_dev = o_host.to(dev), d_host.to(dev)
+    chunk = cfg.eval_num_rays_per_chunk
+
+    # frame-sized outputs; with N > 1 each rank renders into its row block of the gathered frame (in-place all-gather)
+    names = {"rgb": 3, "depth": 1, "accumulation": 1, "prop_depth_0": 1, "sam": cfg.sam_out}
+    full = {k: torch.empty(n_all, c, device=dev) for k, c in names.items()}
+    mine = {k: v[lo:lo + n_loc] for k, v in full.items()}
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def frame():
+        r.render_frame(o_dev, d_dev, get_feature=("sam",), chunk=chunk, out=mine)
+        if world > 1:
+            for k in names:
+                dist.all_gather_into_tensor(full[k], mine[k])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        frame()
+    barrier()
+    r.kernel_times()
+    r.set_timing(True)
+    launches0 = r.launch_count
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    for s, e in ev:
+        flush.zero_()  # evict L2 between timed frames (not timed)
+        s.record()
+        frame()
+        e.record()
+    barrier()
+    clk = clocks.stop() if rank == 0 else None
+    r.set_timing(False)
+    ktimes = r.kernel_times()
+    launches = r.launch_count - launches0
+    total_ms = sum(s.elapsed_time(e) for s, e in ev)
+    t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    value = n_all * args.steps / (total_ms * 1e-3) / 1e6
+
+    # ---- end to end: pinned host rays in, host images + features out, copies inside the timed region ----------
+    out_host = {k: torch.empty(n_loc, c).pin_memory() for k, c in names.items()}
+    s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    o_stage, d_stage = torch.empty_like(o_dev), torch.empty_like(d_dev)
+
+    def frame_e2e():
+        cur = torch.cuda.current_stream(dev)
+        done = []
+        for i in range(0, n_loc, chunk):
+            sl = slice(i, min(i + chunk, n_loc))
+            with torch.cuda.stream(s_in):
+                o_stage[sl].copy_(o_host[sl], non_blocking=True)
+                d_stage[sl].copy_(d_host[sl], non_blocking=True)
+                ready = torch.cuda.Event()
+                ready.record(s_in)
+            cur.wait_event(ready)
+            r.render(o_stage[sl], d_stage[sl], get_feature=("sam",), out={k: v[sl] for k, v in mine.items()})
+            rendered = torch.cuda.Event()
+            rendered.record(cur)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(rendered)
+                for k in names:
+                    out_host[k][sl].copy_(mine[k][sl], non_blocking=True)
+                fin = torch.cuda.Event()
+                fin.record(s_out)
+            done.append(fin)
+        for f in done:
+            cur.wait_event(f)
+
+    for _ in range(2):
+        frame_e2e()
+    barrier()
+    e2e_steps = max(3, min(args.steps, 5))
+    ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(e2e_steps)]
+    for s, e in ev2:
+        s.record()
+        frame_e2e()
+        e.record()
+    barrier()
+    t2 = torch.tensor([sum(s.elapsed_time(e) for s, e in ev2)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    e2e_value = n_all * e2e_steps / (float(t2.item()) * 1e-3) / 1e6
+    h2d = 2 * n_all * 3 * 4
+    d2h = n_all * sum(names.values()) * 4
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        f_ms, f_cnt = ktimes["feature"]
+        m_ms, m_cnt = ktimes["march"]
+        g_ms, g_cnt = ktimes["tapgemm"]
+        rays_per_launch = n_loc * args.steps / max(f_cnt, 1)
+        ach = BYTES_PER_RAY["sam"] * rays_per_launch / (f_ms / max(f_cnt, 1) * 1e-3) / 1e9 if f_ms > 0 else None
+        path_bytes = sum(BYTES_PER_RAY.values())
+        line = {
+            "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f16 operands / f32 accumulate", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "regime": args.regime, "engine": args.engine,
+                       "l2": "256 MiB buffer zeroed between timed frames (untimed); tables 158 MB + outputs 668 MB > 126 MB L2",
+                       "tiles": f"{world} row block(s) of {H // world} rows + NCCL all-gather" if world > 1 else "single GPU"},
+            "roofline": {"bound": "hbm", "kernel": "sam_kernel (feature-field gather + MLP layer 1 + weighted sum)",
+                         "achieved": ach, "peak": peak, "unit": "GB/s", "frac": (ach / peak) if ach else None,
+                         "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": BYTES_PER_RAY["sam"] * rays_per_launch,
+                         "avg_launch_ms": f_ms / max(f_cnt, 1), "launches_timed": f_cnt,
+                         "path": {"bytes_per_ray": path_bytes, "achieved": value * 1e6 * path_bytes / 1e9 / world,
+                                  "frac": value * 1e6 * path_bytes / 1e9 / world / peak},
+                         "kernel_share_ms_per_step": {"march": m_ms / args.steps, "feature": f_ms / args.steps,
+                                                      "tapgemm": g_ms / args.steps}},
+            "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps, "api": "Renderer.render per chunk, pinned host buffers, 3-stream pipeline"},
+            "gpu_launches": launches,
+            "clocks": clk,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            v, cores, sample = cpu_reference_rate(args.cpu_rays, 2, cfg, params)
+            line["cpu_baseline"] = {"value": v, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["native", "reference"], default="native")
+    ap.add_argument("--regime", choices=["scene", "init"], default="scene")
+    ap.add_argument("--engine", choices=["tcgen05", "mma_sync"], default="tcgen05")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-rays", type=int, default=16384)
+    ap.add_argument("--ref-rays", type=int, default=4096)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

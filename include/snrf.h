@@ -1,0 +1,156 @@
+/* libsnrf - C ABI of the B200-native SAM-NeRF feature-field renderer.
+ *
+ * The reference (WangFeng18/Segment-Anything-in-NeRF) has no FFI of its own: its hot path sits behind the
+ * nerfstudio Python module surface and reaches native code through the `tinycudann` PyTorch extension
+ * (call sites: samnerf/sam_field.py:51,63,84,99; nerfstudio/fields/nerfacto_field.py:144-175,228-240;
+ * nerfstudio/fields/density_fields.py:92-100) plus ~60 ATen launches per chunk.  This header is the boundary a
+ * drop-in replaces that with: plain pointers and sizes, int status codes, no torch types.  Every pointer
+ * argument is a DEVICE pointer unless it says "host"; tensors are contiguous, row-major, rays-major.
+ * All calls are stream-ordered on the `cudaStream_t` passed as `void* stream` (0 = default stream).
+ * One context per (process, device); a context is not thread-safe (the reference serialises its two threads
+ * with train_lock: nerfstudio/viewer/server/render_state_machine.py:190, nerfstudio/engine/trainer.py:222).
+ *
+ * Return value: 0 on success, otherwise a negative SNRF_E_* code; snrf_last_error() has the message.
+ */
+#ifndef SNRF_H_
+#define SNRF_H_
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SNRF_MAX_LEVELS 16
+
+#define SNRF_OK 0
+#define SNRF_E_INVALID (-1) /* bad argument / unsupported configuration */
+#define SNRF_E_CUDA (-2)    /* a CUDA call failed                        */
+#define SNRF_E_STATE (-3)   /* parameters for the requested output were never uploaded */
+
+typedef struct snrf_ctx snrf_ctx;
+
+/* One level of a tcnn HashGrid. */
+typedef struct snrf_level {
+  float scale;     /* exp2f(l*log2f(per_level_scale))*base - 1 */
+  uint32_t res;    /* ceil(scale)+1                             */
+  uint32_t size;   /* entries: min(round_up(res^3,8), 2^log2T)  */
+  uint32_t offset; /* first entry of the level                  */
+  uint32_t hashed; /* res^3 > size                              */
+} snrf_level;
+
+typedef struct snrf_grid_desc {
+  int32_t n_levels;
+  int32_t n_features; /* 2 (density fields) or 8 (feature field) */
+  snrf_level lv[SNRF_MAX_LEVELS];
+} snrf_grid_desc;
+
+/* Fill a descriptor with tcnn's geometry rule.  Replaces the `encoding_config` dict handed to
+ * tcnn.Encoding / tcnn.NetworkWithInputEncoding (samnerf/sam_field.py:99-109, nerfacto_field.py:160-167,
+ * density_fields.py:73-81). */
+int snrf_grid_desc_init(snrf_grid_desc* d, int n_levels, int n_features, int log2_hashmap_size, int base_resolution,
+                        float per_level_scale);
+
+/* ---- lifetime ------------------------------------------------------------------------------------ */
+int snrf_ctx_create(int device, snrf_ctx** out);
+void snrf_ctx_destroy(snrf_ctx* ctx);
+const char* snrf_last_error(snrf_ctx* ctx); /* valid until the next call on ctx; ctx may be NULL */
+/* tensor-core engine for the 192->256->{256,192} feature MLP and the conv head:
+ * 1 = tcgen05.mma + TMEM (default), 0 = mma.sync (the recompiled-legacy comparison path). */
+int snrf_set_engine(snrf_ctx* ctx, int engine);
+/* eval-mode PDF sample positions u[33] = linspace(0, 1-1/33, 33) + 1/66 (ray_samplers.py:325-327).  The
+ * library computes the same table itself; a host may override it so that both sides share the bits. */
+int snrf_set_pdf_u(snrf_ctx* ctx, const float* u_host, int n);
+
+/* ---- parameters: flat fp32 tensors in tcnn order, host OR device pointers --------------------------
+ * Each call converts to fp16 and packs into the kernels' layouts once (replaces tcnn's `params` tensors:
+ * network weights first, then the grid).  Re-upload after every optimiser step if training continues. */
+/* proposal_networks.0.mlp_base.params : MLP 16->16->16 then 5x2 grid (density_fields.py:50-100) */
+int snrf_upload_proposal(snrf_ctx* ctx, const float* params, int64_t n, const snrf_grid_desc* grid, void* stream);
+/* field.mlp_base.params : MLP 32->64->16 then 16x2 grid (nerfacto_field.py:157-175) */
+int snrf_upload_field_base(snrf_ctx* ctx, const float* params, int64_t n, const snrf_grid_desc* grid, void* stream);
+/* field.mlp_head.params : MLP 32->64->64->16 (nerfacto_field.py:228-240) */
+int snrf_upload_field_head(snrf_ctx* ctx, const float* params, int64_t n, void* stream);
+/* sam_field.clip_encs.{idx}.params (which=0) / sam_field.clipseg_encs.{idx}.params (which=1) */
+int snrf_upload_feature_grid(snrf_ctx* ctx, int which, int idx, const float* params, int64_t n,
+                             const snrf_grid_desc* grid, void* stream);
+/* sam_field.sam_net.params (which=0, n_out=256) / sam_field.clipseg_net.params (which=1, n_out=192) */
+int snrf_upload_feature_net(snrf_ctx* ctx, int which, const float* params, int64_t n, int n_out, void* stream);
+/* conv_head.{0,2}.{weight,bias} : two Conv2d(256,256,3,pad 1) (sam_model.py:202-208) */
+int snrf_upload_conv_head(snrf_ctx* ctx, const float* w0, const float* b0, const float* w2, const float* b2,
+                          void* stream);
+
+/* ---- the hot path -------------------------------------------------------------------------------- */
+#define SNRF_WANT_SAM 1u     /* also render the 256-d SAM feature (sam_model.py:243-265)            */
+#define SNRF_WANT_CLIPSEG 2u /* also render the 192-d ClipSeg feature (sam_model.py:272-277)         */
+#define SNRF_PATCH 4u        /* push p x p ray patches through the conv head (sam_model.py:260-265)   */
+#define SNRF_BG_LAST_SAMPLE 0
+#define SNRF_BG_FIXED 1
+
+typedef struct snrf_render_opts {
+  float near_plane;   /* used when `nears` is NULL (eval: 0, scene_colliders.py:185) */
+  float far_plane;    /* used when `fars` is NULL (1000, nerfacto.py:73)             */
+  float hist_padding; /* PDFSampler histogram_padding (0.01)                         */
+  int32_t bg_mode;    /* SNRF_BG_*                                                   */
+  float bg[3];
+  int32_t k_sam;      /* num_sam_samples (16)                                        */
+  float sharpen;      /* sharpening_temperature (10)                                 */
+  int32_t patch_size; /* p for SNRF_PATCH (4)                                        */
+} snrf_render_opts;
+
+/* optional per-stage outputs (NULL = skip); back the component shims and the staged parity tests */
+typedef struct snrf_debug_out {
+  float* prop_weights; /* [N,64]   proposal weights                      */
+  float* edges;        /* [N,33]   nerf bin edges (euclidean t)          */
+  float* weights;      /* [N,32]   nerf weights                          */
+  float* density;      /* [N,32]   nerf densities                        */
+  float* rgb_samples;  /* [N,32,3] per-sample colour                     */
+  float* sam_t;        /* [N,k]    2 x midpoint t of the picked samples  */
+  float* sam_w;        /* [N,k]    sharpened renormalised weights        */
+  void* sam_feat;      /* [N,k,192] fp16 encoder output at those samples */
+} snrf_debug_out;
+
+/* SAMModel.forward / get_outputs for one chunk of rays in eval mode (samnerf/sam_model.py:226-314).
+ * nears/fars: NULL or [N].  rgb[N,3] depth[N] are always written; acc[N], prop_depth[N] may be NULL ("fast");
+ * sam: [N,256] or [N/p^2,256] with SNRF_PATCH; clipseg: [N,192]; dbg may be NULL. */
+int snrf_render(snrf_ctx* ctx, const float* origins, const float* dirs, const float* nears, const float* fars,
+                int64_t n_rays, uint32_t flags, const snrf_render_opts* opts, float* rgb, float* depth, float* acc,
+                float* prop_depth, float* sam, float* clipseg, const snrf_debug_out* dbg, void* stream);
+
+/* ProposalNetworkSampler.generate_ray_samples (ray_samplers.py:558-599): proposal weights [N,64], nerf bin
+ * edges [N,33] and optionally the proposal median depth [N]. */
+int snrf_sample(snrf_ctx* ctx, const float* origins, const float* dirs, const float* nears, const float* fars,
+                int64_t n_rays, const snrf_render_opts* opts, float* prop_weights, float* edges, float* prop_depth,
+                void* stream);
+
+/* conv head on patch-major feature rows: feat_in[P*p*p,256] -> out[P,256] (sam_model.py:260-265) */
+int snrf_patch_aggregate(snrf_ctx* ctx, const float* feat_in, int64_t n_patches, int p, float* out, void* stream);
+
+/* ---- component-level entry points (back Field.density_fn / SAMField.get_outputs / renderers) ------- */
+/* which: 0 = proposal field (density_fields.py:102-125), 1 = nerfacto field (nerfacto_field.py:242-266);
+ * geo_f16: [n,15] fp16 or NULL (nerfacto only). */
+int snrf_query_density(snrf_ctx* ctx, int which, const float* xyz, int64_t n, float* density, void* geo_f16,
+                       void* stream);
+/* nerfacto colour head (nerfacto_field.py:268-351): dirs[n,3], geo_f16[n,15] -> rgb[n,3] */
+int snrf_query_rgb(snrf_ctx* ctx, const float* dirs, const void* geo_f16, int64_t n, float* rgb, void* stream);
+/* SAMField.get_outputs per sample (sam_field.py:112-140): which 0 = sam, 1 = clipseg;
+ * hashgrid_f16: [n,192] fp16 or NULL; out: [n,n_out] fp32 */
+int snrf_query_features(snrf_ctx* ctx, int which, const float* xyz, int64_t n, void* hashgrid_f16, float* out,
+                        void* stream);
+/* ray-wise renderer ops: 0 get_weights(a=deltas,b=densities)->[N,S] (rays.py:141-163); 1 accumulation(a=w)->[N]
+ * (renderers.py:197-223); 2 median depth(a=w,b=starts,c=ends)->[N] (renderers.py:260-270); 3 rgb(a=rgb[N,S,3],
+ * b=w)->[N,3] (renderers.py:69-140); 4 mean(a=embeds[N,S,C],b=w)->[N,C] (sam_model.py:126-137) */
+int snrf_ray_op(snrf_ctx* ctx, int mode, const float* a, const float* b, const float* c, float* out, int64_t n, int S,
+                int C, int bg_mode, const float* bg_host, void* stream);
+
+/* number of kernels this library has launched on ctx since creation (bench.py's gpu_launches) */
+int64_t snrf_launch_count(snrf_ctx* ctx);
+/* Bracket the three hot kernels of snrf_render with CUDA events on the launching stream (bench.py's roofline). */
+int snrf_set_timing(snrf_ctx* ctx, int enable);
+/* Synchronise on the recorded events; ms_out[3] / count_out[3] = accumulated duration and launches of
+ * {0: per-ray march, 1: feature gather + first MLP layer, 2: tap GEMM} since the previous call. */
+int snrf_kernel_times(snrf_ctx* ctx, double* ms_out, int64_t* count_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SNRF_H_ */

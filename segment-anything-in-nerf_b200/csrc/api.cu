@@ -1,0 +1,760 @@
+// extern "C" entry points of libsnrf (see include/snrf.h): context, parameter packing, the render call and the
+// component-level queries.  Host code only; every kernel lives in march.cu / sam.cu / gemm.cu / query.cu.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/snrf.h"
+#include "kernels.cuh"
+
+using namespace snrf;
+
+namespace {
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  cudaError_t ensure(size_t need) {
+    if (need <= bytes) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+    cudaError_t e = cudaMalloc(&p, need);
+    if (e == cudaSuccess) bytes = need;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+  }
+  template <typename T>
+  T* as() const {
+    return reinterpret_cast<T*>(p);
+  }
+};
+
+struct FeatureNet {
+  DevBuf table[2];
+  GridDev grid[2];
+  bool have_grid[2] = {false, false};
+  DevBuf w1_core, w2_core;  // tensor-core layouts
+  DevBuf w1_rm, w2_rm;      // row-major fp16 (component queries)
+  int n_out = 0;
+  bool have_net = false;
+};
+
+}  // namespace
+
+struct snrf_ctx {
+  int device = 0;
+  int sm_count = 148;
+  int engine = 1;
+  std::string err;
+  int64_t launches = 0;
+  // proposal field
+  DevBuf prop_table, prop_w1f, prop_w2f, prop_w1_rm, prop_w2_rm;
+  GridDev prop_grid;
+  bool have_prop = false;
+  // nerfacto field
+  DevBuf field_table, base_w1_rm, base_w2_rm, head_w1_rm, head_w2_rm, head_w3_rm, wfrag, head_perm;
+  GridDev field_grid;
+  bool have_base = false, have_head = false;
+  // feature nets: 0 = sam, 1 = clipseg
+  FeatureNet feat[2];
+  // conv head
+  DevBuf conv_w[2], conv_b[2];
+  bool have_conv = false;
+  // per-kernel CUDA-event timing (bench.py's roofline): 0 march, 1 feature gather+MLP1, 2 tap GEMM
+  bool timing = false;
+  std::vector<cudaEvent_t> ev_pool;
+  std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> ev_used;
+  double k_ms[3] = {0, 0, 0};
+  int64_t k_count[3] = {0, 0, 0};
+  // misc
+  DevBuf pdf_u;
+  DevBuf sam_t, sam_w, hbar, feat_f16, hid_f16, q_feat, q_h1, q_h2, q_sel, q_x;
+};
+
+namespace {
+
+int fail(snrf_ctx* ctx, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (ctx) ctx->err = buf;
+  return code;
+}
+std::string g_null_err = "null context";
+
+#define CK(expr)                                                                                        \
+  do {                                                                                                  \
+    cudaError_t e__ = (expr);                                                                           \
+    if (e__ != cudaSuccess) return fail(ctx, SNRF_E_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e__)); \
+  } while (0)
+#define LAUNCH(expr) \
+  do {               \
+    CK(expr);        \
+    ctx->launches++; \
+  } while (0)
+
+cudaEvent_t get_event(snrf_ctx* ctx) {
+  if (!ctx->ev_pool.empty()) {
+    cudaEvent_t e = ctx->ev_pool.back();
+    ctx->ev_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+// LAUNCH, bracketed by events on the launching stream when timing is enabled
+#define TIMED_LAUNCH(kid, s, expr)                                   \
+  do {                                                               \
+    cudaEvent_t e0__ = nullptr, e1__ = nullptr;                      \
+    if (ctx->timing) {                                               \
+      e0__ = get_event(ctx);                                         \
+      e1__ = get_event(ctx);                                         \
+      cudaEventRecord(e0__, s);                                      \
+    }                                                                \
+    LAUNCH(expr);                                                    \
+    if (ctx->timing) {                                               \
+      cudaEventRecord(e1__, s);                                      \
+      ctx->ev_used.push_back({kid, {e0__, e1__}});                   \
+    }                                                                \
+  } while (0)
+
+GridDev to_dev(const snrf_grid_desc* d, const __half* table) {
+  GridDev g;
+  memset(&g, 0, sizeof(g));
+  g.table = table;
+  g.n_levels = d->n_levels;
+  g.n_features = d->n_features;
+  for (int l = 0; l < d->n_levels; ++l) {
+    g.lv[l].scale = d->lv[l].scale;
+    g.lv[l].res = d->lv[l].res;
+    g.lv[l].size = d->lv[l].size;
+    g.lv[l].offset = d->lv[l].offset;
+    g.lv[l].hashed = d->lv[l].hashed;
+  }
+  return g;
+}
+int64_t grid_entries(const snrf_grid_desc* d) {
+  return static_cast<int64_t>(d->lv[d->n_levels - 1].offset) + d->lv[d->n_levels - 1].size;
+}
+bool grid_ok(const snrf_grid_desc* d, int levels, int feats) {
+  if (!d || d->n_levels != levels || d->n_features != feats) return false;
+  for (int l = 0; l < levels; ++l)
+    if (d->lv[l].size == 0 || d->lv[l].res < 2) return false;
+  return true;
+}
+
+// stage `n` floats (host or device source) in a temporary device buffer
+int stage(snrf_ctx* ctx, const float* src, int64_t n, DevBuf& tmp, cudaStream_t s) {
+  CK(tmp.ensure(static_cast<size_t>(n) * sizeof(float)));
+  CK(cudaMemcpyAsync(tmp.p, src, static_cast<size_t>(n) * sizeof(float), cudaMemcpyDefault, s));
+  return SNRF_OK;
+}
+
+void default_pdf_u(float* u, int n_bins) {
+  // torch.linspace(0, 1 - 1/n_bins, n_bins) (float32, symmetric fill) + 1/(2 n_bins)   ray_samplers.py:325-327
+  const float end = static_cast<float>(1.0 - (1.0 / n_bins));
+  const float step = (end - 0.f) / static_cast<float>(n_bins - 1);
+  const int half = n_bins / 2;
+  const float off = static_cast<float>(1.0 / (2 * n_bins));
+  for (int i = 0; i < n_bins; ++i) {
+    const float v = i < half ? 0.f + step * static_cast<float>(i) : end - step * static_cast<float>(n_bins - i - 1);
+    u[i] = v + off;
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int snrf_grid_desc_init(snrf_grid_desc* d, int n_levels, int n_features, int log2_hashmap_size, int base_resolution,
+                        float per_level_scale) {
+  if (!d || n_levels < 1 || n_levels > SNRF_MAX_LEVELS) return SNRF_E_INVALID;
+  memset(d, 0, sizeof(*d));
+  d->n_levels = n_levels;
+  d->n_features = n_features;
+  const float log2_pls = log2f(per_level_scale);
+  uint32_t offset = 0;
+  for (int l = 0; l < n_levels; ++l) {
+    const float scale = exp2f(static_cast<float>(l) * log2_pls) * static_cast<float>(base_resolution) - 1.0f;
+    const uint32_t res = static_cast<uint32_t>(ceilf(scale)) + 1u;
+    const uint64_t dense = static_cast<uint64_t>(res) * res * res;
+    uint64_t size = (dense + 7) / 8 * 8;
+    const uint64_t cap = 1ull << log2_hashmap_size;
+    if (size > cap) size = cap;
+    d->lv[l].scale = scale;
+    d->lv[l].res = res;
+    d->lv[l].size = static_cast<uint32_t>(size);
+    d->lv[l].offset = offset;
+    d->lv[l].hashed = dense > size ? 1u : 0u;
+    offset += static_cast<uint32_t>(size);
+  }
+  return SNRF_OK;
+}
+
+int snrf_ctx_create(int device, snrf_ctx** out) {
+  if (!out) return SNRF_E_INVALID;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return SNRF_E_CUDA;
+  if (cudaSetDevice(device) != cudaSuccess) return SNRF_E_CUDA;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return SNRF_E_CUDA;
+  snrf_ctx* ctx = new snrf_ctx();
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  if (prop.major != 10) {
+    // this library is compiled for sm_100a only; refuse loudly instead of failing at the first launch
+    fprintf(stderr, "libsnrf: device %d is sm_%d%d, built for sm_100a\n", device, prop.major, prop.minor);
+    delete ctx;
+    return SNRF_E_INVALID;
+  }
+  float u[33];
+  default_pdf_u(u, 33);
+  if (ctx->pdf_u.ensure(sizeof(u)) != cudaSuccess ||
+      cudaMemcpy(ctx->pdf_u.p, u, sizeof(u), cudaMemcpyHostToDevice) != cudaSuccess) {
+    delete ctx;
+    return SNRF_E_CUDA;
+  }
+  *out = ctx;
+  return SNRF_OK;
+}
+
+void snrf_ctx_destroy(snrf_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  DevBuf* bufs[] = {&ctx->prop_table, &ctx->prop_w1f,   &ctx->prop_w2f,   &ctx->prop_w1_rm, &ctx->prop_w2_rm,
+                    &ctx->field_table, &ctx->base_w1_rm, &ctx->base_w2_rm, &ctx->head_w1_rm, &ctx->head_w2_rm,
+                    &ctx->head_w3_rm, &ctx->wfrag,      &ctx->head_perm,  &ctx->pdf_u,      &ctx->sam_t,
+                    &ctx->sam_w,      &ctx->hbar,       &ctx->feat_f16,   &ctx->hid_f16,    &ctx->q_feat,
+                    &ctx->q_h1,       &ctx->q_h2,       &ctx->q_sel,      &ctx->q_x,        &ctx->conv_w[0],
+                    &ctx->conv_w[1],  &ctx->conv_b[0],  &ctx->conv_b[1]};
+  for (DevBuf* b : bufs) b->release();
+  for (auto& u : ctx->ev_used) {
+    cudaEventDestroy(u.second.first);
+    cudaEventDestroy(u.second.second);
+  }
+  for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
+  for (int w = 0; w < 2; ++w) {
+    FeatureNet& f = ctx->feat[w];
+    f.table[0].release(); f.table[1].release();
+    f.w1_core.release(); f.w2_core.release(); f.w1_rm.release(); f.w2_rm.release();
+  }
+  delete ctx;
+}
+
+const char* snrf_last_error(snrf_ctx* ctx) { return ctx ? ctx->err.c_str() : g_null_err.c_str(); }
+
+int snrf_set_engine(snrf_ctx* ctx, int engine) {
+  if (!ctx || (engine != 0 && engine != 1)) return fail(ctx, SNRF_E_INVALID, "engine must be 0 (mma.sync) or 1 (tcgen05)");
+  ctx->engine = engine;
+  return SNRF_OK;
+}
+
+int snrf_set_pdf_u(snrf_ctx* ctx, const float* u_host, int n) {
+  if (!ctx || !u_host || n != 33) return fail(ctx, SNRF_E_INVALID, "pdf_u must have 33 entries");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaMemcpy(ctx->pdf_u.p, u_host, 33 * sizeof(float), cudaMemcpyHostToDevice));
+  return SNRF_OK;
+}
+
+int64_t snrf_launch_count(snrf_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int snrf_set_timing(snrf_ctx* ctx, int enable) {
+  if (!ctx) return SNRF_E_INVALID;
+  ctx->timing = enable != 0;
+  return SNRF_OK;
+}
+
+int snrf_kernel_times(snrf_ctx* ctx, double* ms_out, int64_t* count_out) {
+  if (!ctx || !ms_out || !count_out) return fail(ctx, SNRF_E_INVALID, "null argument");
+  CK(cudaSetDevice(ctx->device));
+  for (auto& u : ctx->ev_used) {
+    CK(cudaEventSynchronize(u.second.second));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, u.second.first, u.second.second));
+    ctx->k_ms[u.first] += ms;
+    ctx->k_count[u.first] += 1;
+    ctx->ev_pool.push_back(u.second.first);
+    ctx->ev_pool.push_back(u.second.second);
+  }
+  ctx->ev_used.clear();
+  for (int k = 0; k < 3; ++k) {
+    ms_out[k] = ctx->k_ms[k];
+    count_out[k] = ctx->k_count[k];
+    ctx->k_ms[k] = 0;
+    ctx->k_count[k] = 0;
+  }
+  return SNRF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// uploads
+// ---------------------------------------------------------------------------------------------------
+int snrf_upload_proposal(snrf_ctx* ctx, const float* params, int64_t n, const snrf_grid_desc* grid, void* stream) {
+  if (!ctx || !params) return fail(ctx, SNRF_E_INVALID, "null argument");
+  if (!grid_ok(grid, 5, 2)) return fail(ctx, SNRF_E_INVALID, "proposal grid must be 5 levels x 2 features");
+  const int64_t n_net = 16 * 16 + 16 * 16, n_grid = grid_entries(grid) * 2;
+  if (n != n_net + n_grid) return fail(ctx, SNRF_E_INVALID, "proposal params: got %lld, expected %lld", (long long)n, (long long)(n_net + n_grid));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CK(cudaSetDevice(ctx->device));
+  DevBuf tmp;
+  int rc = stage(ctx, params, n, tmp, s);
+  if (rc) return rc;
+  const float* src = tmp.as<float>();
+  CK(ctx->prop_table.ensure(n_grid * 2));
+  CK(ctx->prop_w1f.ensure(16 * 17 * 4));
+  CK(ctx->prop_w2f.ensure(16 * 4));
+  CK(ctx->prop_w1_rm.ensure(256 * 2));
+  CK(ctx->prop_w2_rm.ensure(256 * 2));
+  CK(cudaMemsetAsync(ctx->prop_w1f.p, 0, 16 * 17 * 4, s));
+  LAUNCH(launch_f32_to_f16(src + n_net, ctx->prop_table.as<__half>(), n_grid, s));
+  LAUNCH(launch_pack_prop(src, 16, src + 256, ctx->prop_w1f.as<float>(), ctx->prop_w2f.as<float>(), s));
+  LAUNCH(launch_f32_to_f16(src, ctx->prop_w1_rm.as<__half>(), 256, s));
+  LAUNCH(launch_f32_to_f16(src + 256, ctx->prop_w2_rm.as<__half>(), 256, s));
+  CK(cudaStreamSynchronize(s));
+  tmp.release();
+  ctx->prop_grid = to_dev(grid, ctx->prop_table.as<__half>());
+  ctx->have_prop = true;
+  return SNRF_OK;
+}
+
+int snrf_upload_field_base(snrf_ctx* ctx, const float* params, int64_t n, const snrf_grid_desc* grid, void* stream) {
+  if (!ctx || !params) return fail(ctx, SNRF_E_INVALID, "null argument");
+  if (!grid_ok(grid, 16, 2)) return fail(ctx, SNRF_E_INVALID, "field grid must be 16 levels x 2 features");
+  const int64_t n_net = 64 * 32 + 16 * 64, n_grid = grid_entries(grid) * 2;
+  if (n != n_net + n_grid) return fail(ctx, SNRF_E_INVALID, "field base params: got %lld, expected %lld", (long long)n, (long long)(n_net + n_grid));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CK(cudaSetDevice(ctx->device));
+  DevBuf tmp;
+  int rc = stage(ctx, params, n, tmp, s);
+  if (rc) return rc;
+  const float* src = tmp.as<float>();
+  CK(ctx->field_table.ensure(n_grid * 2));
+  CK(ctx->base_w1_rm.ensure(64 * 32 * 2));
+  CK(ctx->base_w2_rm.ensure(16 * 64 * 2));
+  CK(ctx->wfrag.ensure(kMarchFragTiles * 256));
+  LAUNCH(launch_f32_to_f16(src + n_net, ctx->field_table.as<__half>(), n_grid, s));
+  LAUNCH(launch_f32_to_f16(src, ctx->base_w1_rm.as<__half>(), 64 * 32, s));
+  LAUNCH(launch_f32_to_f16(src + 64 * 32, ctx->base_w2_rm.as<__half>(), 16 * 64, s));
+  uint2* wf = ctx->wfrag.as<uint2>();
+  LAUNCH(launch_pack_frag(src, 32, nullptr, wf + kFragBase1 * 32, 8, 2, s));
+  LAUNCH(launch_pack_frag(src + 64 * 32, 64, nullptr, wf + kFragBase2 * 32, 2, 4, s));
+  CK(cudaStreamSynchronize(s));
+  tmp.release();
+  ctx->field_grid = to_dev(grid, ctx->field_table.as<__half>());
+  ctx->have_base = true;
+  return SNRF_OK;
+}
+
+int snrf_upload_field_head(snrf_ctx* ctx, const float* params, int64_t n, void* stream) {
+  if (!ctx || !params) return fail(ctx, SNRF_E_INVALID, "null argument");
+  const int64_t expect = 64 * 32 + 64 * 64 + 16 * 64;
+  if (n != expect) return fail(ctx, SNRF_E_INVALID, "field head params: got %lld, expected %lld", (long long)n, (long long)expect);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CK(cudaSetDevice(ctx->device));
+  DevBuf tmp;
+  int rc = stage(ctx, params, n, tmp, s);
+  if (rc) return rc;
+  const float* src = tmp.as<float>();
+  CK(ctx->head_w1_rm.ensure(64 * 32 * 2));
+  CK(ctx->head_w2_rm.ensure(64 * 64 * 2));
+  CK(ctx->head_w3_rm.ensure(16 * 64 * 2));
+  CK(ctx->wfrag.ensure(kMarchFragTiles * 256));
+  CK(ctx->head_perm.ensure(32 * sizeof(int)));
+  // kernel-side input order [pad, geo0..14, SH0..15]  <-  tcnn order [SH0..15, geo0..14, pad]
+  int perm[32];
+  perm[0] = 31;
+  for (int c = 1; c < 16; ++c) perm[c] = 15 + c;
+  for (int c = 0; c < 16; ++c) perm[16 + c] = c;
+  CK(cudaMemcpyAsync(ctx->head_perm.p, perm, sizeof(perm), cudaMemcpyHostToDevice, s));
+  LAUNCH(launch_f32_to_f16(src, ctx->head_w1_rm.as<__half>(), 64 * 32, s));
+  LAUNCH(launch_f32_to_f16(src + 64 * 32, ctx->head_w2_rm.as<__half>(), 64 * 64, s));
+  LAUNCH(launch_f32_to_f16(src + 64 * 32 + 64 * 64, ctx->head_w3_rm.as<__half>(), 16 * 64, s));
+  uint2* wf = ctx->wfrag.as<uint2>();
+  LAUNCH(launch_pack_frag(src, 32, ctx->head_perm.as<int>(), wf + kFragHead1 * 32, 8, 2, s));
+  LAUNCH(launch_pack_frag(src + 64 * 32, 64, nullptr, wf + kFragHead2 * 32, 8, 4, s));
+  LAUNCH(launch_pack_frag(src + 64 * 32 + 64 * 64, 64, nullptr, wf + kFragHead3 * 32, 1, 4, s));
+  CK(cudaStreamSynchronize(s));
+  tmp.release();
+  ctx->have_head = true;
+  return SNRF_OK;
+}
+
+int snrf_upload_feature_grid(snrf_ctx* ctx, int which, int idx, const float* params, int64_t n,
+                             const snrf_grid_desc* grid, void* stream) {
+  if (!ctx || !params || which < 0 || which > 1 || idx < 0 || idx > 1) return fail(ctx, SNRF_E_INVALID, "bad argument");
+  if (!grid_ok(grid, 12, 8)) return fail(ctx, SNRF_E_INVALID, "feature grid must be 12 levels x 8 features");
+  const int64_t n_grid = grid_entries(grid) * 8;
+  if (n != n_grid) return fail(ctx, SNRF_E_INVALID, "feature grid params: got %lld, expected %lld", (long long)n, (long long)n_grid);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CK(cudaSetDevice(ctx->device));
+  DevBuf tmp;
+  int rc = stage(ctx, params, n, tmp, s);
+  if (rc) return rc;
+  FeatureNet& f = ctx->feat[which];
+  CK(f.table[idx].ensure(n_grid * 2));
+  LAUNCH(launch_f32_to_f16(tmp.as<float>(), f.table[idx].as<__half>(), n_grid, s));
+  CK(cudaStreamSynchronize(s));
+  tmp.release();
+  f.grid[idx] = to_dev(grid, f.table[idx].as<__half>());
+  f.have_grid[idx] = true;
+  return SNRF_OK;
+}
+
+int snrf_upload_feature_net(snrf_ctx* ctx, int which, const float* params, int64_t n, int n_out, void* stream) {
+  if (!ctx || !params || which < 0 || which > 1) return fail(ctx, SNRF_E_INVALID, "bad argument");
+  if (n_out != 256 && n_out != 192) return fail(ctx, SNRF_E_INVALID, "feature net output width must be 256 or 192");
+  const int64_t expect = 256 * 192 + static_cast<int64_t>(n_out) * 256;
+  if (n != expect) return fail(ctx, SNRF_E_INVALID, "feature net params: got %lld, expected %lld", (long long)n, (long long)expect);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CK(cudaSetDevice(ctx->device));
+  DevBuf tmp;
+  int rc = stage(ctx, params, n, tmp, s);
+  if (rc) return rc;
+  const float* src = tmp.as<float>();
+  FeatureNet& f = ctx->feat[which];
+  CK(f.w1_core.ensure(256 * 192 * 2));
+  CK(f.w2_core.ensure(static_cast<size_t>(n_out) * 256 * 2));
+  CK(f.w1_rm.ensure(256 * 192 * 2));
+  CK(f.w2_rm.ensure(static_cast<size_t>(n_out) * 256 * 2));
+  LAUNCH(launch_pack_core(src, f.w1_core.as<__half>(), 256, 192, s));
+  LAUNCH(launch_pack_core(src + 256 * 192, f.w2_core.as<__half>(), n_out, 256, s));
+  LAUNCH(launch_f32_to_f16(src, f.w1_rm.as<__half>(), 256 * 192, s));
+  LAUNCH(launch_f32_to_f16(src + 256 * 192, f.w2_rm.as<__half>(), static_cast<int64_t>(n_out) * 256, s));
+  CK(cudaStreamSynchronize(s));
+  tmp.release();
+  f.n_out = n_out;
+  f.have_net = true;
+  return SNRF_OK;
+}
+
+int snrf_upload_conv_head(snrf_ctx* ctx, const float* w0, const float* b0, const float* w2, const float* b2,
+                          void* stream) {
+  if (!ctx || !w0 || !b0 || !w2 || !b2) return fail(ctx, SNRF_E_INVALID, "null argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CK(cudaSetDevice(ctx->device));
+  // Conv2d weight [out=256][in=256][3][3] -> 9 per-tap [out x in] matrices, each in core-matrix layout.
+  // The tap split is done on the host side of the staging copy to keep the packing kernel generic.
+  const float* ws[2] = {w0, w2};
+  const float* bs[2] = {b0, b2};
+  const int64_t n_w = 256LL * 256 * 9;
+  std::vector<float> host(n_w), taps(n_w);
+  for (int c = 0; c < 2; ++c) {
+    CK(cudaMemcpyAsync(host.data(), ws[c], n_w * sizeof(float), cudaMemcpyDefault, s));
+    CK(cudaStreamSynchronize(s));
+    for (int o = 0; o < 256; ++o)
+      for (int i = 0; i < 256; ++i)
+        for (int t = 0; t < 9; ++t) taps[(static_cast<size_t>(t) * 256 + o) * 256 + i] = host[(static_cast<size_t>(o) * 256 + i) * 9 + t];
+    DevBuf tmp;
+    int rc = stage(ctx, taps.data(), n_w, tmp, s);
+    if (rc) return rc;
+    CK(ctx->conv_w[c].ensure(n_w * 2));
+    for (int t = 0; t < 9; ++t)
+      LAUNCH(launch_pack_core(tmp.as<float>() + static_cast<size_t>(t) * 65536,
+                              ctx->conv_w[c].as<__half>() + static_cast<size_t>(t) * 65536, 256, 256, s));
+    CK(ctx->conv_b[c].ensure(256 * sizeof(float)));
+    CK(cudaMemcpyAsync(ctx->conv_b[c].p, bs[c], 256 * sizeof(float), cudaMemcpyDefault, s));
+    CK(cudaStreamSynchronize(s));
+    tmp.release();
+  }
+  ctx->have_conv = true;
+  return SNRF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// render
+// ---------------------------------------------------------------------------------------------------
+static int fill_march(snrf_ctx* ctx, MarchParams& M, const float* origins, const float* dirs, const float* nears,
+                      const float* fars, int64_t n, const snrf_render_opts* o) {
+  if (!ctx->have_prop) return fail(ctx, SNRF_E_STATE, "proposal parameters not uploaded");
+  memset(&M, 0, sizeof(M));
+  M.origins = origins;
+  M.dirs = dirs;
+  M.nears = nears;
+  M.fars = fars;
+  M.n_rays = n;
+  M.near_default = o->near_plane;
+  M.far_default = o->far_plane;
+  M.prop = ctx->prop_grid;
+  M.field = ctx->field_grid;
+  M.prop_w1 = ctx->prop_w1f.as<float>();
+  M.prop_w2 = ctx->prop_w2f.as<float>();
+  M.wfrag = ctx->wfrag.as<uint2>();
+  M.pdf_u = ctx->pdf_u.as<float>();
+  M.hist_padding = o->hist_padding;
+  M.bg_mode = o->bg_mode == SNRF_BG_FIXED ? kBgFixed : kBgLastSample;
+  M.bg[0] = o->bg[0];
+  M.bg[1] = o->bg[1];
+  M.bg[2] = o->bg[2];
+  M.k_sam = o->k_sam;
+  M.sharpen = o->sharpen;
+  return SNRF_OK;
+}
+
+int snrf_patch_aggregate(snrf_ctx* ctx, const float* feat_in, int64_t n_patches, int p, float* out, void* stream) {
+  if (!ctx || !feat_in || !out) return fail(ctx, SNRF_E_INVALID, "null argument");
+  if (p != 4) return fail(ctx, SNRF_E_INVALID, "patch_size %d unsupported (the conv head kernel is built for p = 4)", p);
+  if (!ctx->have_conv) return fail(ctx, SNRF_E_STATE, "conv head parameters not uploaded");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CK(cudaSetDevice(ctx->device));
+  const int64_t m = n_patches * 16;
+  if (m == 0) return SNRF_OK;
+  CK(ctx->feat_f16.ensure(m * 256 * 2));
+  CK(ctx->hid_f16.ensure(m * 256 * 2));
+  LAUNCH(launch_f32_to_f16(feat_in, ctx->feat_f16.as<__half>(), m * 256, s));
+  GemmParams G;
+  memset(&G, 0, sizeof(G));
+  G.a = ctx->feat_f16.as<__half>();
+  G.w = ctx->conv_w[0].as<__half>();
+  G.bias = ctx->conv_b[0].as<float>();
+  G.out_f16 = ctx->hid_f16.as<__half>();
+  G.m = m; G.n = 256; G.taps = 9; G.relu = 1; G.out_mode = 1;
+  LAUNCH(launch_tapgemm(G, ctx->engine == 1, ctx->sm_count, s));
+  G.a = ctx->hid_f16.as<__half>();
+  G.w = ctx->conv_w[1].as<__half>();
+  G.bias = ctx->conv_b[1].as<float>();
+  G.out_f16 = nullptr;
+  G.out_f32 = out;
+  G.relu = 0; G.out_mode = 2;
+  LAUNCH(launch_tapgemm(G, ctx->engine == 1, ctx->sm_count, s));
+  return SNRF_OK;
+}
+
+int snrf_render(snrf_ctx* ctx, const float* origins, const float* dirs, const float* nears, const float* fars,
+                int64_t n_rays, uint32_t flags, const snrf_render_opts* opts, float* rgb, float* depth, float* acc,
+                float* prop_depth, float* sam, float* clipseg, const snrf_debug_out* dbg, void* stream) {
+  if (!ctx) return SNRF_E_INVALID;
+  if (!origins || !dirs || !opts || !rgb || !depth) return fail(ctx, SNRF_E_INVALID, "null argument");
+  if (n_rays < 0) return fail(ctx, SNRF_E_INVALID, "negative ray count");
+  if (n_rays == 0) return SNRF_OK;
+  if (!ctx->have_base || !ctx->have_head) return fail(ctx, SNRF_E_STATE, "nerfacto field parameters not uploaded");
+  const bool want_sam = (flags & SNRF_WANT_SAM) != 0, want_clip = (flags & SNRF_WANT_CLIPSEG) != 0;
+  const bool patch = (flags & SNRF_PATCH) != 0;
+  if (want_sam && !sam) return fail(ctx, SNRF_E_INVALID, "SNRF_WANT_SAM without an output buffer");
+  if (want_clip && !clipseg) return fail(ctx, SNRF_E_INVALID, "SNRF_WANT_CLIPSEG without an output buffer");
+  if ((want_sam || want_clip) && opts->k_sam != 16)
+    return fail(ctx, SNRF_E_INVALID, "num_sam_samples %d unsupported (the feature kernel is built for k = 16)", opts->k_sam);
+  if (patch && (!want_sam || opts->patch_size != 4 || n_rays % 16 != 0))
+    return fail(ctx, SNRF_E_INVALID, "SNRF_PATCH needs SNRF_WANT_SAM, patch_size 4 and a ray count divisible by 16");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CK(cudaSetDevice(ctx->device));
+
+  MarchParams M;
+  int rc = fill_march(ctx, M, origins, dirs, nears, fars, n_rays, opts);
+  if (rc) return rc;
+  M.rgb = rgb;
+  M.depth = depth;
+  M.acc = acc;
+  M.prop_depth = prop_depth;
+  const bool feats = want_sam || want_clip;
+  if (feats || (dbg && dbg->sam_t)) {
+    CK(ctx->sam_t.ensure(n_rays * 16 * 4));
+    CK(ctx->sam_w.ensure(n_rays * 16 * 4));
+    M.sam_t = ctx->sam_t.as<float>();
+    M.sam_w = ctx->sam_w.as<float>();
+  }
+  if (dbg) {
+    M.dbg_w0 = dbg->prop_weights;
+    M.dbg_edges = dbg->edges;
+    M.dbg_weights = dbg->weights;
+    M.dbg_density = dbg->density;
+    M.dbg_rgb = dbg->rgb_samples;
+  }
+  TIMED_LAUNCH(0, s, launch_march(M, ctx->sm_count, s));
+  if (dbg && dbg->sam_t) {
+    CK(cudaMemcpyAsync(dbg->sam_t, M.sam_t, n_rays * 16 * 4, cudaMemcpyDeviceToDevice, s));
+    if (dbg->sam_w) CK(cudaMemcpyAsync(dbg->sam_w, M.sam_w, n_rays * 16 * 4, cudaMemcpyDeviceToDevice, s));
+  }
+  for (int which = 0; which < 2; ++which) {
+    if (!(which == 0 ? want_sam : want_clip)) continue;
+    FeatureNet& f = ctx->feat[which];
+    if (!f.have_grid[0] || !f.have_grid[1] || !f.have_net)
+      return fail(ctx, SNRF_E_STATE, "%s parameters not uploaded", which == 0 ? "sam_field" : "clipseg");
+    CK(ctx->hbar.ensure(n_rays * 256 * 2));
+    SamParams S;
+    memset(&S, 0, sizeof(S));
+    S.origins = origins;
+    S.dirs = dirs;
+    S.sam_t = M.sam_t;
+    S.sam_w = M.sam_w;
+    S.n_rays = n_rays;
+    S.enc[0] = f.grid[0];
+    S.enc[1] = f.grid[1];
+    S.w1 = f.w1_core.as<__half>();
+    S.hbar = ctx->hbar.as<__half>();
+    S.dbg_feat = (which == 0 && dbg) ? reinterpret_cast<__half*>(dbg->sam_feat) : nullptr;
+    TIMED_LAUNCH(1, s, launch_sam(S, ctx->engine == 1, ctx->sm_count, s));
+    GemmParams G;
+    memset(&G, 0, sizeof(G));
+    G.a = ctx->hbar.as<__half>();
+    G.w = f.w2_core.as<__half>();
+    G.m = n_rays;
+    G.n = f.n_out;
+    G.taps = 1;
+    const bool to_patch = which == 0 && patch;
+    if (to_patch) {
+      CK(ctx->feat_f16.ensure(n_rays * 256 * 2));
+      G.out_f16 = ctx->feat_f16.as<__half>();
+      G.out_mode = 1;
+    } else {
+      G.out_f32 = which == 0 ? sam : clipseg;
+      G.out_mode = 0;
+    }
+    TIMED_LAUNCH(2, s, launch_tapgemm(G, ctx->engine == 1, ctx->sm_count, s));
+    if (to_patch) {
+      if (!ctx->have_conv) return fail(ctx, SNRF_E_STATE, "conv head parameters not uploaded");
+      CK(ctx->hid_f16.ensure(n_rays * 256 * 2));
+      GemmParams C;
+      memset(&C, 0, sizeof(C));
+      C.a = ctx->feat_f16.as<__half>();
+      C.w = ctx->conv_w[0].as<__half>();
+      C.bias = ctx->conv_b[0].as<float>();
+      C.out_f16 = ctx->hid_f16.as<__half>();
+      C.m = n_rays; C.n = 256; C.taps = 9; C.relu = 1; C.out_mode = 1;
+      LAUNCH(launch_tapgemm(C, ctx->engine == 1, ctx->sm_count, s));
+      C.a = ctx->hid_f16.as<__half>();
+      C.w = ctx->conv_w[1].as<__half>();
+      C.bias = ctx->conv_b[1].as<float>();
+      C.out_f16 = nullptr;
+      C.out_f32 = sam;
+      C.relu = 0; C.out_mode = 2;
+      LAUNCH(launch_tapgemm(C, ctx->engine == 1, ctx->sm_count, s));
+    }
+  }
+  return SNRF_OK;
+}
+
+int snrf_sample(snrf_ctx* ctx, const float* origins, const float* dirs, const float* nears, const float* fars,
+                int64_t n_rays, const snrf_render_opts* opts, float* prop_weights, float* edges, float* prop_depth,
+                void* stream) {
+  if (!ctx) return SNRF_E_INVALID;
+  if (!origins || !dirs || !opts) return fail(ctx, SNRF_E_INVALID, "null argument");
+  if (n_rays <= 0) return n_rays == 0 ? SNRF_OK : fail(ctx, SNRF_E_INVALID, "negative ray count");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CK(cudaSetDevice(ctx->device));
+  MarchParams M;
+  int rc = fill_march(ctx, M, origins, dirs, nears, fars, n_rays, opts);
+  if (rc) return rc;
+  M.flags = kFlagSamplesOnly;
+  M.dbg_w0 = prop_weights;
+  M.dbg_edges = edges;
+  M.prop_depth = prop_depth;
+  LAUNCH(launch_march(M, ctx->sm_count, s));
+  return SNRF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// component-level queries
+// ---------------------------------------------------------------------------------------------------
+int snrf_query_density(snrf_ctx* ctx, int which, const float* xyz, int64_t n, float* density, void* geo_f16,
+                       void* stream) {
+  if (!ctx) return SNRF_E_INVALID;
+  if (!xyz || !density || which < 0 || which > 1) return fail(ctx, SNRF_E_INVALID, "bad argument");
+  if (n == 0) return SNRF_OK;
+  if (which == 0 ? !ctx->have_prop : !ctx->have_base) return fail(ctx, SNRF_E_STATE, "field parameters not uploaded");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CK(cudaSetDevice(ctx->device));
+  const int width = which == 0 ? 10 : 32, hidden = which == 0 ? 16 : 64, k_w = which == 0 ? 16 : 32;
+  CK(ctx->q_feat.ensure(n * width * 2));
+  CK(ctx->q_h1.ensure(n * hidden * 2));
+  CK(ctx->q_h2.ensure(n * 16 * 2));
+  CK(ctx->q_sel.ensure(n * 4));
+  QueryParams Q;
+  memset(&Q, 0, sizeof(Q));
+  Q.xyz = xyz;
+  Q.n = n;
+  Q.grid[0] = which == 0 ? ctx->prop_grid : ctx->field_grid;
+  Q.n_grids = 1;
+  Q.linf = 1;
+  Q.selector = 1;
+  Q.feat = ctx->q_feat.as<__half>();
+  Q.sel = ctx->q_sel.as<float>();
+  LAUNCH(launch_encode(Q, s));
+  const __half* w1 = which == 0 ? ctx->prop_w1_rm.as<__half>() : ctx->base_w1_rm.as<__half>();
+  const __half* w2 = which == 0 ? ctx->prop_w2_rm.as<__half>() : ctx->base_w2_rm.as<__half>();
+  LAUNCH(launch_dense(Q.feat, width, width, w1, k_w, 0.f, ctx->q_h1.as<__half>(), hidden, hidden, 1, n, s));
+  LAUNCH(launch_dense(ctx->q_h1.as<__half>(), hidden, hidden, w2, hidden, 0.f, ctx->q_h2.as<__half>(), 16, 16, 0, n, s));
+  LAUNCH(launch_density_finish(ctx->q_h2.as<__half>(), 16, Q.sel, density,
+                               which == 1 ? reinterpret_cast<__half*>(geo_f16) : nullptr, 15, n, s));
+  return SNRF_OK;
+}
+
+int snrf_query_rgb(snrf_ctx* ctx, const float* dirs, const void* geo_f16, int64_t n, float* rgb, void* stream) {
+  if (!ctx) return SNRF_E_INVALID;
+  if (!dirs || !geo_f16 || !rgb) return fail(ctx, SNRF_E_INVALID, "null argument");
+  if (n == 0) return SNRF_OK;
+  if (!ctx->have_head) return fail(ctx, SNRF_E_STATE, "field head parameters not uploaded");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CK(cudaSetDevice(ctx->device));
+  CK(ctx->q_x.ensure(n * 32 * 2));
+  CK(ctx->q_h1.ensure(n * 64 * 2));
+  CK(ctx->q_h2.ensure(n * 64 * 2));
+  CK(ctx->q_feat.ensure(n * 16 * 2));
+  LAUNCH(launch_head_input(dirs, reinterpret_cast<const __half*>(geo_f16), ctx->q_x.as<__half>(), n, s));
+  LAUNCH(launch_dense(ctx->q_x.as<__half>(), 32, 32, ctx->head_w1_rm.as<__half>(), 32, 1.f, ctx->q_h1.as<__half>(), 64, 64, 1, n, s));
+  LAUNCH(launch_dense(ctx->q_h1.as<__half>(), 64, 64, ctx->head_w2_rm.as<__half>(), 64, 0.f, ctx->q_h2.as<__half>(), 64, 64, 1, n, s));
+  LAUNCH(launch_dense(ctx->q_h2.as<__half>(), 64, 64, ctx->head_w3_rm.as<__half>(), 64, 0.f, ctx->q_feat.as<__half>(), 16, 16, 2, n, s));
+  LAUNCH(launch_half_to_float(ctx->q_feat.as<__half>(), 16, rgb, 3, 3, n, s));
+  return SNRF_OK;
+}
+
+int snrf_query_features(snrf_ctx* ctx, int which, const float* xyz, int64_t n, void* hashgrid_f16, float* out,
+                        void* stream) {
+  if (!ctx) return SNRF_E_INVALID;
+  if (!xyz || !out || which < 0 || which > 1) return fail(ctx, SNRF_E_INVALID, "bad argument");
+  if (n == 0) return SNRF_OK;
+  FeatureNet& f = ctx->feat[which];
+  if (!f.have_grid[0] || !f.have_grid[1] || !f.have_net) return fail(ctx, SNRF_E_STATE, "feature field parameters not uploaded");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CK(cudaSetDevice(ctx->device));
+  __half* feat = reinterpret_cast<__half*>(hashgrid_f16);
+  if (!feat) {
+    CK(ctx->q_feat.ensure(n * 192 * 2));
+    feat = ctx->q_feat.as<__half>();
+  }
+  CK(ctx->q_h1.ensure(n * 256 * 2));
+  CK(ctx->q_h2.ensure(n * 256 * 2));
+  QueryParams Q;
+  memset(&Q, 0, sizeof(Q));
+  Q.xyz = xyz;
+  Q.n = n;
+  Q.grid[0] = f.grid[0];
+  Q.grid[1] = f.grid[1];
+  Q.n_grids = 2;
+  Q.linf = 0;
+  Q.selector = 0;
+  Q.feat = feat;
+  LAUNCH(launch_encode(Q, s));
+  LAUNCH(launch_dense(feat, 192, 192, f.w1_rm.as<__half>(), 192, 0.f, ctx->q_h1.as<__half>(), 256, 256, 1, n, s));
+  LAUNCH(launch_dense(ctx->q_h1.as<__half>(), 256, 256, f.w2_rm.as<__half>(), 256, 0.f, ctx->q_h2.as<__half>(), f.n_out, f.n_out, 0, n, s));
+  LAUNCH(launch_half_to_float(ctx->q_h2.as<__half>(), f.n_out, out, f.n_out, f.n_out, n, s));
+  return SNRF_OK;
+}
+
+int snrf_ray_op(snrf_ctx* ctx, int mode, const float* a, const float* b, const float* c, float* out, int64_t n, int S,
+                int C, int bg_mode, const float* bg_host, void* stream) {
+  if (!ctx) return SNRF_E_INVALID;
+  if (mode < 0 || mode > 4 || !a || !out || S <= 0) return fail(ctx, SNRF_E_INVALID, "bad argument");
+  if ((mode == 0 || mode == 2 || mode == 3 || mode == 4) && !b) return fail(ctx, SNRF_E_INVALID, "missing operand b");
+  if (mode == 2 && !c) return fail(ctx, SNRF_E_INVALID, "missing operand c");
+  if (n == 0) return SNRF_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CK(cudaSetDevice(ctx->device));
+  LAUNCH(launch_ray_ops(mode, a, b, c, out, n, S, C, bg_mode == SNRF_BG_FIXED ? kBgFixed : kBgLastSample, bg_host, s));
+  return SNRF_OK;
+}
+
+}  // extern "C"

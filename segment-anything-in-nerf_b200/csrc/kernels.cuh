@@ -1,0 +1,109 @@
+// Kernel parameter blocks and launch entry points (internal to libsnrf).
+#pragma once
+#include "common.cuh"
+
+namespace snrf {
+
+// ---- kernel A: per-ray march -----------------------------------------------------------------
+// packed mma.sync B-fragment tiles (32 lanes x uint2 = 256 B each), in this order:
+constexpr int kFragBase1 = 0;    // base MLP  32 -> 64 : 8 n-tiles x 2 k-steps
+constexpr int kFragBase2 = 16;   // base MLP  64 -> 16 : 2 x 4
+constexpr int kFragHead1 = 24;   // head MLP  32 -> 64 : 8 x 2   (input columns permuted: [pad, geo(15), SH(16)])
+constexpr int kFragHead2 = 40;   // head MLP  64 -> 64 : 8 x 4
+constexpr int kFragHead3 = 72;   // head MLP  64 -> 8  : 1 x 4   (only rgb = outputs 0..2 are used)
+constexpr int kMarchFragTiles = 76;
+
+constexpr uint32_t kFlagSamplesOnly = 1u;  // stop after the PDF resample (backs ProposalNetworkSampler)
+constexpr int kBgLastSample = 0;           // RGBRenderer background "last_sample" (renderers.py:102-103)
+constexpr int kBgFixed = 1;                // fixed colour (black / white / background_color_override_context)
+
+struct MarchParams {
+  const float* origins;  // [N,3]
+  const float* dirs;     // [N,3]
+  const float* nears;    // [N] or null -> near_default
+  const float* fars;     // [N] or null -> far_default
+  int64_t n_rays;
+  float near_default, far_default;
+  GridDev prop;          // 5 levels x 2
+  GridDev field;         // 16 levels x 2
+  const float* prop_w1;  // [16][17] fp32 (fp16-representable): hidden x input, row stride 17
+  const float* prop_w2;  // [16] density row of the output layer
+  const uint2* wfrag;    // kMarchFragTiles x 32 fragment words
+  const float* pdf_u;    // [33] eval-mode PDF sample positions
+  float hist_padding;
+  int bg_mode;
+  float bg[3];
+  int k_sam;
+  float sharpen;
+  uint32_t flags;
+  float* rgb;         // [N,3]
+  float* depth;       // [N]
+  float* acc;         // [N] or null
+  float* prop_depth;  // [N] or null
+  float* sam_t;       // [N,k] 2 x midpoint of the picked samples, or null
+  float* sam_w;       // [N,k] sharpened, renormalised weights
+  float* dbg_w0;      // [N,64] proposal weights, or null
+  float* dbg_edges;   // [N,33] nerf bin edges, or null
+  float* dbg_weights; // [N,32]
+  float* dbg_density; // [N,32]
+  float* dbg_rgb;     // [N,32,3]
+};
+cudaError_t launch_march(const MarchParams& P, int sm_count, cudaStream_t stream);
+
+// ---- kernel B: feature-field gather + first MLP layer + weighted sample reduction ---------------
+struct SamParams {
+  const float* origins;
+  const float* dirs;
+  const float* sam_t;  // [N,16]
+  const float* sam_w;  // [N,16]
+  int64_t n_rays;
+  GridDev enc[2];      // 12 levels x 8 each
+  const __half* w1;    // [256 x 192] fp16 in core-matrix layout (98304 B)
+  __half* hbar;        // [N,256] fp16: sum_k w_k * fp16(relu(W1 x_k))
+  __half* dbg_feat;    // [N,16,192] encoder output, or null
+};
+cudaError_t launch_sam(const SamParams& P, bool tcgen05, int sm_count, cudaStream_t stream);
+
+// ---- kernel C/D: tap GEMM  out = act(sum_t A_t[M,256] x W_t[N,256]^T + bias) ----------------------
+struct GemmParams {
+  const __half* a;     // [M,256] fp16 rows
+  const __half* w;     // taps x [N x 256] fp16 in core-matrix layout
+  const float* bias;   // [N] or null
+  float* out_f32;      // out_mode 0: [M,N];  out_mode 2: [M/16,N] mean over each 16-row patch
+  __half* out_f16;     // out_mode 1: [M,N]
+  int64_t m;
+  int n;               // 256 or 192
+  int taps;            // 1 (plain GEMM) or 9 (3x3 conv over 4x4 patches of 16 consecutive rows)
+  int relu;
+  int out_mode;
+};
+cudaError_t launch_tapgemm(const GemmParams& P, bool tcgen05, int sm_count, cudaStream_t stream);
+
+// ---- stand-alone field queries (back Field.density_fn / SAMField.get_outputs) --------------------
+struct QueryParams {
+  const float* xyz;  // [N,3] world positions
+  int64_t n;
+  GridDev grid[2];
+  int n_grids;
+  int linf;          // contraction order
+  int selector;
+  __half* feat;      // [N, sum(L*F)] encoder output (fp16)
+  float* sel;        // [N] selector or null
+};
+cudaError_t launch_encode(const QueryParams& P, cudaStream_t stream);
+cudaError_t launch_dense(const __half* in, int ld_in, int k_in, const __half* w, int k_w, float pad_value, __half* out,
+                         int ld_out, int n_out, int act, int64_t n, cudaStream_t stream);
+cudaError_t launch_density_finish(const __half* h, int ld, const float* sel, float* density, __half* geo, int n_geo,
+                                  int64_t n, cudaStream_t stream);
+cudaError_t launch_head_input(const float* dirs, const __half* geo, __half* x, int64_t n, cudaStream_t stream);
+cudaError_t launch_half_to_float(const __half* in, int ld_in, float* out, int ld_out, int cols, int64_t n,
+                                 cudaStream_t stream);
+cudaError_t launch_ray_ops(int mode, const float* a, const float* b, const float* c, float* out, int64_t n, int S, int C,
+                           int bg_mode, const float* bg, cudaStream_t stream);
+cudaError_t launch_f32_to_f16(const float* in, __half* out, int64_t n, cudaStream_t stream);
+cudaError_t launch_pack_core(const float* w, __half* out, int rows, int cols, cudaStream_t stream);
+cudaError_t launch_pack_frag(const float* w, int k_w, const int* perm, uint2* out, int n_tiles, int k_steps,
+                             cudaStream_t stream);
+cudaError_t launch_pack_prop(const float* w1, int k_w, const float* w2, float* o1, float* o2, cudaStream_t stream);
+
+}  // namespace snrf

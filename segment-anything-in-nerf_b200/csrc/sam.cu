@@ -1,0 +1,258 @@
+// Kernel B - SAMField at the k picked samples of every ray: 24-level x 8-feature hash-grid gather (the
+// dominant HBM traffic of the whole path: 3072 B per sample), first MLP layer 192 -> 256 on the tensor cores,
+// ReLU, and the MeanRenderer's weighted sum over the ray's 16 samples, all in one launch.
+//
+// Reference path restated: samnerf/sam_field.py:112-140 (SAMField.get_outputs: L2 contraction, (p+2)/4, no
+// selector, concat of the two encodings, CutlassMLP 192->256->256) and samnerf/sam_model.py:126-137,243-277
+// (MeanRenderer over the top-k samples).  The second (linear, activation-free) layer commutes with the
+// weighted sum, so this kernel emits hbar = sum_k w_k * fp16(relu(W1 x_k)) per ray and kernel C applies W2
+// once per ray instead of once per sample (16x fewer FLOPs; rounding differs from the reference only in
+// where the fp16 round of the per-sample output happens - inside the stated tolerance).
+//
+// CTA = 16 warps = one tile of 8 rays x 16 samples = 128 rows.  Warp w gathers ray (w&7), encoding (w>>3);
+// lane = (sample, x-neighbour) so the two 16-byte corner loads of an x-pair share a 32-byte sector.
+// The A tile and W1 live in shared memory in the core-matrix layout (common.cuh) that both tensor-core
+// engines read:  tcgen05.mma (M=128, N=256, K=16 x 12, accumulator in TMEM, double-buffered against the
+// next tile's gather) or, as the recompiled-legacy comparison path, mma.sync m16n8k16.
+#include "kernels.cuh"
+
+namespace snrf {
+namespace {
+
+constexpr int kWarps = 16;
+constexpr int kThreads = kWarps * 32;
+constexpr int kRaysPerTile = 8;
+constexpr int kK = 16;      // samples per ray
+constexpr int kIn = 192;    // encoder width
+constexpr int kHid = 256;   // hidden width
+constexpr uint32_t kSBO = kIn * 16;                 // bytes between 8-row groups
+constexpr uint32_t kW1Bytes = kHid * kIn * 2;       // 98304
+constexpr uint32_t kATileBytes = 128 * kIn * 2;     // 49152
+constexpr uint32_t kSmemBytes = kW1Bytes + 2 * kATileBytes + 2 * 128 * 4 + 64;
+
+// reduce v[0..31] over the 16 lanes of each half-warp; on return v[0], v[1] hold the sums of columns
+// (base, base+1) with base = 16*b0 + 8*b1 + 4*b2 + 2*b3 (b_i = bit i of the lane).  30 shuffles.
+__device__ __forceinline__ int halving_reduce16(float (&v)[32], int lane) {
+  const unsigned FULL = 0xffffffffu;
+  int base = 0;
+#pragma unroll
+  for (int step = 0; step < 4; ++step) {
+    const int half = 16 >> step;
+    const bool up = (lane >> step) & 1;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      const float send = up ? v[i] : v[i + half];
+      const float keep = up ? v[i + half] : v[i];
+      v[i] = keep + __shfl_xor_sync(FULL, send, 1 << step);
+    }
+    base += up ? half : 0;
+  }
+  return base;
+}
+
+template <bool TC>
+__global__ void __launch_bounds__(kThreads, 1) sam_kernel(const SamParams P) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  unsigned char* s_w1 = smem;
+  unsigned char* s_a = smem + kW1Bytes;
+  float* s_sw = reinterpret_cast<float*>(smem + kW1Bytes + 2 * kATileBytes);  // [2][128]
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_sw + 256);                  // [2]
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 2);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const unsigned FULL = 0xffffffffu;
+
+  // W1 is already in core-matrix layout in HBM: straight 16-byte copy
+  for (uint32_t i = tid; i < kW1Bytes / 16; i += kThreads)
+    reinterpret_cast<uint4*>(s_w1)[i] = ldg_u128(reinterpret_cast<const uint4*>(P.w1) + i);
+  uint32_t tmem_base = 0;
+  if (TC) {
+    if (tid == 0) {
+      mbar_init(smem_u32(&s_bar[0]), 1);
+      mbar_init(smem_u32(&s_bar[1]), 1);
+      asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    if (warp == 0) tmem_alloc(smem_u32(s_tmem), 512);
+    fence_async_smem();
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (TC) {
+    tc_fence_after();
+    tmem_base = *s_tmem;
+  }
+
+  const int64_t n_tiles = (P.n_rays + kRaysPerTile - 1) / kRaysPerTile;
+  const int r_loc = warp & 7, e = warp >> 3;
+  const int s16 = lane >> 1, xb = lane & 1;
+  const GridDev& G = P.enc[e];
+
+  // ---- epilogue of one tile out of TMEM (tcgen05 engine) ---------------------------------------
+  auto epilogue_tc = [&](int64_t tile, int buf, uint32_t parity) {
+    mbar_wait(smem_u32(&s_bar[buf]), parity);
+    tc_fence_after();
+    const int quarter = warp & 3, cq = warp >> 2;
+    const int row = quarter * 32 + lane;
+    const float wgt = s_sw[buf * 128 + row];
+    const int64_t ray = tile * kRaysPerTile + (row >> 4);
+#pragma unroll 1
+    for (int chunk = 0; chunk < 2; ++chunk) {
+      float v[32];
+      const int col0 = cq * 64 + chunk * 32;
+      tmem_ld32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * 256 + col0, v);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = round_f16(fmaxf(v[i], 0.f)) * wgt;
+      const int base = halving_reduce16(v, lane & 15);
+      if (ray < P.n_rays)
+        *reinterpret_cast<uint32_t*>(P.hbar + ray * kHid + col0 + base) = f2_to_h2(v[0], v[1]);
+    }
+    tc_fence_before();
+  };
+
+  int64_t prev_tile = -1;
+  int it = 0;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+    const int buf = it & 1;
+    unsigned char* a_tile = s_a + buf * kATileBytes;
+    const int64_t ray = tile * kRaysPerTile + r_loc;
+    const int row = r_loc * kK + s16;
+
+    // ---------------- gather: 12 levels x 4 (y,z) corners x 16 B per lane ------------------------
+    if (ray < P.n_rays) {
+      const float tm2 = P.sam_t[ray * kK + s16];
+      if (e == 0 && xb == 0) s_sw[buf * 128 + row] = P.sam_w[ray * kK + s16];
+      const float px = __fadd_rn(P.origins[3 * ray + 0], __fmul_rn(P.dirs[3 * ray + 0], tm2) / 2.f);
+      const float py = __fadd_rn(P.origins[3 * ray + 1], __fmul_rn(P.dirs[3 * ray + 1], tm2) / 2.f);
+      const float pz = __fadd_rn(P.origins[3 * ray + 2], __fmul_rn(P.dirs[3 * ray + 2], tm2) / 2.f);
+      float x, y, z, sel;
+      contract_normalize(px, py, pz, false, false, x, y, z, sel);
+#pragma unroll 2
+      for (int l = 0; l < 12; ++l) {
+        const GridLevel L = G.lv[l];
+        const float qx = __fadd_rn(__fmul_rn(x, L.scale), 0.5f);
+        const float qy = __fadd_rn(__fmul_rn(y, L.scale), 0.5f);
+        const float qz = __fadd_rn(__fmul_rn(z, L.scale), 0.5f);
+        const float fx = floorf(qx), fy = floorf(qy), fz = floorf(qz);
+        const float rx = qx - fx, ry = qy - fy, rz = qz - fz;
+        const uint32_t gx = static_cast<uint32_t>(static_cast<int>(fx)) + xb;
+        const uint32_t gy = static_cast<uint32_t>(static_cast<int>(fy));
+        const uint32_t gz = static_cast<uint32_t>(static_cast<int>(fz));
+        const float wx = xb ? rx : 1.f - rx;
+        uint4 v[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const uint32_t idx = grid_index(L, gx, gy + (c & 1), gz + (c >> 1));
+          v[c] = ldg_u128(G.table + 8 * static_cast<size_t>(idx));
+        }
+        float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          float w = wx * ((c & 1) ? ry : 1.f - ry);
+          w *= ((c >> 1) ? rz : 1.f - rz);
+          const float2 f0 = h2_to_f2(v[c].x), f1 = h2_to_f2(v[c].y), f2 = h2_to_f2(v[c].z), f3 = h2_to_f2(v[c].w);
+          a[0] += w * f0.x; a[1] += w * f0.y; a[2] += w * f1.x; a[3] += w * f1.y;
+          a[4] += w * f2.x; a[5] += w * f2.y; a[6] += w * f3.x; a[7] += w * f3.y;
+        }
+        // lane xb=0 finishes features 0-3, lane xb=1 features 4-7
+        float o[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float send = xb ? a[i] : a[i + 4];
+          const float mine = xb ? a[i + 4] : a[i];
+          o[i] = mine + __shfl_xor_sync(FULL, send, 1);
+        }
+        const uint2 pk = make_uint2(f2_to_h2(o[0], o[1]), f2_to_h2(o[2], o[3]));
+        const uint32_t k = e * 96 + l * 8 + xb * 4;
+        *reinterpret_cast<uint2*>(a_tile + core_offset(row, k, kIn)) = pk;
+        if (P.dbg_feat) *reinterpret_cast<uint2*>(P.dbg_feat + (ray * kK + s16) * kIn + k) = pk;
+      }
+    } else {
+      // tail tile: keep the rows finite so the (discarded) accumulator rows are well defined
+      if (e == 0 && xb == 0) s_sw[buf * 128 + row] = 0.f;
+      for (int l = 0; l < 12; ++l)
+        *reinterpret_cast<uint2*>(a_tile + core_offset(row, e * 96 + l * 8 + xb * 4, kIn)) = make_uint2(0u, 0u);
+    }
+    if (TC) fence_async_smem();
+    __syncthreads();
+
+    if (TC) {
+      if (tid == 0) {
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(a_tile), b_addr = smem_u32(s_w1);
+        const uint32_t idesc = umma_idesc_f16(128, 256);
+#pragma unroll
+        for (int ks = 0; ks < kIn / 16; ++ks) {
+          umma_f16(tmem_base + buf * 256, umma_desc(a_addr + ks * 256, 128, kSBO),
+                   umma_desc(b_addr + ks * 256, 128, kSBO), idesc, ks > 0 ? 1u : 0u);
+        }
+        umma_commit(smem_u32(&s_bar[buf]));
+      }
+      __syncwarp();
+      if (it > 0) epilogue_tc(prev_tile, buf ^ 1, static_cast<uint32_t>(((it - 1) >> 1) & 1));
+      prev_tile = tile;
+    } else {
+      // ---------------- legacy engine: warp = (ray, 128-column half), mma.sync m16n8k16 ----------
+      const int nh = warp >> 3;
+      float acc[16][4];
+#pragma unroll
+      for (int nt = 0; nt < 16; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+      const uint32_t a_addr = smem_u32(a_tile), b_addr = smem_u32(s_w1);
+      const uint32_t a_row = r_loc * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+#pragma unroll 1
+      for (int ks = 0; ks < kIn / 16; ++ks) {
+        uint32_t af[4];
+        ldmatrix_x4(af, a_addr + core_offset(a_row, (2 * ks + (lane >> 4)) * 8, kIn));
+#pragma unroll
+        for (int np = 0; np < 8; ++np) {
+          uint32_t bf[4];
+          const uint32_t n_row = nh * 128 + (2 * np + (lane >> 4)) * 8 + (lane & 7);
+          ldmatrix_x4(bf, b_addr + core_offset(n_row, (2 * ks + ((lane >> 3) & 1)) * 8, kIn));
+          mma_16816(acc[2 * np], af, bf[0], bf[1]);
+          mma_16816(acc[2 * np + 1], af, bf[2], bf[3]);
+        }
+      }
+      const int g = lane >> 2, q = lane & 3;
+      const float w_lo = s_sw[buf * 128 + r_loc * 16 + g], w_hi = s_sw[buf * 128 + r_loc * 16 + g + 8];
+#pragma unroll
+      for (int nt = 0; nt < 16; ++nt) {
+        float c0 = round_f16(fmaxf(acc[nt][0], 0.f)) * w_lo + round_f16(fmaxf(acc[nt][2], 0.f)) * w_hi;
+        float c1 = round_f16(fmaxf(acc[nt][1], 0.f)) * w_lo + round_f16(fmaxf(acc[nt][3], 0.f)) * w_hi;
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) {
+          c0 += __shfl_xor_sync(FULL, c0, o);
+          c1 += __shfl_xor_sync(FULL, c1, o);
+        }
+        if (g == 0 && ray < P.n_rays)
+          *reinterpret_cast<uint32_t*>(P.hbar + ray * kHid + nh * 128 + nt * 8 + 2 * q) = f2_to_h2(c0, c1);
+      }
+    }
+  }
+  if (TC) {
+    if (it > 0) epilogue_tc(prev_tile, (it - 1) & 1, static_cast<uint32_t>(((it - 1) >> 1) & 1));
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_sam(const SamParams& P, bool tcgen05, int sm_count, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(sam_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(sam_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  if (P.n_rays <= 0) return cudaSuccess;
+  const int64_t n_tiles = (P.n_rays + kRaysPerTile - 1) / kRaysPerTile;
+  const int grid = static_cast<int>(n_tiles < sm_count ? n_tiles : sm_count);  // persistent: one CTA per SM
+  if (tcgen05)
+    sam_kernel<true><<<grid, kThreads, kSmemBytes, stream>>>(P);
+  else
+    sam_kernel<false><<<grid, kThreads, kSmemBytes, stream>>>(P);
+  return cudaGetLastError();
+}
+
+}  // namespace snrf

@@ -1,0 +1,443 @@
+"""The reference's nerfstudio-facing surface for the hot path, backed by ``libsnrf``.
+
+Same class names, argument meaning and return keys as the reference modules they replace, so that
+``samnerf.train`` / the viewer / ``scripts/render.py`` call sites read the same:
+
+    reference                                                   here
+    nerfstudio/cameras/rays.py:31,97,166                        Frustums, RaySamples, RayBundle
+    nerfstudio/model_components/scene_colliders.py:170-188      NearFarCollider
+    nerfstudio/model_components/ray_samplers.py:509-599         ProposalNetworkSampler
+    nerfstudio/fields/density_fields.py:39-125                  HashMLPDensityField
+    nerfstudio/fields/nerfacto_field.py:67-351                  TCNNNerfactoField
+    samnerf/sam_field.py:25-140                                 SAMField
+    nerfstudio/model_components/renderers.py:58,197,226         RGBRenderer, AccumulationRenderer, DepthRenderer
+    samnerf/sam_model.py:126,179                                MeanRenderer, SAMModel
+
+Every method that computes something calls into the CUDA library (through ``renderer.Renderer``); nothing here
+falls back to PyTorch math.  Inference (eval-mode) semantics only - training-mode jitter and autograd are a
+"next" row (SURVEY.md section 8 f).
+"""
+from __future__ import annotations
+
+import contextlib
+from dataclasses import dataclass, fields
+from enum import Enum
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from .config import SAMNeRFConfig, get_feature_size
+from .renderer import Renderer
+
+
+class FieldHeadNames(Enum):
+    """nerfstudio/field_components/field_heads.py (subset used on this path)."""
+
+    RGB = "rgb"
+    DENSITY = "density"
+
+
+# ------------------------------------------------------------------------------------------------
+# data carriers
+# ------------------------------------------------------------------------------------------------
+class _Carrier:
+    """Minimal stand-in for ``TensorDataclass`` (nerfstudio/utils/tensor_dataclass.py): index / reshape /
+    flatten applied to every tensor field over the leading (batch) dims."""
+
+    def _map(self, fn):
+        kw = {}
+        for f in fields(self):
+            v = getattr(self, f.name)
+            if torch.is_tensor(v):
+                kw[f.name] = fn(v)
+            elif isinstance(v, _Carrier):
+                kw[f.name] = v._map(fn)
+            else:
+                kw[f.name] = v
+        return type(self)(**kw)
+
+    @property
+    def shape(self):
+        return tuple(self._lead().shape[:-1])
+
+    def __len__(self):
+        t = self._lead()
+        return t.numel() // t.shape[-1]
+
+    def flatten(self):
+        return self._map(lambda t: t.reshape(-1, t.shape[-1]))
+
+    def reshape(self, shape):
+        return self._map(lambda t: t.reshape(*shape, t.shape[-1]))
+
+    def __getitem__(self, idx):
+        if not isinstance(idx, tuple):
+            idx = (idx,)
+        return self._map(lambda t: t[idx + (slice(None),)] if Ellipsis not in idx else t[idx])
+
+    def to(self, device):
+        return self._map(lambda t: t.to(device))
+
+    def _apply_fn_to_fields(self, fn, dataclass_fn=None):
+        return self._map(fn)
+
+
+@dataclass
+class Frustums(_Carrier):
+    origins: torch.Tensor
+    directions: torch.Tensor
+    starts: torch.Tensor
+    ends: torch.Tensor
+    pixel_area: Optional[torch.Tensor] = None
+
+    def _lead(self):
+        return self.starts
+
+    def get_positions(self) -> torch.Tensor:
+        """rays.py:48-57 - frustum centres (pure indexing arithmetic on the carrier; kernels recompute it)."""
+        return self.origins + self.directions * (self.starts + self.ends) / 2
+
+
+@dataclass
+class RaySamples(_Carrier):
+    frustums: Frustums
+    camera_indices: Optional[torch.Tensor] = None
+    deltas: Optional[torch.Tensor] = None
+    spacing_starts: Optional[torch.Tensor] = None
+    spacing_ends: Optional[torch.Tensor] = None
+    spacing_to_euclidean_fn: Optional[Callable] = None
+    renderer: Optional[Renderer] = None
+
+    def _lead(self):
+        return self.frustums.starts
+
+    def get_weights(self, densities: torch.Tensor) -> torch.Tensor:
+        """rays.py:141-163 -> ``snrf_ray_op`` mode 0."""
+        n, s = densities.shape[0], densities.shape[1]
+        w = self.renderer.ray_op(0, self.deltas.reshape(n, s), densities.reshape(n, s))
+        return w[..., None]
+
+
+@dataclass
+class RayBundle(_Carrier):
+    origins: torch.Tensor
+    directions: torch.Tensor
+    pixel_area: Optional[torch.Tensor] = None
+    camera_indices: Optional[torch.Tensor] = None
+    nears: Optional[torch.Tensor] = None
+    fars: Optional[torch.Tensor] = None
+
+    def _lead(self):
+        return self.origins
+
+    def get_row_major_sliced_ray_bundle(self, start_idx: int, end_idx: int) -> "RayBundle":
+        """rays.py:213-224."""
+        return self.flatten()[start_idx:end_idx]
+
+
+class NearFarCollider:
+    """scene_colliders.py:170-188 (eval mode: near plane 0).  Bundles that already carry nears/fars pass through
+    (scene_colliders.py:40-44)."""
+
+    def __init__(self, near_plane: float, far_plane: float, training: bool = False):
+        self.near_plane, self.far_plane, self.training = near_plane, far_plane, training
+
+    def __call__(self, ray_bundle: RayBundle) -> RayBundle:
+        if ray_bundle.nears is not None and ray_bundle.fars is not None:
+            return ray_bundle
+        ones = torch.ones_like(ray_bundle.origins[..., 0:1])
+        ray_bundle.nears = ones * (self.near_plane if self.training else 0)
+        ray_bundle.fars = ones * self.far_plane
+        return ray_bundle
+
+
+# ------------------------------------------------------------------------------------------------
+# fields
+# ------------------------------------------------------------------------------------------------
+class _Field:
+    def __init__(self, renderer: Renderer):
+        self.renderer = renderer
+
+    def density_fn(self, positions: torch.Tensor) -> torch.Tensor:
+        """base_field.py:38-56."""
+        return self._density(positions)[0]
+
+    def __call__(self, ray_samples: RaySamples, compute_normals: bool = False):
+        return self.forward(ray_samples, compute_normals)
+
+
+class HashMLPDensityField(_Field):
+    """density_fields.py:39-125 (the proposal network)."""
+
+    def _density(self, positions):
+        return self.renderer.query_density("proposal", positions)
+
+    def get_density(self, ray_samples: RaySamples):
+        return self._density(ray_samples.frustums.get_positions())[0], None
+
+    def get_outputs(self, ray_samples, density_embedding=None) -> dict:
+        return {}
+
+    def forward(self, ray_samples, compute_normals: bool = False):
+        density, _ = self.get_density(ray_samples)
+        return {FieldHeadNames.DENSITY: density}
+
+
+class TCNNNerfactoField(_Field):
+    """nerfacto_field.py:67-351 with appearance embedding off (samconfigs.py:80,134)."""
+
+    def _density(self, positions):
+        return self.renderer.query_density("field", positions)
+
+    def get_density(self, ray_samples: RaySamples):
+        return self._density(ray_samples.frustums.get_positions())
+
+    def get_outputs(self, ray_samples: RaySamples, density_embedding=None):
+        assert density_embedding is not None
+        if ray_samples.camera_indices is None:
+            raise AttributeError("Camera indices are not provided.")  # nerfacto_field.py:273-275
+        rgb = self.renderer.query_rgb(ray_samples.frustums.directions, density_embedding)
+        return {FieldHeadNames.RGB: rgb}
+
+    def forward(self, ray_samples: RaySamples, compute_normals: bool = False):
+        density, emb = self.get_density(ray_samples)
+        out = self.get_outputs(ray_samples, density_embedding=emb)
+        out[FieldHeadNames.DENSITY] = density
+        return out
+
+
+class SAMField(_Field):
+    """sam_field.py:25-140.  ``get_feautre`` keeps the reference's spelling of the keyword."""
+
+    def get_outputs(self, ray_samples: RaySamples, get_feautre=("sam", "dino", "clipseg")):
+        pos = ray_samples.frustums.get_positions().detach()
+        out = {}
+        if "sam" in get_feautre:
+            out["hashgrid"], out["sam"] = self.renderer.query_features("sam", pos)
+        if "clipseg" in get_feautre and self.renderer.cfg.use_clipseg_feature:
+            _, out["clipseg"] = self.renderer.query_features("clipseg", pos)
+        return out
+
+
+# ------------------------------------------------------------------------------------------------
+# sampler
+# ------------------------------------------------------------------------------------------------
+class ProposalNetworkSampler:
+    """ray_samplers.py:509-599, eval mode, one proposal iteration (samconfigs.py:84,138)."""
+
+    def __init__(self, renderer: Renderer):
+        self.renderer = renderer
+
+    def _samples(self, bundle: RayBundle, edges: torch.Tensor, spacing: Optional[torch.Tensor]) -> RaySamples:
+        o, d = bundle.origins[:, None, :], bundle.directions[:, None, :]
+        starts, ends = edges[:, :-1, None], edges[:, 1:, None]
+        fr = Frustums(origins=o.expand(-1, starts.shape[1], -1), directions=d.expand(-1, starts.shape[1], -1),
+                      starts=starts, ends=ends,
+                      pixel_area=None if bundle.pixel_area is None else bundle.pixel_area[:, None, :].expand(-1, starts.shape[1], -1))
+        cam = None if bundle.camera_indices is None else bundle.camera_indices[:, None, :].expand(-1, starts.shape[1], -1)
+        return RaySamples(frustums=fr, camera_indices=cam, deltas=ends - starts,
+                          spacing_starts=None if spacing is None else spacing[:, :-1, None],
+                          spacing_ends=None if spacing is None else spacing[:, 1:, None], renderer=self.renderer)
+
+    def generate_ray_samples(self, ray_bundle: RayBundle, density_fns=None) -> Tuple[RaySamples, List, List]:
+        r = self.renderer
+        w0, edges1, _ = r.sample(ray_bundle.origins, ray_bundle.directions, ray_bundle.nears, ray_bundle.fars)
+        n = w0.shape[0]
+        # level-0 samples for ray_samples_list: the piecewise bins are a closed form of (near, far)
+        nears = ray_bundle.nears if ray_bundle.nears is not None else torch.zeros(n, 1, device=w0.device)
+        fars = ray_bundle.fars if ray_bundle.fars is not None else torch.full((n, 1), r.cfg.far_plane, device=w0.device)
+        bins = torch.linspace(0.0, 1.0, r.cfg.num_proposal_samples + 1, device=w0.device)[None]
+        sp = lambda x: torch.where(x < 1, x / 2, 1 - 1 / (2 * x))  # noqa: E731  ray_samplers.py:242
+        sp_inv = lambda x: torch.where(x < 0.5, 2 * x, 1 / (2 - 2 * x))  # noqa: E731  ray_samplers.py:243
+        s_near, s_far = sp(nears.to(w0.device)), sp(fars.to(w0.device))
+        edges0 = sp_inv(bins * s_far + (1 - bins) * s_near)
+        rs0 = self._samples(ray_bundle, edges0, bins.expand(n, -1))
+        rs1 = self._samples(ray_bundle, edges1, None)
+        return rs1, [w0[..., None]], [rs0]
+
+    __call__ = generate_ray_samples
+    forward = generate_ray_samples
+
+
+# ------------------------------------------------------------------------------------------------
+# renderers
+# ------------------------------------------------------------------------------------------------
+BACKGROUND_COLOR_OVERRIDE: Optional[torch.Tensor] = None
+
+
+@contextlib.contextmanager
+def background_color_override_context(mode):
+    """renderers.py:46-55."""
+    global BACKGROUND_COLOR_OVERRIDE
+    old = BACKGROUND_COLOR_OVERRIDE
+    try:
+        BACKGROUND_COLOR_OVERRIDE = mode
+        yield
+    finally:
+        BACKGROUND_COLOR_OVERRIDE = old
+
+
+_COLORS = {"white": (1.0, 1.0, 1.0), "black": (0.0, 0.0, 0.0)}
+
+
+def _resolve_background(background_color):
+    bg = BACKGROUND_COLOR_OVERRIDE if BACKGROUND_COLOR_OVERRIDE is not None else background_color
+    if isinstance(bg, str):
+        if bg == "last_sample":
+            return None
+        if bg in _COLORS:
+            return _COLORS[bg]
+        raise NotImplementedError(f"background {bg!r}: random backgrounds are a training-only mode")
+    return [float(v) for v in bg]
+
+
+class RGBRenderer:
+    """renderers.py:58-140 (eval: nan_to_num + clamp)."""
+
+    def __init__(self, renderer: Renderer, background_color="last_sample"):
+        self.renderer, self.background_color = renderer, background_color
+
+    def forward(self, rgb, weights, ray_indices=None, num_rays=None):
+        if ray_indices is not None:
+            raise NotImplementedError("packed samples are not on this path (renderers.py:90-95)")
+        n, s = weights.shape[0], weights.shape[1]
+        return self.renderer.ray_op(3, rgb.reshape(n, s, 3), weights.reshape(n, s),
+                                    background=_resolve_background(self.background_color))
+
+    __call__ = forward
+
+
+class AccumulationRenderer:
+    """renderers.py:197-223."""
+
+    def __init__(self, renderer: Renderer):
+        self.renderer = renderer
+
+    def forward(self, weights, ray_indices=None, num_rays=None):
+        return self.renderer.ray_op(1, weights.reshape(weights.shape[0], weights.shape[1]))
+
+    __call__ = forward
+
+
+class DepthRenderer:
+    """renderers.py:226-270, method "median"."""
+
+    def __init__(self, renderer: Renderer, method: str = "median"):
+        if method != "median":
+            raise NotImplementedError("SAMModel uses the median depth (nerfacto.py:222)")
+        self.renderer = renderer
+
+    def forward(self, weights, ray_samples: RaySamples, ray_indices=None, num_rays=None):
+        n, s = weights.shape[0], weights.shape[1]
+        return self.renderer.ray_op(2, weights.reshape(n, s), ray_samples.frustums.starts.reshape(n, s),
+                                    ray_samples.frustums.ends.reshape(n, s))
+
+    __call__ = forward
+
+
+class MeanRenderer:
+    """sam_model.py:126-137."""
+
+    def __init__(self, renderer: Renderer):
+        self.renderer = renderer
+
+    def forward(self, embeds, weights):
+        n, s, c = embeds.shape
+        return self.renderer.ray_op(4, embeds.to(torch.float32), weights.reshape(n, s), n_channels=c)
+
+    __call__ = forward
+
+
+# ------------------------------------------------------------------------------------------------
+# the model
+# ------------------------------------------------------------------------------------------------
+class SAMModel:
+    """samnerf/sam_model.py:179-418, inference side.
+
+    ``get_outputs`` / ``forward`` run one fused ``snrf_render`` call per chunk; the component objects
+    (``proposal_sampler``, ``field``, ``sam_field``, renderers) expose the same pieces individually.
+    Prompt lifting and mask decoding (sam_model.py:420-548) consume the rendered feature map and are out of
+    scope here (SURVEY.md section 8 f, row 4).
+    """
+
+    def __init__(self, config: SAMNeRFConfig, device: int = 0, engine: str = "tcgen05"):
+        self.config = config
+        self.renderer = Renderer(config, device=device, engine=engine)
+        self.training = False
+        r = self.renderer
+        self.collider = NearFarCollider(near_plane=0.05, far_plane=config.far_plane)
+        self.proposal_networks = [HashMLPDensityField(r)]
+        self.density_fns = [n.density_fn for n in self.proposal_networks]
+        self.proposal_sampler = ProposalNetworkSampler(r)
+        self.field = TCNNNerfactoField(r)
+        self.sam_field = SAMField(r) if config.distill_sam else None
+        self.renderer_rgb = RGBRenderer(r, background_color="last_sample")
+        self.renderer_accumulation = AccumulationRenderer(r)
+        self.renderer_depth = DepthRenderer(r)
+        self.renderer_mean = MeanRenderer(r)
+
+    def load_state_dict(self, state_dict: Dict[str, torch.Tensor], strict: bool = False):
+        """Accepts the reference's pipeline keys (with or without the ``_model.`` prefix, base_pipeline.py:366-375)."""
+        sd = {k[len("_model."):] if k.startswith("_model.") else k: v for k, v in state_dict.items()}
+        self.renderer.load_params(sd)
+
+    def eval(self):
+        return self
+
+    # sam_model.py:303-314
+    def forward(self, ray_bundle: RayBundle, **kwargs):
+        if self.collider is not None:
+            ray_bundle = self.collider(ray_bundle)
+        return self.get_outputs(ray_bundle, **kwargs)
+
+    __call__ = forward
+
+    # sam_model.py:226-278
+    def get_outputs(self, ray_bundle: RayBundle, get_rgbsigma=True, get_feature=("sam", "dino", "clipseg"), fast=False):
+        cfg = self.config
+        feats = [f for f in get_feature if f in ("sam", "clipseg")] if cfg.distill_sam else []
+        bg = _resolve_background(self.renderer_rgb.background_color)
+        out = self.renderer.render(
+            ray_bundle.origins, ray_bundle.directions, ray_bundle.nears, ray_bundle.fars, get_feature=feats,
+            patch=cfg.patch_size > 1 and "sam" in feats, fast=fast, background=bg,
+        )
+        return out
+
+    # sam_model.py:338-418 (up to the prompt handling)
+    @torch.no_grad()
+    def get_outputs_for_camera_ray_bundle(self, camera_ray_bundle: RayBundle, points=None, intrin=None, c2w=None,
+                                          text_prompt=None, topk=5, thresh=0.5, fast=False):
+        cfg = self.config
+        chunk = cfg.eval_num_rays_per_chunk
+        h, w = camera_ray_bundle.origins.shape[:2]
+        dev = self.renderer.device
+        bundle = camera_ray_bundle.to(dev)
+        flat = bundle.flatten()
+        lists: Dict[str, List[torch.Tensor]] = {}
+        for i in range(0, h * w, chunk):  # LOOP A
+            o = self.forward(flat[i:i + chunk], get_feature=[], fast=fast)
+            for k, v in o.items():
+                lists.setdefault(k, []).append(v)
+        outputs = {k: torch.cat(v).view(h, w, -1) for k, v in lists.items()}
+        if cfg.distill_sam:
+            fh, fw = get_feature_size(h, w)
+            p = cfg.patch_size
+            hi = torch.linspace(0, h - 1, fh * p, dtype=torch.long, device=dev)
+            wi = torch.linspace(0, w - 1, fw * p, dtype=torch.long, device=dev)
+            hind, wind = torch.meshgrid(hi, wi, indexing="ij")
+            fb = bundle[hind.flatten(), wind.flatten()].reshape((fh, p, fw, p))
+            fb = fb._apply_fn_to_fields(lambda x: x.transpose(1, 2)).flatten()
+            feats = []
+            for i in range(0, len(fb), chunk):  # LOOP B
+                feats.append(self.forward(fb[i:i + chunk], get_feature=["sam"])["sam"])
+            outputs["sam"] = torch.cat(feats).view(fh, fw, -1)
+            if cfg.use_clipseg_feature:  # LOOP C
+                hi = torch.linspace(0, h - 1, 32, dtype=torch.long, device=dev)
+                wi = torch.linspace(0, w - 1, 32, dtype=torch.long, device=dev)
+                hind, wind = torch.meshgrid(hi, wi, indexing="ij")
+                cb = bundle[hind.flatten(), wind.flatten()]
+                feats = []
+                for i in range(0, len(cb), chunk):
+                    feats.append(self.forward(cb[i:i + chunk], get_feature=["clipseg"])["clipseg"])
+                outputs["clipseg"] = torch.cat(feats).view(32, 32, -1)
+        return outputs

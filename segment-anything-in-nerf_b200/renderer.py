@@ -1,0 +1,311 @@
+"""Host-side driver of ``libsnrf``: owns one library context, uploads parameters, launches renders.
+
+PyTorch is used for device memory and streams only; every computation happens inside the CUDA library.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional, Sequence
+
+import torch
+
+from . import _lib as L
+from .config import GridConfig, SAMNeRFConfig
+
+
+def grid_desc(g: GridConfig) -> L.GridDesc:
+    """Level table computed on the host exactly as the oracle computes it (``GridConfig.levels``)."""
+    d = L.GridDesc()
+    d.n_levels, d.n_features = g.n_levels, g.n_features
+    for i, (scale, res, offset, size, hashed) in enumerate(g.levels()):
+        d.lv[i].scale, d.lv[i].res, d.lv[i].size, d.lv[i].offset, d.lv[i].hashed = scale, res, size, offset, int(hashed)
+    return d
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+class Renderer:
+    """One ``snrf_ctx`` on one CUDA device."""
+
+    def __init__(self, cfg: SAMNeRFConfig, device: int = 0, engine: str = "tcgen05"):
+        if not torch.cuda.is_available():
+            raise RuntimeError("samnerf_b200 needs a CUDA device (sm_100a); there is no CPU path")
+        if cfg.num_proposal_samples != 64 or cfg.num_nerf_samples != 32:
+            raise ValueError("kernels are built for 64 proposal / 32 nerf samples per ray (samconfigs.py:84-87)")
+        self.cfg = cfg
+        self.device = torch.device("cuda", device)
+        self.lib = L.load()
+        h = C.c_void_p()
+        rc = self.lib.snrf_ctx_create(device, C.byref(h))
+        if rc != 0:
+            raise RuntimeError(f"snrf_ctx_create({device}) failed with {rc}")
+        self.h = h
+        self.set_engine(engine)
+        # share the bits of the eval-mode PDF sample positions with torch (ray_samplers.py:325-327)
+        nb = cfg.num_nerf_samples + 1
+        u = torch.linspace(0.0, 1.0 - (1.0 / nb), steps=nb) + 1.0 / (2 * nb)
+        u = u.contiguous()
+        self._check(self.lib.snrf_set_pdf_u(self.h, u.data_ptr(), nb))
+        self.have_sam = self.have_clipseg = self.have_conv = False
+
+    # ------------------------------------------------------------------------------------------
+    def _check(self, rc: int) -> None:
+        if rc != 0:
+            msg = self.lib.snrf_last_error(self.h)
+            raise RuntimeError(f"libsnrf error {rc}: {msg.decode() if msg else ''}")
+
+    def close(self) -> None:
+        if getattr(self, "h", None) is not None and self.h:
+            self.lib.snrf_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.snrf_launch_count(self.h))
+
+    def set_timing(self, enable: bool) -> None:
+        self._check(self.lib.snrf_set_timing(self.h, int(enable)))
+
+    def kernel_times(self):
+        """{kernel: (total ms, launches)} since the previous call, from CUDA events on the launching stream."""
+        ms = (C.c_double * 3)()
+        cnt = (C.c_int64 * 3)()
+        self._check(self.lib.snrf_kernel_times(self.h, ms, cnt))
+        return {k: (ms[i], cnt[i]) for i, k in enumerate(("march", "feature", "tapgemm"))}
+
+    def set_engine(self, engine: str) -> None:
+        """``tcgen05`` (default) or ``mma_sync`` (the recompiled-legacy comparison path)."""
+        self.engine = engine
+        self._check(self.lib.snrf_set_engine(self.h, {"tcgen05": 1, "mma_sync": 0}[engine]))
+
+    # ------------------------------------------------------------------------------------------
+    def load_params(self, params: Dict[str, torch.Tensor]) -> None:
+        """Upload a reference-layout ``state_dict`` subset (keys as in ``synthetic.make_synthetic_params``)."""
+        cfg, lib, s = self.cfg, self.lib, self.stream
+
+        def flat(name):
+            t = params[name].detach().to(torch.float32).contiguous().view(-1)
+            return t, t.data_ptr(), t.numel()
+
+        d = grid_desc(cfg.proposal_grid)
+        t, p, n = flat("proposal_networks.0.mlp_base.params")
+        self._check(lib.snrf_upload_proposal(self.h, p, n, C.byref(d), s))
+        d = grid_desc(cfg.field_grid)
+        t, p, n = flat("field.mlp_base.params")
+        self._check(lib.snrf_upload_field_base(self.h, p, n, C.byref(d), s))
+        t, p, n = flat("field.mlp_head.params")
+        self._check(lib.snrf_upload_field_head(self.h, p, n, s))
+        for which, (enc, net, n_out) in enumerate(
+            (("sam_field.clip_encs", "sam_field.sam_net", cfg.sam_out),
+             ("sam_field.clipseg_encs", "sam_field.clipseg_net", cfg.clipseg_out))
+        ):
+            if f"{net}.params" not in params:
+                continue
+            for i, g in enumerate(cfg.sam_grids):
+                d = grid_desc(g)
+                t, p, n = flat(f"{enc}.{i}.params")
+                self._check(lib.snrf_upload_feature_grid(self.h, which, i, p, n, C.byref(d), s))
+            t, p, n = flat(f"{net}.params")
+            self._check(lib.snrf_upload_feature_net(self.h, which, p, n, n_out, s))
+            if which == 0:
+                self.have_sam = True
+            else:
+                self.have_clipseg = True
+        if "conv_head.0.weight" in params:
+            ts = [params[k].detach().to(torch.float32).contiguous()
+                  for k in ("conv_head.0.weight", "conv_head.0.bias", "conv_head.2.weight", "conv_head.2.bias")]
+            self._check(lib.snrf_upload_conv_head(self.h, *[x.data_ptr() for x in ts], s))
+            self.have_conv = True
+
+    # ------------------------------------------------------------------------------------------
+    def _opts(self, background=None) -> L.RenderOpts:
+        cfg = self.cfg
+        o = L.RenderOpts()
+        o.near_plane, o.far_plane, o.hist_padding = cfg.near_plane_eval, cfg.far_plane, cfg.histogram_padding
+        o.k_sam, o.sharpen, o.patch_size = cfg.num_sam_samples, cfg.sharpening_temperature, cfg.patch_size
+        if background is None:
+            o.bg_mode = L.BG_LAST_SAMPLE
+        else:
+            o.bg_mode = L.BG_FIXED
+            for i in range(3):
+                o.bg[i] = float(background[i])
+        return o
+
+    def _prep(self, t: Optional[torch.Tensor], cols: int) -> Optional[torch.Tensor]:
+        if t is None:
+            return None
+        t = t.to(device=self.device, dtype=torch.float32).reshape(-1, cols).contiguous()
+        return t
+
+    def render(
+        self,
+        origins: torch.Tensor,
+        directions: torch.Tensor,
+        nears: Optional[torch.Tensor] = None,
+        fars: Optional[torch.Tensor] = None,
+        get_feature: Sequence[str] = ("sam",),
+        patch: bool = False,
+        fast: bool = False,
+        background=None,
+        debug: bool = False,
+        out: Optional[Dict[str, torch.Tensor]] = None,
+    ) -> Dict[str, torch.Tensor]:
+        """One chunk of rays: ``SAMModel.forward`` in eval mode (samnerf/sam_model.py:226-314).
+        ``out``: optional preallocated CUDA output tensors (e.g. row slices of frame buffers) to write into."""
+        o, d = self._prep(origins, 3), self._prep(directions, 3)
+        nr, fr = self._prep(nears, 1), self._prep(fars, 1)
+        n = o.shape[0]
+        dev = self.device
+        given = out if out is not None else {}
+
+        def buf(name, *shape):
+            t = given.get(name)
+            if t is None:
+                return torch.empty(*shape, device=dev)
+            assert t.is_cuda and t.is_contiguous() and t.dtype == torch.float32 and tuple(t.shape) == shape, name
+            return t
+
+        out = {"rgb": buf("rgb", n, 3), "depth": buf("depth", n, 1)}
+        if not fast:
+            out["accumulation"] = buf("accumulation", n, 1)
+            out["prop_depth_0"] = buf("prop_depth_0", n, 1)
+        flags = 0
+        cfg = self.cfg
+        if cfg.distill_sam and "sam" in get_feature:
+            flags |= L.WANT_SAM
+            if patch:
+                flags |= L.PATCH
+                out["sam"] = buf("sam", n // (cfg.patch_size**2), cfg.sam_out)
+            else:
+                out["sam"] = buf("sam", n, cfg.sam_out)
+        if cfg.distill_sam and cfg.use_clipseg_feature and "clipseg" in get_feature:
+            flags |= L.WANT_CLIPSEG
+            out["clipseg"] = buf("clipseg", n, cfg.clipseg_out)
+        dbg = None
+        if debug:
+            k = cfg.num_sam_samples
+            out["_prop_weights"] = torch.empty(n, 64, device=dev)
+            out["_edges"] = torch.empty(n, 33, device=dev)
+            out["_weights"] = torch.empty(n, 32, device=dev)
+            out["_density"] = torch.empty(n, 32, device=dev)
+            out["_rgb_samples"] = torch.empty(n, 32, 3, device=dev)
+            out["_sam_t"] = torch.empty(n, k, device=dev)
+            out["_sam_w"] = torch.empty(n, k, device=dev)
+            dbg = L.DebugOut()
+            dbg.prop_weights, dbg.edges = out["_prop_weights"].data_ptr(), out["_edges"].data_ptr()
+            dbg.weights, dbg.density = out["_weights"].data_ptr(), out["_density"].data_ptr()
+            dbg.rgb_samples = out["_rgb_samples"].data_ptr()
+            dbg.sam_t, dbg.sam_w = out["_sam_t"].data_ptr(), out["_sam_w"].data_ptr()
+            if flags & L.WANT_SAM:
+                out["_sam_feat"] = torch.empty(n, k, cfg.sam_in, device=dev, dtype=torch.float16)
+                dbg.sam_feat = out["_sam_feat"].data_ptr()
+        opts = self._opts(background)
+        rc = self.lib.snrf_render(
+            self.h, o.data_ptr(), d.data_ptr(), _ptr(nr), _ptr(fr), n, flags, C.byref(opts),
+            out["rgb"].data_ptr(), out["depth"].data_ptr(), _ptr(out.get("accumulation")),
+            _ptr(out.get("prop_depth_0")), _ptr(out.get("sam")), _ptr(out.get("clipseg")),
+            C.byref(dbg) if dbg is not None else None, self.stream,
+        )
+        self._check(rc)
+        return out
+
+    def render_frame(self, origins, directions, get_feature: Sequence[str] = ("sam",), fast: bool = False,
+                     chunk: Optional[int] = None, out: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
+        """All rays of a frame (or of this rank's tile of it) in ``eval_num_rays_per_chunk`` chunks, every ray with
+        its features (SURVEY 8 d config 3), written straight into frame-sized buffers (no concatenation)."""
+        o, d = self._prep(origins, 3), self._prep(directions, 3)
+        n = o.shape[0]
+        chunk = chunk or self.cfg.eval_num_rays_per_chunk
+        cfg, dev = self.cfg, self.device
+        if out is None:
+            out = {"rgb": torch.empty(n, 3, device=dev), "depth": torch.empty(n, 1, device=dev)}
+            if not fast:
+                out["accumulation"] = torch.empty(n, 1, device=dev)
+                out["prop_depth_0"] = torch.empty(n, 1, device=dev)
+            if cfg.distill_sam and "sam" in get_feature:
+                out["sam"] = torch.empty(n, cfg.sam_out, device=dev)
+            if cfg.distill_sam and cfg.use_clipseg_feature and "clipseg" in get_feature:
+                out["clipseg"] = torch.empty(n, cfg.clipseg_out, device=dev)
+        for i in range(0, n, chunk):
+            self.render(o[i:i + chunk], d[i:i + chunk], get_feature=get_feature, fast=fast,
+                        out={k: v[i:i + chunk] for k, v in out.items()})
+        return out
+
+    def sample(self, origins, directions, nears=None, fars=None):
+        """Proposal weights ``[N,64]``, nerf bin edges ``[N,33]`` and proposal median depth ``[N,1]``."""
+        o, d = self._prep(origins, 3), self._prep(directions, 3)
+        nr, fr = self._prep(nears, 1), self._prep(fars, 1)
+        n = o.shape[0]
+        w0 = torch.empty(n, 64, device=self.device)
+        edges = torch.empty(n, 33, device=self.device)
+        pd = torch.empty(n, 1, device=self.device)
+        opts = self._opts()
+        self._check(self.lib.snrf_sample(self.h, o.data_ptr(), d.data_ptr(), _ptr(nr), _ptr(fr), n, C.byref(opts),
+                                         w0.data_ptr(), edges.data_ptr(), pd.data_ptr(), self.stream))
+        return w0, edges, pd
+
+    # ---- component-level queries ---------------------------------------------------------------
+    def query_density(self, which: str, positions: torch.Tensor):
+        """``which``: "proposal" or "field".  Returns ``density[...,1]`` and (field only) ``geo[...,15]`` fp16."""
+        shp = positions.shape[:-1]
+        x = self._prep(positions, 3)
+        n = x.shape[0]
+        dens = torch.empty(n, device=self.device)
+        geo = torch.empty(n, 15, device=self.device, dtype=torch.float16) if which == "field" else None
+        self._check(self.lib.snrf_query_density(self.h, 0 if which == "proposal" else 1, x.data_ptr(), n,
+                                                dens.data_ptr(), _ptr(geo), self.stream))
+        return dens.view(*shp, 1), (geo.view(*shp, 15) if geo is not None else None)
+
+    def query_rgb(self, directions: torch.Tensor, geo: torch.Tensor) -> torch.Tensor:
+        shp = geo.shape[:-1]
+        d = self._prep(directions.expand(*shp, 3), 3)
+        g = geo.to(device=self.device, dtype=torch.float16).reshape(-1, 15).contiguous()
+        rgb = torch.empty(d.shape[0], 3, device=self.device)
+        self._check(self.lib.snrf_query_rgb(self.h, d.data_ptr(), g.data_ptr(), d.shape[0], rgb.data_ptr(), self.stream))
+        return rgb.view(*shp, 3)
+
+    def query_features(self, which: str, positions: torch.Tensor):
+        """``SAMField.get_outputs`` per sample: returns ``(hashgrid[...,192] fp16, out[...,n_out] fp32)``."""
+        shp = positions.shape[:-1]
+        x = self._prep(positions, 3)
+        n = x.shape[0]
+        n_out = self.cfg.sam_out if which == "sam" else self.cfg.clipseg_out
+        hg = torch.empty(n, self.cfg.sam_in, device=self.device, dtype=torch.float16)
+        out = torch.empty(n, n_out, device=self.device)
+        self._check(self.lib.snrf_query_features(self.h, 0 if which == "sam" else 1, x.data_ptr(), n, hg.data_ptr(),
+                                                 out.data_ptr(), self.stream))
+        return hg.view(*shp, -1), out.view(*shp, n_out)
+
+    def ray_op(self, mode: int, a, b=None, c=None, n_channels: int = 0, background=None) -> torch.Tensor:
+        a = a.to(device=self.device, dtype=torch.float32).contiguous()
+        b = None if b is None else b.to(device=self.device, dtype=torch.float32).contiguous()
+        c = None if c is None else c.to(device=self.device, dtype=torch.float32).contiguous()
+        n, s = a.shape[0], a.shape[1]
+        shape = {0: (n, s), 1: (n, 1), 2: (n, 1), 3: (n, 3), 4: (n, n_channels)}[mode]
+        out = torch.empty(*shape, device=self.device)
+        bg = (C.c_float * 3)(*[float(v) for v in background]) if background is not None else None
+        self._check(self.lib.snrf_ray_op(self.h, mode, a.data_ptr(), _ptr(b), _ptr(c), out.data_ptr(), n, s,
+                                         n_channels, L.BG_FIXED if bg is not None else L.BG_LAST_SAMPLE,
+                                         C.cast(bg, C.c_void_p) if bg is not None else None, self.stream))
+        return out
+
+    def patch_aggregate(self, feat: torch.Tensor) -> torch.Tensor:
+        """Conv head on patch-major rows ``[P*p*p, 256]`` -> ``[P, 256]`` (samnerf/sam_model.py:260-265)."""
+        p = self.cfg.patch_size
+        f = feat.to(device=self.device, dtype=torch.float32).contiguous()
+        n_patches = f.shape[0] // (p * p)
+        out = torch.empty(n_patches, f.shape[1], device=self.device)
+        self._check(self.lib.snrf_patch_aggregate(self.h, f.data_ptr(), n_patches, p, out.data_ptr(), self.stream))
+        return out

@@ -1,0 +1,102 @@
+"""Shared helpers for the parity tests: build matching (oracle, CUDA renderer) pairs and compare with stated tolerances."""
+from __future__ import annotations
+
+import functools
+from typing import Dict, Tuple
+
+import numpy as np
+import torch
+
+from samnerf_b200 import SAMNeRFConfig, make_synthetic_params
+
+# ---- stated floating-point tolerances (CUDA path vs fp32 CPU oracle) -----------------------------------------
+# Both sides round parameters, encoder outputs and hidden activations to fp16 at the same places and accumulate
+# in fp32, so they differ by summation order plus the occasional 1-ulp fp16 flip that follows from it; a flip in
+# a density pre-activation moves exp() by ~0.1-0.4 %.  Discrete decisions (PDF bin search, median-depth index,
+# top-k membership) can flip on near-ties, which moves depth / features of that ray discontinuously; those rays
+# are budgeted as outliers (FRAC_*), not hidden.
+TOL = {
+    "density": dict(rtol=1e-2, atol=1e-4),
+    "weights": dict(rtol=2e-2, atol=2e-3),
+    "edges": dict(rtol=2e-3, atol=2e-4),
+    "rgb": dict(rtol=0.0, atol=2.0 / 255.0),
+    "accumulation": dict(rtol=0.0, atol=2e-3),
+    "depth": dict(rtol=2e-3, atol=2e-4),
+    "features": dict(rtol=2e-2, atol=2e-3),
+    "encoding": dict(rtol=0.0, atol=1e-3),
+}
+FRAC_SMOOTH = 0.999   # quantities that are continuous in the inputs
+FRAC_DISCRETE = 0.97  # quantities behind a discrete pick (median index, top-k set)
+
+
+def frac_close(a, b, rtol, atol) -> float:
+    a = torch.as_tensor(a).detach().float().cpu()
+    b = torch.as_tensor(b).detach().float().cpu()
+    assert a.shape == b.shape, (a.shape, b.shape)
+    both_nan = torch.isnan(a) & torch.isnan(b)
+    ok = ((a - b).abs() <= atol + rtol * b.abs()) | both_nan
+    return float(ok.float().mean())
+
+
+def assert_mostly_close(a, b, tol: Dict[str, float], frac: float, what: str, per_row: bool = False):
+    a = torch.as_tensor(a).detach().float().cpu()
+    b = torch.as_tensor(b).detach().float().cpu()
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    both_nan = torch.isnan(a) & torch.isnan(b)
+    ok = ((a - b).abs() <= tol["atol"] + tol["rtol"] * b.abs()) | both_nan
+    if per_row and ok.dim() > 1:
+        ok = ok.reshape(ok.shape[0], -1).all(dim=1)
+    got = float(ok.float().mean())
+    err = torch.nan_to_num((a - b).abs(), nan=0.0)
+    assert got >= frac, (
+        f"{what}: only {got:.5f} within rtol={tol['rtol']} atol={tol['atol']} (need {frac}); "
+        f"max|err|={float(err.max()):.3e} median|err|={float(err.median()):.3e}"
+    )
+    return got
+
+
+def error_stats(a, b) -> str:
+    a = torch.as_tensor(a).detach().float().cpu()
+    b = torch.as_tensor(b).detach().float().cpu()
+    e = torch.nan_to_num((a - b).abs(), nan=0.0).flatten()
+    ref = torch.nan_to_num(b.abs(), nan=0.0).flatten()
+    q = torch.quantile(e[:: max(1, e.numel() // 200000)], torch.tensor([0.5, 0.99, 0.999]))
+    return (f"max={float(e.max()):.3e} p50={float(q[0]):.3e} p99={float(q[1]):.3e} p99.9={float(q[2]):.3e} "
+            f"ref_absmean={float(ref.mean()):.3e}")
+
+
+@functools.lru_cache(maxsize=4)
+def model_pair(kind: str, regime: str, seed: int, clipseg: bool, patch: int):
+    """(cfg, params, Oracle) for a config; the CUDA renderer is created by the caller (needs a GPU)."""
+    from oracle.samnerf_oracle import Oracle
+
+    if kind == "tiny":
+        cfg = SAMNeRFConfig.tiny(clipseg=clipseg, patch_size=patch)
+    else:
+        cfg = SAMNeRFConfig.distill(clipseg=clipseg, patch_size=patch)
+    params = make_synthetic_params(cfg, regime, seed)
+    return cfg, params, Oracle(cfg, params)
+
+
+def make_renderer(cfg, params, engine: str = "tcgen05"):
+    from samnerf_b200.renderer import Renderer
+
+    r = Renderer(cfg, device=0, engine=engine)
+    r.load_params(params)
+    return r
+
+
+def test_rays(n: int, seed: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
+    """A spread of rays of the 800x800 orbit camera plus the two plumbing cameras."""
+    from samnerf_b200.synthetic import orbit_rays, plumbing_rays
+
+    o1, d1 = orbit_rays()
+    o1, d1 = o1.reshape(-1, 3), d1.reshape(-1, 3)
+    o2, d2 = plumbing_rays()
+    g = torch.Generator().manual_seed(seed)
+    i1 = torch.randint(0, o1.shape[0], (n - n // 4,), generator=g)
+    i2 = torch.randint(0, o2.shape[0], (n // 4,), generator=g)
+    return torch.cat([o1[i1], o2[i2]]).contiguous(), torch.cat([d1[i1], d2[i2]]).contiguous()
+
+
+test_rays.__test__ = False  # not a pytest test

@@ -1,0 +1,106 @@
+"""Size-independent properties of the CUDA path at BASELINE.json's full sizes, and the edge cases of the boundary."""
+import pytest
+import torch
+
+from helpers import make_renderer, model_pair, test_rays
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def full():
+    cfg, params, orc = model_pair("full", "scene", 0, False, 1)
+    return cfg, make_renderer(cfg, params)
+
+
+def test_full_frame_properties(full):
+    """800x800 frame (640 000 rays, 20 chunks of 32 768): invariants the reference's math guarantees."""
+    from samnerf_b200.synthetic import orbit_rays
+
+    cfg, r = full
+    o, d = orbit_rays()
+    o, d = o.reshape(-1, 3).cuda(), d.reshape(-1, 3).cuda()
+    chunk = cfg.eval_num_rays_per_chunk
+    outs = [r.render(o[i:i + chunk], d[i:i + chunk], get_feature=("sam",), debug=(i == 0)) for i in range(0, o.shape[0], chunk)]
+    torch.cuda.synchronize()
+    rgb = torch.cat([x["rgb"] for x in outs])
+    acc = torch.cat([x["accumulation"] for x in outs])
+    depth = torch.cat([x["depth"] for x in outs])
+    sam = torch.cat([x["sam"] for x in outs])
+    assert rgb.shape == (640000, 3) and sam.shape == (640000, 256)
+    assert torch.isfinite(rgb).all() and float(rgb.min()) >= 0.0 and float(rgb.max()) <= 1.0
+    assert float(acc.min()) >= 0.0 and float(acc.max()) <= 1.0 + 1e-5        # sum of alpha*T never exceeds 1
+    assert float(depth.min()) >= 0.0 and float(depth.max()) <= cfg.far_plane
+    d0 = outs[0]
+    e = d0["_edges"]
+    assert bool((e[:, 1:] >= e[:, :-1]).all()), "PDF samples must be monotone along the ray"
+    assert bool((d0["_weights"] >= 0).all()) and bool((d0["_prop_weights"] >= 0).all())
+    sw = d0["_sam_w"]
+    ok = torch.isfinite(sw).all(dim=-1)
+    assert float(ok.float().mean()) > 0.99
+    assert torch.allclose(sw[ok].sum(-1), torch.ones_like(sw[ok].sum(-1)), atol=1e-5), "top-k weights renormalise to 1"
+    assert bool((sw[ok][:, :-1] >= sw[ok][:, 1:]).all()), "slot order is descending weight"
+    assert float(torch.isfinite(sam).all(dim=-1).float().mean()) > 0.99
+
+
+def test_chunking_and_determinism(full):
+    """Rays are independent: any chunking, any position in the batch, any repeat gives the same bits."""
+    cfg, r = full
+    o, d = test_rays(5000, seed=3)
+    o, d = o.cuda(), d.cuda()
+    a = r.render(o, d, get_feature=("sam",))
+    b = r.render(o, d, get_feature=("sam",))
+    parts = [r.render(o[i:i + 777], d[i:i + 777], get_feature=("sam",)) for i in range(0, 5000, 777)]
+    perm = torch.randperm(5000, generator=torch.Generator().manual_seed(1)).cuda()
+    c = r.render(o[perm], d[perm], get_feature=("sam",))
+    torch.cuda.synchronize()
+    for k in ("rgb", "depth", "accumulation", "prop_depth_0", "sam"):
+        assert torch.equal(a[k], b[k]), f"{k}: not deterministic"
+        assert torch.equal(a[k], torch.cat([p[k] for p in parts])), f"{k}: depends on chunking"
+        assert torch.equal(a[k][perm], c[k]), f"{k}: depends on position in the batch"
+
+
+def test_edge_cases(full):
+    cfg, r = full
+    o, d = test_rays(64, seed=4)
+    # empty batch
+    out = r.render(o[:0], d[:0], get_feature=("sam",))
+    assert out["rgb"].shape == (0, 3) and out["sam"].shape == (0, 256)
+    # single ray / ragged sizes around the warp-per-ray CTA (8) and the 8-ray feature tile
+    ref = r.render(o, d, get_feature=("sam",))
+    for n in (1, 7, 9, 63):
+        part = r.render(o[:n], d[:n], get_feature=("sam",))
+        for k in ("rgb", "depth", "sam"):
+            assert torch.equal(part[k], ref[k][:n]), (k, n)
+    # caller-supplied nears / fars (viewer crop box path, scene_colliders.py:40-44) equal to the defaults
+    nf = r.render(o, d, nears=torch.zeros(64, 1), fars=torch.full((64, 1), cfg.far_plane), get_feature=("sam",))
+    assert torch.equal(nf["rgb"], ref["rgb"]) and torch.equal(nf["sam"], ref["sam"])
+    # a tighter far plane changes the samples
+    near2 = r.render(o, d, nears=torch.full((64, 1), 0.05), fars=torch.full((64, 1), 6.0), get_feature=())
+    assert float(near2["depth"].max()) <= 6.0
+    # fixed background only matters where accumulation < 1
+    white = r.render(o, d, get_feature=(), background=(1.0, 1.0, 1.0))
+    black = r.render(o, d, get_feature=(), background=(0.0, 0.0, 0.0))
+    diff = (white["rgb"] - black["rgb"]).sum(-1, keepdim=True) / 3.0
+    assert torch.allclose(diff, (1.0 - ref["accumulation"]).clamp(0, 1), atol=2e-3)
+    # fast mode drops accumulation / prop_depth_0 (sam_model.py:284-299) and leaves the rest untouched
+    fast = r.render(o, d, get_feature=(), fast=True)
+    assert "accumulation" not in fast and "prop_depth_0" not in fast and torch.equal(fast["rgb"], ref["rgb"])
+
+
+def test_errors_are_loud(full):
+    cfg, r = full
+    o, d = test_rays(16, seed=5)
+    with pytest.raises(RuntimeError, match="clipseg"):
+        # this renderer was built without ClipSeg parameters
+        import ctypes as C
+        from samnerf_b200 import _lib as L
+        o_, d_ = o.cuda(), d.cuda()
+        rgb, dep = torch.empty(16, 3, device="cuda"), torch.empty(16, 1, device="cuda")
+        cs = torch.empty(16, 192, device="cuda")
+        opts = r._opts()
+        rc = r.lib.snrf_render(r.h, o_.data_ptr(), d_.data_ptr(), None, None, 16, L.WANT_CLIPSEG, C.byref(opts),
+                               rgb.data_ptr(), dep.data_ptr(), None, None, None, cs.data_ptr(), None, r.stream)
+        r._check(rc)
+    with pytest.raises(RuntimeError, match="divisible by 16"):
+        r.render(o[:10], d[:10], get_feature=("sam",), patch=True)
