@@ -11,7 +11,7 @@ import subprocess
 import sys
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsnrf.so")
+LIB_PATH = os.environ.get("SNRF_LIB_PATH") or os.path.join(_HERE, "libsnrf.so")
 CSRC = os.path.join(_HERE, "csrc")
 SOURCES = ["api.cu", "march.cu", "sam.cu", "gemm.cu", "query.cu"]
 NVCC_FLAGS = [

@@ -150,8 +150,11 @@ int64_t grid_entries(const snrf_grid_desc* d) {
 }
 bool grid_ok(const snrf_grid_desc* d, int levels, int feats) {
   if (!d || d->n_levels != levels || d->n_features != feats) return false;
-  for (int l = 0; l < levels; ++l)
+  for (int l = 0; l < levels; ++l) {
     if (d->lv[l].size == 0 || d->lv[l].res < 2) return false;
+    // the kernels replace `% size` by a mask on hashed levels (tcnn: hashed size == 2^log2_hashmap_size)
+    if (d->lv[l].hashed && (d->lv[l].size & (d->lv[l].size - 1u)) != 0) return false;
+  }
   return true;
 }
 
@@ -537,9 +540,9 @@ int snrf_render(snrf_ctx* ctx, const float* origins, const float* dirs, const fl
                 int64_t n_rays, uint32_t flags, const snrf_render_opts* opts, float* rgb, float* depth, float* acc,
                 float* prop_depth, float* sam, float* clipseg, const snrf_debug_out* dbg, void* stream) {
   if (!ctx) return SNRF_E_INVALID;
-  if (!origins || !dirs || !opts || !rgb || !depth) return fail(ctx, SNRF_E_INVALID, "null argument");
   if (n_rays < 0) return fail(ctx, SNRF_E_INVALID, "negative ray count");
-  if (n_rays == 0) return SNRF_OK;
+  if (n_rays == 0) return SNRF_OK;  // empty chunk: nothing to read or write, pointers may be null
+  if (!origins || !dirs || !opts || !rgb || !depth) return fail(ctx, SNRF_E_INVALID, "null argument");
   if (!ctx->have_base || !ctx->have_head) return fail(ctx, SNRF_E_STATE, "nerfacto field parameters not uploaded");
   const bool want_sam = (flags & SNRF_WANT_SAM) != 0, want_clip = (flags & SNRF_WANT_CLIPSEG) != 0;
   const bool patch = (flags & SNRF_PATCH) != 0;
@@ -641,8 +644,8 @@ int snrf_sample(snrf_ctx* ctx, const float* origins, const float* dirs, const fl
                 int64_t n_rays, const snrf_render_opts* opts, float* prop_weights, float* edges, float* prop_depth,
                 void* stream) {
   if (!ctx) return SNRF_E_INVALID;
-  if (!origins || !dirs || !opts) return fail(ctx, SNRF_E_INVALID, "null argument");
   if (n_rays <= 0) return n_rays == 0 ? SNRF_OK : fail(ctx, SNRF_E_INVALID, "negative ray count");
+  if (!origins || !dirs || !opts) return fail(ctx, SNRF_E_INVALID, "null argument");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   CK(cudaSetDevice(ctx->device));
   MarchParams M;

@@ -78,14 +78,51 @@ __device__ __forceinline__ void contract_normalize(float px, float py, float pz,
   }
 }
 
+// Hashed levels always have a power-of-two size (2^log2_hashmap_size; checked at upload), so `% size` is a mask.
+// Dense levels: idx <= res + res^2 + res^3 < 2*size, and idx >= size only for the +1 corner of a coordinate on the
+// upper boundary, so `% size` is one conditional subtract; the final min() keeps non-finite inputs in bounds.
+__device__ __forceinline__ uint32_t wrap_dense(uint32_t idx, uint32_t size) {
+  return min(idx >= size ? idx - size : idx, size - 1u);
+}
+
 __device__ __forceinline__ uint32_t grid_index(const GridLevel& L, uint32_t gx, uint32_t gy, uint32_t gz) {
-  uint32_t idx;
-  if (L.hashed) {
-    idx = gx ^ (gy * kPrimeY) ^ (gz * kPrimeZ);
+  if (L.hashed) return ((gx ^ (gy * kPrimeY) ^ (gz * kPrimeZ)) & (L.size - 1u)) + L.offset;
+  return wrap_dense(gx + gy * L.res + gz * L.res * L.res, L.size) + L.offset;
+}
+
+// Level-type masks: bit l set = level l is hashed.  Kernels are instantiated for the reference configs' masks so
+// that the dense / hashed choice is resolved at compile time (no branches between the loads of different levels);
+// any other configuration runs the kRuntimeMask instantiation, which reads GridLevel::hashed.
+constexpr uint32_t kRuntimeMask = 0x80000000u;
+template <uint32_t MASK>
+__device__ __forceinline__ bool level_hashed(const GridLevel& L, int l) {
+  return (MASK & kRuntimeMask) ? (L.hashed != 0u) : (((MASK >> l) & 1u) != 0u);
+}
+
+// entry indices of the four (y,z) corners c = dy + 2*dz of a voxel for a fixed x coordinate
+__device__ __forceinline__ void corner_indices(const GridLevel& L, bool hashed, uint32_t gx, uint32_t gy, uint32_t gz,
+                                               uint32_t (&idx)[4]) {
+  if (hashed) {
+    const uint32_t m = L.size - 1u;
+    const uint32_t hy0 = gy * kPrimeY, hy1 = hy0 + kPrimeY;
+    const uint32_t hz0 = gz * kPrimeZ, hz1 = hz0 + kPrimeZ;
+    idx[0] = ((gx ^ hy0 ^ hz0) & m) + L.offset;
+    idx[1] = ((gx ^ hy1 ^ hz0) & m) + L.offset;
+    idx[2] = ((gx ^ hy0 ^ hz1) & m) + L.offset;
+    idx[3] = ((gx ^ hy1 ^ hz1) & m) + L.offset;
   } else {
-    idx = gx + gy * L.res + gz * L.res * L.res;
+    const uint32_t r = L.res, r2 = r * r;
+    const uint32_t b = gx + gy * r + gz * r2;
+    idx[0] = wrap_dense(b, L.size) + L.offset;
+    idx[1] = wrap_dense(b + r, L.size) + L.offset;
+    idx[2] = wrap_dense(b + r2, L.size) + L.offset;
+    idx[3] = wrap_dense(b + r + r2, L.size) + L.offset;
   }
-  return idx % L.size + L.offset;
+}
+inline uint32_t hashed_mask(const GridDev& g) {
+  uint32_t m = 0;
+  for (int l = 0; l < g.n_levels; ++l) m |= (g.lv[l].hashed ? 1u : 0u) << l;
+  return m;
 }
 
 // ---------------------------------------------------------------------------------------------

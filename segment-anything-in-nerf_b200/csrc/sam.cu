@@ -19,6 +19,10 @@
 namespace snrf {
 namespace {
 
+#ifndef SNRF_SAM_UNROLL
+#define SNRF_SAM_UNROLL 2
+#endif
+constexpr int kGatherUnroll = SNRF_SAM_UNROLL;  // levels in flight per lane (4 x 16-byte loads each)
 constexpr int kWarps = 16;
 constexpr int kThreads = kWarps * 32;
 constexpr int kRaysPerTile = 8;
@@ -50,7 +54,55 @@ __device__ __forceinline__ int halving_reduce16(float (&v)[32], int lane) {
   return base;
 }
 
-template <bool TC>
+// 12 levels x 4 (y,z) corners x 16 B for the sample this lane pair owns; writes this lane's 4 finished features of
+// every level (fp16) into the A tile.  MASK resolves dense / hashed per level at compile time, so the 48 loads of
+// a lane are independent straight-line code the scheduler can keep in flight together.
+template <uint32_t MASK>
+__device__ __forceinline__ void gather_f8(const GridDev& G, int k0, float x, float y, float z, int xb, int row,
+                                          unsigned char* a_tile, __half* dbg_row) {
+  const unsigned FULL = 0xffffffffu;
+#pragma unroll
+  for (int l = 0; l < 12; ++l) {
+    const GridLevel& L = G.lv[l];
+    const float qx = __fadd_rn(__fmul_rn(x, L.scale), 0.5f);
+    const float qy = __fadd_rn(__fmul_rn(y, L.scale), 0.5f);
+    const float qz = __fadd_rn(__fmul_rn(z, L.scale), 0.5f);
+    const float fx = floorf(qx), fy = floorf(qy), fz = floorf(qz);
+    const float rx = qx - fx, ry = qy - fy, rz = qz - fz;
+    const uint32_t gx = static_cast<uint32_t>(static_cast<int>(fx)) + xb;
+    const uint32_t gy = static_cast<uint32_t>(static_cast<int>(fy));
+    const uint32_t gz = static_cast<uint32_t>(static_cast<int>(fz));
+    const float wx = xb ? rx : 1.f - rx;
+    uint32_t idx[4];
+    uint4 v[4];
+    corner_indices(L, level_hashed<MASK>(L, l), gx, gy, gz, idx);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) v[c] = ldg_u128(G.table + 8 * static_cast<size_t>(idx[c]));
+    float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      float w = wx * ((c & 1) ? ry : 1.f - ry);
+      w *= ((c >> 1) ? rz : 1.f - rz);
+      const float2 f0 = h2_to_f2(v[c].x), f1 = h2_to_f2(v[c].y), f2 = h2_to_f2(v[c].z), f3 = h2_to_f2(v[c].w);
+      a[0] += w * f0.x; a[1] += w * f0.y; a[2] += w * f1.x; a[3] += w * f1.y;
+      a[4] += w * f2.x; a[5] += w * f2.y; a[6] += w * f3.x; a[7] += w * f3.y;
+    }
+    // lane xb=0 finishes features 0-3, lane xb=1 features 4-7
+    float o[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float send = xb ? a[i] : a[i + 4];
+      const float mine = xb ? a[i + 4] : a[i];
+      o[i] = mine + __shfl_xor_sync(FULL, send, 1);
+    }
+    const uint2 pk = make_uint2(f2_to_h2(o[0], o[1]), f2_to_h2(o[2], o[3]));
+    const uint32_t k = k0 + l * 8 + xb * 4;
+    *reinterpret_cast<uint2*>(a_tile + core_offset(row, k, kIn)) = pk;
+    if (dbg_row) *reinterpret_cast<uint2*>(dbg_row + k) = pk;
+  }
+}
+
+template <bool TC, uint32_t M0, uint32_t M1>
 __global__ void __launch_bounds__(kThreads, 1) sam_kernel(const SamParams P) {
   extern __shared__ __align__(128) unsigned char smem[];
   unsigned char* s_w1 = smem;
@@ -85,7 +137,6 @@ __global__ void __launch_bounds__(kThreads, 1) sam_kernel(const SamParams P) {
   const int64_t n_tiles = (P.n_rays + kRaysPerTile - 1) / kRaysPerTile;
   const int r_loc = warp & 7, e = warp >> 3;
   const int s16 = lane >> 1, xb = lane & 1;
-  const GridDev& G = P.enc[e];
 
   // ---- epilogue of one tile out of TMEM (tcgen05 engine) ---------------------------------------
   auto epilogue_tc = [&](int64_t tile, int buf, uint32_t parity) {
@@ -126,46 +177,10 @@ __global__ void __launch_bounds__(kThreads, 1) sam_kernel(const SamParams P) {
       const float pz = __fadd_rn(P.origins[3 * ray + 2], __fmul_rn(P.dirs[3 * ray + 2], tm2) / 2.f);
       float x, y, z, sel;
       contract_normalize(px, py, pz, false, false, x, y, z, sel);
-#pragma unroll 2
-      for (int l = 0; l < 12; ++l) {
-        const GridLevel L = G.lv[l];
-        const float qx = __fadd_rn(__fmul_rn(x, L.scale), 0.5f);
-        const float qy = __fadd_rn(__fmul_rn(y, L.scale), 0.5f);
-        const float qz = __fadd_rn(__fmul_rn(z, L.scale), 0.5f);
-        const float fx = floorf(qx), fy = floorf(qy), fz = floorf(qz);
-        const float rx = qx - fx, ry = qy - fy, rz = qz - fz;
-        const uint32_t gx = static_cast<uint32_t>(static_cast<int>(fx)) + xb;
-        const uint32_t gy = static_cast<uint32_t>(static_cast<int>(fy));
-        const uint32_t gz = static_cast<uint32_t>(static_cast<int>(fz));
-        const float wx = xb ? rx : 1.f - rx;
-        uint4 v[4];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const uint32_t idx = grid_index(L, gx, gy + (c & 1), gz + (c >> 1));
-          v[c] = ldg_u128(G.table + 8 * static_cast<size_t>(idx));
-        }
-        float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          float w = wx * ((c & 1) ? ry : 1.f - ry);
-          w *= ((c >> 1) ? rz : 1.f - rz);
-          const float2 f0 = h2_to_f2(v[c].x), f1 = h2_to_f2(v[c].y), f2 = h2_to_f2(v[c].z), f3 = h2_to_f2(v[c].w);
-          a[0] += w * f0.x; a[1] += w * f0.y; a[2] += w * f1.x; a[3] += w * f1.y;
-          a[4] += w * f2.x; a[5] += w * f2.y; a[6] += w * f3.x; a[7] += w * f3.y;
-        }
-        // lane xb=0 finishes features 0-3, lane xb=1 features 4-7
-        float o[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float send = xb ? a[i] : a[i + 4];
-          const float mine = xb ? a[i + 4] : a[i];
-          o[i] = mine + __shfl_xor_sync(FULL, send, 1);
-        }
-        const uint2 pk = make_uint2(f2_to_h2(o[0], o[1]), f2_to_h2(o[2], o[3]));
-        const uint32_t k = e * 96 + l * 8 + xb * 4;
-        *reinterpret_cast<uint2*>(a_tile + core_offset(row, k, kIn)) = pk;
-        if (P.dbg_feat) *reinterpret_cast<uint2*>(P.dbg_feat + (ray * kK + s16) * kIn + k) = pk;
-      }
+      if (e == 0)
+        gather_f8<M0>(P.enc[0], 0, x, y, z, xb, row, a_tile, P.dbg_feat ? P.dbg_feat + (ray * kK + s16) * kIn : nullptr);
+      else
+        gather_f8<M1>(P.enc[1], 96, x, y, z, xb, row, a_tile, P.dbg_feat ? P.dbg_feat + (ray * kK + s16) * kIn : nullptr);
     } else {
       // tail tile: keep the rows finite so the (discarded) accumulator rows are well defined
       if (e == 0 && xb == 0) s_sw[buf * 128 + row] = 0.f;
@@ -234,25 +249,35 @@ __global__ void __launch_bounds__(kThreads, 1) sam_kernel(const SamParams P) {
   }
 }
 
-}  // namespace
+// hashed-level masks of the shipped SAMField grids (sam_model.py:153-155): 16..128 at T=2^19 -> levels 9-11 hashed;
+// 128..512 -> all 12 levels hashed
+constexpr uint32_t kEnc0MaskStd = 0xE00u, kEnc1MaskStd = 0xFFFu;
 
-cudaError_t launch_sam(const SamParams& P, bool tcgen05, int sm_count, cudaStream_t stream) {
+template <bool TC, uint32_t M0, uint32_t M1>
+static cudaError_t launch_one(const SamParams& P, int grid, cudaStream_t stream) {
   static bool configured = false;
+  auto* k = sam_kernel<TC, M0, M1>;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(sam_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(sam_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
     if (e != cudaSuccess) return e;
     configured = true;
   }
+  k<<<grid, kThreads, kSmemBytes, stream>>>(P);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t launch_sam(const SamParams& P, bool tcgen05, int sm_count, cudaStream_t stream) {
   if (P.n_rays <= 0) return cudaSuccess;
   const int64_t n_tiles = (P.n_rays + kRaysPerTile - 1) / kRaysPerTile;
   const int grid = static_cast<int>(n_tiles < sm_count ? n_tiles : sm_count);  // persistent: one CTA per SM
+  const bool std_cfg = hashed_mask(P.enc[0]) == kEnc0MaskStd && hashed_mask(P.enc[1]) == kEnc1MaskStd;
   if (tcgen05)
-    sam_kernel<true><<<grid, kThreads, kSmemBytes, stream>>>(P);
-  else
-    sam_kernel<false><<<grid, kThreads, kSmemBytes, stream>>>(P);
-  return cudaGetLastError();
+    return std_cfg ? launch_one<true, kEnc0MaskStd, kEnc1MaskStd>(P, grid, stream)
+                   : launch_one<true, kRuntimeMask, kRuntimeMask>(P, grid, stream);
+  return std_cfg ? launch_one<false, kEnc0MaskStd, kEnc1MaskStd>(P, grid, stream)
+                 : launch_one<false, kRuntimeMask, kRuntimeMask>(P, grid, stream);
 }
 
 }  // namespace snrf

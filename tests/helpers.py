@@ -55,6 +55,26 @@ def assert_mostly_close(a, b, tol: Dict[str, float], frac: float, what: str, per
     return got
 
 
+def assert_features_close(a, b, what: str, row_frac: float = FRAC_DISCRETE, elem_frac: float = 0.99,
+                          rel_l2: float = 2e-2, tol=None):
+    """Feature maps: (1) elementwise TOL["features"] for >= elem_frac of all elements and (2) per-ray relative L2
+    error <= rel_l2 for >= row_frac of the rays.  The sharpening w**10 multiplies a relative weight error by 10
+    (a 1e-3 density wobble becomes a 1e-2 wobble of the mixing weights), so single channels of a ray can leave
+    the elementwise band while the feature vector as a whole stays within 2 %."""
+    tol = tol or TOL["features"]
+    a = torch.as_tensor(a).detach().float().cpu()
+    b = torch.as_tensor(b).detach().float().cpu()
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    assert_mostly_close(a, b, tol, elem_frac, what + " (elementwise)")
+    a2, b2 = a.reshape(-1, a.shape[-1]), b.reshape(-1, b.shape[-1])
+    nan_rows = torch.isnan(a2).any(-1) & torch.isnan(b2).any(-1)
+    rel = torch.linalg.norm(torch.nan_to_num(a2 - b2), dim=-1) / torch.linalg.norm(torch.nan_to_num(b2), dim=-1).clamp_min(1e-6)
+    ok = (rel <= rel_l2) | nan_rows
+    got = float(ok.float().mean())
+    assert got >= row_frac, f"{what}: only {got:.5f} of rays within relative L2 {rel_l2} (need {row_frac}); median {float(rel.median()):.2e}"
+    return got
+
+
 def error_stats(a, b) -> str:
     a = torch.as_tensor(a).detach().float().cpu()
     b = torch.as_tensor(b).detach().float().cpu()

@@ -9,7 +9,8 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import (FRAC_DISCRETE, FRAC_SMOOTH, TOL, assert_mostly_close, make_renderer, model_pair, test_rays)
+from helpers import (FRAC_DISCRETE, FRAC_SMOOTH, TOL, assert_features_close, assert_mostly_close, make_renderer,
+                     model_pair, test_rays)
 
 pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
@@ -88,9 +89,9 @@ def test_render_stages(which, regime):
     sw_ref = torch.sort(ref["_sam_weights"], dim=-1, descending=True).values
     sw_gpu = torch.sort(out["_sam_w"].cpu(), dim=-1, descending=True).values
     assert_mostly_close(sw_gpu, sw_ref, dict(rtol=5e-2, atol=2e-3), FRAC_DISCRETE, "sharpened top-k weights", per_row=True)
-    assert_mostly_close(out["sam"], ref["sam"], TOL["features"], FRAC_DISCRETE, "sam feature", per_row=True)
+    assert_features_close(out["sam"], ref["sam"], "sam feature")
     if cfg.use_clipseg_feature:
-        assert_mostly_close(out["clipseg"], ref["clipseg"], TOL["features"], FRAC_DISCRETE, "clipseg feature", per_row=True)
+        assert_features_close(out["clipseg"], ref["clipseg"], "clipseg feature")
 
 
 @pytest.mark.parametrize("engine", ["tcgen05", "mma_sync"])
@@ -101,8 +102,8 @@ def test_engines_agree_with_oracle(engine):
     o, d = test_rays(515, seed=9)  # not a multiple of 8: exercises the tail tile of the feature kernel
     ref = orc.render_rays(o, d, get_feature=("sam", "clipseg"))
     out = r.render(o, d, get_feature=("sam", "clipseg"))
-    assert_mostly_close(out["sam"], ref["sam"], TOL["features"], FRAC_DISCRETE, f"sam[{engine}]", per_row=True)
-    assert_mostly_close(out["clipseg"], ref["clipseg"], TOL["features"], FRAC_DISCRETE, f"clipseg[{engine}]", per_row=True)
+    assert_features_close(out["sam"], ref["sam"], f"sam[{engine}]")
+    assert_features_close(out["clipseg"], ref["clipseg"], f"clipseg[{engine}]")
 
 
 # ---- golden fixtures produced by the reference's own Python (oracle/make_golden.py) ----------------------------
@@ -124,10 +125,13 @@ def test_golden_chunks(name):
     assert_mostly_close(out["accumulation"], z["accumulation"], TOL["accumulation"], 0.99, "accumulation")
     assert_mostly_close(out["depth"], z["depth"], TOL["depth"], 0.95, "depth")
     assert_mostly_close(out["prop_depth_0"], z["prop_depth_0"], TOL["depth"], 0.95, "prop depth")
-    ftol = TOL["features"] if cfg.patch_size == 1 else dict(rtol=3e-2, atol=3e-3)
-    assert_mostly_close(out["sam"], z["sam"], ftol, 0.93 if cfg.patch_size == 1 else 0.6, "sam", per_row=True)
+    if cfg.patch_size == 1:
+        assert_features_close(out["sam"], z["sam"], "sam", row_frac=0.95)
+    else:  # 16 patch-aggregated rows: one flipped ray moves a whole row, so allow 2 of 16
+        assert_features_close(out["sam"], z["sam"], "sam", row_frac=0.85, elem_frac=0.9, rel_l2=3e-2,
+                              tol=dict(rtol=3e-2, atol=3e-3))
     if "clipseg" in z.files:
-        assert_mostly_close(out["clipseg"], z["clipseg"], TOL["features"], 0.93, "clipseg", per_row=True)
+        assert_features_close(out["clipseg"], z["clipseg"], "clipseg", row_frac=0.95)
 
 
 def test_golden_image_through_model_shim():
@@ -150,8 +154,9 @@ def test_golden_image_through_model_shim():
     assert_mostly_close(out["rgb"], z["rgb"], TOL["rgb"], 0.99, "rgb", per_row=False)
     assert_mostly_close(out["depth"], z["depth"], TOL["depth"], 0.95, "depth")
     st = int(z["_sam_stride"])
-    assert_mostly_close(out["sam"][::st, ::st], z["sam"], dict(rtol=3e-2, atol=3e-3), 0.97, "patch-aggregated sam")
-    assert_mostly_close(out["clipseg"], z["clipseg"], TOL["features"], 0.97, "clipseg")
+    assert_features_close(out["sam"][::st, ::st], z["sam"], "patch-aggregated sam", row_frac=0.95, elem_frac=0.97,
+                          rel_l2=3e-2, tol=dict(rtol=3e-2, atol=3e-3))
+    assert_features_close(out["clipseg"], z["clipseg"], "clipseg", row_frac=0.95)
 
 
 # ---- patch aggregation kernel on its own -----------------------------------------------------------------------
