@@ -45,6 +45,17 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(rays_per_launch: float):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed ncu capture, scaled
+    to this run's rays per launch (None when no capture is committed)."""
+    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if not os.path.exists(path):
+        return None
+    with open(path) as f:
+        t = json.load(f)["sam_kernel"]
+    return (t["dram_bytes_read"] + t["dram_bytes_write"]) * rays_per_launch / t["rays_per_launch"]
+
+
 class ClockSampler:
     """nvidia-smi clock / throttle-reason samples taken DURING the timed region."""
 
@@ -200,11 +211,13 @@ def run_native(args):
     mine = {k: v[lo:lo + n_loc] for k, v in full.items()}
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
+    from samnerf_b200.tiles import all_gather_tiles, ray_block
+
+    assert ray_block(rank, world, H, W) == (lo, lo + n_loc)
+
     def frame():
         r.render_frame(o_dev, d_dev, get_feature=("sam",), chunk=chunk, out=mine)
-        if world > 1:
-            for k in names:
-                dist.all_gather_into_tensor(full[k], mine[k])
+        all_gather_tiles(full, H, W) if world > 1 else None
 
     def barrier():
         if world > 1:
@@ -302,7 +315,10 @@ def run_native(args):
                        "tiles": f"{world} row block(s) of {H // world} rows + NCCL all-gather" if world > 1 else "single GPU"},
             "roofline": {"bound": "hbm", "kernel": "sam_kernel (feature-field gather + MLP layer 1 + weighted sum)",
                          "achieved": ach, "peak": peak, "unit": "GB/s", "frac": (ach / peak) if ach else None,
-                         "traffic": None, "peak_source": peak_src,
+                         "traffic": ncu_traffic(rays_per_launch), "peak_source": peak_src,
+                         "traffic_note": "ncu dram bytes of one launch (profiles/r01_traffic.json): far below the "
+                                         "algorithmic bytes - the launch's table footprint is L2/L1-resident; the kernel "
+                                         "is bound by the L1 tag stage and issue, not HBM (DESIGN.md section 4 B)",
                          "algorithmic_bytes_per_launch": BYTES_PER_RAY["sam"] * rays_per_launch,
                          "avg_launch_ms": f_ms / max(f_cnt, 1), "launches_timed": f_cnt,
                          "path": {"bytes_per_ray": path_bytes, "achieved": value * 1e6 * path_bytes / 1e9 / world,
