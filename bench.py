@@ -203,21 +203,56 @@ def run_native(args):
     o_host = o_all[lo:lo + n_loc].contiguous().pin_memory()
     d_host = d_all[lo:lo + n_loc].contiguous().pin_memory()
     o_dev, d_dev = o_host.to(dev), d_host.to(dev)
-    chunk = cfg.eval_num_rays_per_chunk
+    # reference chunk size on one GPU; with N ranks the tile is cut finer so that the NVLink exchange of chunk c
+    # overlaps the compute of chunk c+1 (the chunk size is caller-tunable in the reference too, eval_utils.py:90-91)
+    chunk = args.chunk or (cfg.eval_num_rays_per_chunk if world == 1 else
+                           min(cfg.eval_num_rays_per_chunk, max(4096, (n_loc // 8 + 1023) // 1024 * 1024)))
 
     # frame-sized outputs; with N > 1 each rank renders into its row block of the gathered frame (in-place all-gather)
     names = {"rgb": 3, "depth": 1, "accumulation": 1, "prop_depth_0": 1, "sam": cfg.sam_out}
-    full = {k: torch.empty(n_all, c, device=dev) for k, c in names.items()}
+    # With N > 1 the rendered tiles are exchanged by the kernels themselves: every output row is stored into every
+    # rank's frame buffer over NVLink (one multimem.st through the NVSwitch multicast alias when available, else
+    # peer-mapped pointers), overlapped with the next chunk's compute; a symmetric-memory barrier ends the frame.
+    # Fallback / comparison: NCCL all-gather of the rendered tiles (--gather nccl).
+    gather_mode, symm, full = "single", None, {}
+    if world > 1:
+        gather_mode = "nccl"
+        if args.gather != "nccl":
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+
+                big = symm_mem.empty(n_all * sum(names.values()), dtype=torch.float32, device=dev)
+                symm = symm_mem.rendezvous(big, dist.group.WORLD.group_name)
+                mc = int(getattr(symm, "multicast_ptr", 0) or 0) if args.gather in ("auto", "mc") else 0
+                off = 0
+                for k, c in names.items():
+                    full[k] = big[off:off + n_all * c].view(n_all, c)
+                    peers = [int(symm.buffer_ptrs[p]) + off * 4 for p in range(world) if p != rank]
+                    r.set_replication(k, full[k], () if mc else peers, mc + off * 4 if mc else 0)
+                    off += n_all * c
+                gather_mode = "fused multimem.st (NVSwitch multicast)" if mc else "fused peer stores (NVLink P2P)"
+            except Exception as e:  # no symmetric memory on this box: say so and use NCCL
+                if rank == 0:
+                    print(f"[bench] symmetric memory unavailable ({type(e).__name__}: {e}); using NCCL all-gather", file=sys.stderr)
+                symm, gather_mode, full = None, "nccl", {}
+    for k, c in names.items():
+        if k not in full:
+            full[k] = torch.empty(n_all, c, device=dev)
     mine = {k: v[lo:lo + n_loc] for k, v in full.items()}
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     from samnerf_b200.tiles import all_gather_tiles, ray_block
 
     assert ray_block(rank, world, H, W) == (lo, lo + n_loc)
+    r.set_pipeline(0 if args.no_pipeline else 1)
 
     def frame():
         r.render_frame(o_dev, d_dev, get_feature=("sam",), chunk=chunk, out=mine)
-        all_gather_tiles(full, H, W) if world > 1 else None
+        if world > 1:
+            if symm is not None:
+                symm.barrier()  # every rank's stores have landed in every frame buffer
+            else:
+                all_gather_tiles(full, H, W)
 
     def barrier():
         if world > 1:
@@ -227,6 +262,15 @@ def run_native(args):
     for _ in range(max(args.warmup, 3)):
         frame()
     barrier()
+    if world > 1:
+        # every rank must now hold the same complete frame: compare per-tile checksums across ranks (untimed)
+        sums = torch.stack([full["sam"][p * n_loc:(p + 1) * n_loc].double().nan_to_num().abs().sum() for p in range(world)]
+                           + [full["rgb"].double().sum()])
+        allsums = [torch.empty_like(sums) for _ in range(world)]
+        dist.all_gather(allsums, sums)
+        for p in range(1, world):
+            if not torch.equal(allsums[0], allsums[p]) or float(allsums[0].min()) <= 0.0:
+                raise SystemExit(f"tile exchange ({gather_mode}) is wrong: rank 0 {allsums[0].tolist()} vs rank {p} {allsums[p].tolist()}")
     r.kernel_times()
     r.set_timing(True)
     launches0 = r.launch_count
@@ -312,7 +356,9 @@ def run_native(args):
             "scaling": "strong", "vs_baseline": None, "dtype": "f16 operands / f32 accumulate", "data": "synthetic",
             "config": {"workload": WORKLOAD, "regime": args.regime, "engine": args.engine,
                        "l2": "256 MiB buffer zeroed between timed frames (untimed); tables 158 MB + outputs 668 MB > 126 MB L2",
-                       "tiles": f"{world} row block(s) of {H // world} rows + NCCL all-gather" if world > 1 else "single GPU"},
+                       "tiles": (f"{world} row blocks of {H // world} rows; 256-d features exchanged by {gather_mode}, "
+                                 "frame ends with a symmetric-memory barrier") if world > 1 else "single GPU",
+                       "chunk": chunk, "pipeline": "chunks pipelined over 3 streams" if (world > 1 and symm is not None and not args.no_pipeline) else "sequential"},
             "roofline": {"bound": "hbm", "kernel": "sam_kernel (feature-field gather + MLP layer 1 + weighted sum)",
                          "achieved": ach, "peak": peak, "unit": "GB/s", "frac": (ach / peak) if ach else None,
                          "traffic": ncu_traffic(rays_per_launch), "peak_source": peak_src,
@@ -346,6 +392,10 @@ def main():
     ap.add_argument("--impl", choices=["native", "reference"], default="native")
     ap.add_argument("--regime", choices=["scene", "init"], default="scene")
     ap.add_argument("--engine", choices=["tcgen05", "mma_sync"], default="tcgen05")
+    ap.add_argument("--gather", choices=["auto", "mc", "peer", "nccl"], default="auto",
+                    help="N > 1: how the feature tiles are exchanged (fused multicast / peer stores, or NCCL)")
+    ap.add_argument("--chunk", type=int, default=0, help="rays per chunk (default: 32768, finer with N > 1)")
+    ap.add_argument("--no-pipeline", action="store_true", help="run the chunks strictly one after another on one stream")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-rays", type=int, default=16384)
     ap.add_argument("--ref-rays", type=int, default=4096)

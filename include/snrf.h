@@ -142,6 +142,31 @@ int snrf_query_features(snrf_ctx* ctx, int which, const float* xyz, int64_t n, v
 int snrf_ray_op(snrf_ctx* ctx, int mode, const float* a, const float* b, const float* c, float* out, int64_t n, int S,
                 int C, int bg_mode, const float* bg_host, void* stream);
 
+/* Whole frame (or this rank's tile of it): n_rays rays in chunks of `chunk` (the reference's
+ * eval_num_rays_per_chunk, sam_model.py:354-364), same outputs as snrf_render over all rays.  When pipelining is
+ * active the three stages of a chunk run on three streams inside the library, so chunk c+1's march overlaps chunk
+ * c's feature gather and its output layer (whose replicated stores are NVLink-bound); the caller's stream resumes
+ * only after every chunk is complete, so the call is stream-ordered like any other. */
+int snrf_render_frame(snrf_ctx* ctx, const float* origins, const float* dirs, const float* nears, const float* fars,
+                      int64_t n_rays, int64_t chunk, uint32_t flags, const snrf_render_opts* opts, float* rgb,
+                      float* depth, float* acc, float* prop_depth, float* sam, float* clipseg, void* stream);
+/* chunk pipelining of snrf_render_frame: 0 = off (strictly sequential on the caller's stream), 1 = auto (default:
+ * only when outputs are replicated to other ranks - on one GPU the stages cannot share an SM, so it gains nothing),
+ * 2 = always */
+int snrf_set_pipeline(snrf_ctx* ctx, int enable);
+
+/* ---- multi-GPU: fused tile all-gather (SURVEY.md 8 e; the reference has no multi-GPU render) -------------
+ * When a frame is cut into row blocks across ranks, the kernels can store every output row they produce not only
+ * into this rank's frame buffer but, at the same byte offset, into every other rank's frame buffer, so the
+ * all-gather of the rendered tiles rides on the kernels' own stores over NVLink instead of a separate collective.
+ * which: 0 sam[.,256], 1 rgb[.,3], 2 depth, 3 accumulation, 4 prop_depth.  local_base / bytes: this rank's frame
+ * buffer (output pointers later passed to snrf_render* must lie inside it for the replication to apply).
+ * mc_base: NVSwitch multicast alias of that buffer (one multimem.st reaches every rank) or NULL;
+ * peer_bases_host[n_peers]: peer-mapped aliases on the other ranks, used when mc_base is NULL.  The caller
+ * synchronises the ranks after the frame (e.g. a symmetric-memory barrier).  local_base NULL clears. */
+int snrf_set_replication(snrf_ctx* ctx, int which, void* local_base, int64_t bytes, void* mc_base,
+                         void* const* peer_bases_host, int n_peers);
+
 /* number of kernels this library has launched on ctx since creation (bench.py's gpu_launches) */
 int64_t snrf_launch_count(snrf_ctx* ctx);
 /* Bracket the three hot kernels of snrf_render with CUDA events on the launching stream (bench.py's roofline). */

@@ -68,6 +68,9 @@ SYMBOLS = {
     "snrf_query_rgb": (_I, [_P, _P, _P, _L, _P, _P]),
     "snrf_query_features": (_I, [_P, _I, _P, _L, _P, _P, _P]),
     "snrf_ray_op": (_I, [_P, _I, _P, _P, _P, _P, _L, _I, _I, _I, _P, _P]),
+    "snrf_render_frame": (_I, [_P, _P, _P, _P, _P, _L, _L, _U, C.POINTER(RenderOpts), _P, _P, _P, _P, _P, _P, _P]),
+    "snrf_set_pipeline": (_I, [_P, _I]),
+    "snrf_set_replication": (_I, [_P, _I, _P, _L, _P, C.POINTER(C.c_void_p), _I]),
     "snrf_launch_count": (_L, [_P]),
     "snrf_set_timing": (_I, [_P, _I]),
     "snrf_kernel_times": (_I, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),

@@ -3,6 +3,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -36,6 +37,14 @@ struct DevBuf {
   T* as() const {
     return reinterpret_cast<T*>(p);
   }
+};
+
+struct Replication {
+  float* local = nullptr;
+  size_t bytes = 0;
+  float* mc = nullptr;
+  float* peer[kMaxPeers] = {nullptr};
+  int n = 0;
 };
 
 struct FeatureNet {
@@ -75,9 +84,17 @@ struct snrf_ctx {
   std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> ev_used;
   double k_ms[3] = {0, 0, 0};
   int64_t k_count[3] = {0, 0, 0};
+  // fused tile all-gather (snrf_set_replication): 0 sam, 1 rgb, 2 depth, 3 accumulation, 4 prop_depth
+  Replication rep[5];
+  // frame-level pipelining (snrf_render_frame)
+  int pipeline = 1;  // 0 off, 1 auto (only when outputs are replicated to other ranks), 2 always
+  bool aux_ready = false;
+  cudaStream_t aux_feat = nullptr, aux_out = nullptr;
+  cudaEvent_t ev_march[2] = {nullptr, nullptr}, ev_feat[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+  cudaEvent_t ev_feat_done[2] = {nullptr, nullptr}, ev_out_done[2] = {nullptr, nullptr}, ev_join = nullptr, ev_join2 = nullptr;
   // misc
   DevBuf pdf_u;
-  DevBuf sam_t, sam_w, hbar, feat_f16, hid_f16, q_feat, q_h1, q_h2, q_sel, q_x;
+  DevBuf sam_t[2], sam_w[2], hbar[2][2], feat_f16, hid_f16, q_feat, q_h1, q_h2, q_sel, q_x;
 };
 
 namespace {
@@ -230,6 +247,14 @@ int snrf_ctx_create(int device, snrf_ctx** out) {
     delete ctx;
     return SNRF_E_CUDA;
   }
+  cudaEvent_t* evs[] = {&ctx->ev_march[0], &ctx->ev_march[1], &ctx->ev_feat[0][0], &ctx->ev_feat[0][1], &ctx->ev_feat[1][0],
+                        &ctx->ev_feat[1][1], &ctx->ev_feat_done[0], &ctx->ev_feat_done[1], &ctx->ev_out_done[0],
+                        &ctx->ev_out_done[1], &ctx->ev_join, &ctx->ev_join2};
+  for (cudaEvent_t* e : evs)
+    if (cudaEventCreateWithFlags(e, cudaEventDisableTiming) != cudaSuccess) {
+      delete ctx;
+      return SNRF_E_CUDA;
+    }
   *out = ctx;
   return SNRF_OK;
 }
@@ -240,11 +265,15 @@ void snrf_ctx_destroy(snrf_ctx* ctx) {
   cudaDeviceSynchronize();
   DevBuf* bufs[] = {&ctx->prop_table, &ctx->prop_w1f,   &ctx->prop_w2f,   &ctx->prop_w1_rm, &ctx->prop_w2_rm,
                     &ctx->field_table, &ctx->base_w1_rm, &ctx->base_w2_rm, &ctx->head_w1_rm, &ctx->head_w2_rm,
-                    &ctx->head_w3_rm, &ctx->wfrag,      &ctx->head_perm,  &ctx->pdf_u,      &ctx->sam_t,
-                    &ctx->sam_w,      &ctx->hbar,       &ctx->feat_f16,   &ctx->hid_f16,    &ctx->q_feat,
+                    &ctx->head_w3_rm, &ctx->wfrag,      &ctx->head_perm,  &ctx->pdf_u,      &ctx->sam_t[0],
+                    &ctx->sam_w[0],   &ctx->hbar[0][0], &ctx->feat_f16,   &ctx->hid_f16,    &ctx->q_feat,
                     &ctx->q_h1,       &ctx->q_h2,       &ctx->q_sel,      &ctx->q_x,        &ctx->conv_w[0],
                     &ctx->conv_w[1],  &ctx->conv_b[0],  &ctx->conv_b[1]};
   for (DevBuf* b : bufs) b->release();
+  ctx->sam_t[1].release(); ctx->sam_w[1].release();
+  ctx->hbar[0][1].release(); ctx->hbar[1][0].release(); ctx->hbar[1][1].release();
+  if (ctx->aux_feat) cudaStreamDestroy(ctx->aux_feat);
+  if (ctx->aux_out) cudaStreamDestroy(ctx->aux_out);
   for (auto& u : ctx->ev_used) {
     cudaEventDestroy(u.second.first);
     cudaEventDestroy(u.second.second);
@@ -274,6 +303,28 @@ int snrf_set_pdf_u(snrf_ctx* ctx, const float* u_host, int n) {
 }
 
 int64_t snrf_launch_count(snrf_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int snrf_set_replication(snrf_ctx* ctx, int which, void* local_base, int64_t bytes, void* mc_base,
+                         void* const* peer_bases_host, int n_peers) {
+  if (!ctx) return SNRF_E_INVALID;
+  if (which < 0 || which > 4 || n_peers < 0 || n_peers > kMaxPeers || (n_peers > 0 && !peer_bases_host) || bytes < 0)
+    return fail(ctx, SNRF_E_INVALID, "bad replication descriptor");
+  Replication& R = ctx->rep[which];
+  R = Replication();
+  if (!local_base || (n_peers == 0 && !mc_base)) return SNRF_OK;  // cleared
+  R.local = reinterpret_cast<float*>(local_base);
+  R.bytes = static_cast<size_t>(bytes);
+  R.mc = reinterpret_cast<float*>(mc_base);
+  R.n = n_peers;
+  for (int i = 0; i < n_peers; ++i) R.peer[i] = reinterpret_cast<float*>(peer_bases_host[i]);
+  return SNRF_OK;
+}
+
+int snrf_set_pipeline(snrf_ctx* ctx, int enable) {
+  if (!ctx) return SNRF_E_INVALID;
+  ctx->pipeline = enable < 0 ? 0 : (enable > 2 ? 2 : enable);
+  return SNRF_OK;
+}
 
 int snrf_set_timing(snrf_ctx* ctx, int enable) {
   if (!ctx) return SNRF_E_INVALID;
@@ -536,11 +587,35 @@ int snrf_patch_aggregate(snrf_ctx* ctx, const float* feat_in, int64_t n_patches,
   return SNRF_OK;
 }
 
-int snrf_render(snrf_ctx* ctx, const float* origins, const float* dirs, const float* nears, const float* fars,
-                int64_t n_rays, uint32_t flags, const snrf_render_opts* opts, float* rgb, float* depth, float* acc,
-                float* prop_depth, float* sam, float* clipseg, const snrf_debug_out* dbg, void* stream) {
-  if (!ctx) return SNRF_E_INVALID;
-  if (n_rays < 0) return fail(ctx, SNRF_E_INVALID, "negative ray count");
+// Streams of one chunk.  Plain snrf_render runs everything on the caller's stream; snrf_render_frame spreads the
+// three stages over three streams so that chunk c+1's march overlaps chunk c's feature gather and output layer.
+struct ChunkStreams {
+  cudaStream_t march, feat, out;
+  int slot;        // which copy of the per-chunk scratch (sam_t / sam_w / hbar) to use
+  int out_grid;    // CTA cap of the output-layer kernel (0 = one per SM)
+};
+
+// offset-preserving aliases of an output pointer in the other ranks' frame buffers (snrf_set_replication)
+static void replicate(const snrf_ctx* ctx, int which, const float* out, int64_t n_floats, float** mc, float** peers,
+                      int* n_peers) {
+  *mc = nullptr;
+  *n_peers = 0;
+  const Replication& R = ctx->rep[which];
+  const char* lo = reinterpret_cast<const char*>(R.local);
+  const char* p = reinterpret_cast<const char*>(out);
+  if (!R.local || !out || p < lo || p + n_floats * sizeof(float) > lo + R.bytes) return;
+  const int64_t off = (p - lo) / static_cast<int64_t>(sizeof(float));
+  if (R.mc) {
+    *mc = R.mc + off;
+  } else {
+    *n_peers = R.n;
+    for (int i = 0; i < R.n; ++i) peers[i] = R.peer[i] + off;
+  }
+}
+
+static int render_chunk(snrf_ctx* ctx, const float* origins, const float* dirs, const float* nears, const float* fars,
+                        int64_t n_rays, uint32_t flags, const snrf_render_opts* opts, float* rgb, float* depth, float* acc,
+                        float* prop_depth, float* sam, float* clipseg, const snrf_debug_out* dbg, const ChunkStreams& cs) {
   if (n_rays == 0) return SNRF_OK;  // empty chunk: nothing to read or write, pointers may be null
   if (!origins || !dirs || !opts || !rgb || !depth) return fail(ctx, SNRF_E_INVALID, "null argument");
   if (!ctx->have_base || !ctx->have_head) return fail(ctx, SNRF_E_STATE, "nerfacto field parameters not uploaded");
@@ -552,8 +627,7 @@ int snrf_render(snrf_ctx* ctx, const float* origins, const float* dirs, const fl
     return fail(ctx, SNRF_E_INVALID, "num_sam_samples %d unsupported (the feature kernel is built for k = 16)", opts->k_sam);
   if (patch && (!want_sam || opts->patch_size != 4 || n_rays % 16 != 0))
     return fail(ctx, SNRF_E_INVALID, "SNRF_PATCH needs SNRF_WANT_SAM, patch_size 4 and a ray count divisible by 16");
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
-  CK(cudaSetDevice(ctx->device));
+  const int slot = cs.slot;
 
   MarchParams M;
   int rc = fill_march(ctx, M, origins, dirs, nears, fars, n_rays, opts);
@@ -562,12 +636,16 @@ int snrf_render(snrf_ctx* ctx, const float* origins, const float* dirs, const fl
   M.depth = depth;
   M.acc = acc;
   M.prop_depth = prop_depth;
+  replicate(ctx, 1, rgb, n_rays * 3, &M.rep[0].mc, M.rep[0].peer, &M.rep[0].n);
+  replicate(ctx, 2, depth, n_rays, &M.rep[1].mc, M.rep[1].peer, &M.rep[1].n);
+  replicate(ctx, 3, acc, n_rays, &M.rep[2].mc, M.rep[2].peer, &M.rep[2].n);
+  replicate(ctx, 4, prop_depth, n_rays, &M.rep[3].mc, M.rep[3].peer, &M.rep[3].n);
   const bool feats = want_sam || want_clip;
   if (feats || (dbg && dbg->sam_t)) {
-    CK(ctx->sam_t.ensure(n_rays * 16 * 4));
-    CK(ctx->sam_w.ensure(n_rays * 16 * 4));
-    M.sam_t = ctx->sam_t.as<float>();
-    M.sam_w = ctx->sam_w.as<float>();
+    CK(ctx->sam_t[slot].ensure(n_rays * 16 * 4));
+    CK(ctx->sam_w[slot].ensure(n_rays * 16 * 4));
+    M.sam_t = ctx->sam_t[slot].as<float>();
+    M.sam_w = ctx->sam_w[slot].as<float>();
   }
   if (dbg) {
     M.dbg_w0 = dbg->prop_weights;
@@ -576,17 +654,23 @@ int snrf_render(snrf_ctx* ctx, const float* origins, const float* dirs, const fl
     M.dbg_density = dbg->density;
     M.dbg_rgb = dbg->rgb_samples;
   }
-  TIMED_LAUNCH(0, s, launch_march(M, ctx->sm_count, s));
+  TIMED_LAUNCH(0, cs.march, launch_march(M, ctx->sm_count, cs.march));
   if (dbg && dbg->sam_t) {
-    CK(cudaMemcpyAsync(dbg->sam_t, M.sam_t, n_rays * 16 * 4, cudaMemcpyDeviceToDevice, s));
-    if (dbg->sam_w) CK(cudaMemcpyAsync(dbg->sam_w, M.sam_w, n_rays * 16 * 4, cudaMemcpyDeviceToDevice, s));
+    CK(cudaMemcpyAsync(dbg->sam_t, M.sam_t, n_rays * 16 * 4, cudaMemcpyDeviceToDevice, cs.march));
+    if (dbg->sam_w) CK(cudaMemcpyAsync(dbg->sam_w, M.sam_w, n_rays * 16 * 4, cudaMemcpyDeviceToDevice, cs.march));
+  }
+  if (!feats) return SNRF_OK;
+  if (cs.feat != cs.march) {
+    CK(cudaEventRecord(ctx->ev_march[slot], cs.march));
+    CK(cudaStreamWaitEvent(cs.feat, ctx->ev_march[slot], 0));
   }
   for (int which = 0; which < 2; ++which) {
     if (!(which == 0 ? want_sam : want_clip)) continue;
     FeatureNet& f = ctx->feat[which];
     if (!f.have_grid[0] || !f.have_grid[1] || !f.have_net)
       return fail(ctx, SNRF_E_STATE, "%s parameters not uploaded", which == 0 ? "sam_field" : "clipseg");
-    CK(ctx->hbar.ensure(n_rays * 256 * 2));
+    DevBuf& hbar = ctx->hbar[slot][which];
+    CK(hbar.ensure(n_rays * 256 * 2));
     SamParams S;
     memset(&S, 0, sizeof(S));
     S.origins = origins;
@@ -597,16 +681,21 @@ int snrf_render(snrf_ctx* ctx, const float* origins, const float* dirs, const fl
     S.enc[0] = f.grid[0];
     S.enc[1] = f.grid[1];
     S.w1 = f.w1_core.as<__half>();
-    S.hbar = ctx->hbar.as<__half>();
+    S.hbar = hbar.as<__half>();
     S.dbg_feat = (which == 0 && dbg) ? reinterpret_cast<__half*>(dbg->sam_feat) : nullptr;
-    TIMED_LAUNCH(1, s, launch_sam(S, ctx->engine == 1, ctx->sm_count, s));
+    TIMED_LAUNCH(1, cs.feat, launch_sam(S, ctx->engine == 1, ctx->sm_count, cs.feat));
+    if (cs.out != cs.feat) {
+      CK(cudaEventRecord(ctx->ev_feat[slot][which], cs.feat));
+      CK(cudaStreamWaitEvent(cs.out, ctx->ev_feat[slot][which], 0));
+    }
     GemmParams G;
     memset(&G, 0, sizeof(G));
-    G.a = ctx->hbar.as<__half>();
+    G.a = hbar.as<__half>();
     G.w = f.w2_core.as<__half>();
     G.m = n_rays;
     G.n = f.n_out;
     G.taps = 1;
+    const int out_sms = cs.out_grid > 0 && cs.out_grid < ctx->sm_count ? cs.out_grid : ctx->sm_count;
     const bool to_patch = which == 0 && patch;
     if (to_patch) {
       CK(ctx->feat_f16.ensure(n_rays * 256 * 2));
@@ -615,8 +704,10 @@ int snrf_render(snrf_ctx* ctx, const float* origins, const float* dirs, const fl
     } else {
       G.out_f32 = which == 0 ? sam : clipseg;
       G.out_mode = 0;
+      // fused tile all-gather: mirror the rows into the other ranks' frame buffers at the same offset
+      if (which == 0) replicate(ctx, 0, sam, n_rays * 256, &G.out_mc, G.out_peer, &G.n_peers);
     }
-    TIMED_LAUNCH(2, s, launch_tapgemm(G, ctx->engine == 1, ctx->sm_count, s));
+    TIMED_LAUNCH(2, cs.out, launch_tapgemm(G, ctx->engine == 1, out_sms, cs.out));
     if (to_patch) {
       if (!ctx->have_conv) return fail(ctx, SNRF_E_STATE, "conv head parameters not uploaded");
       CK(ctx->hid_f16.ensure(n_rays * 256 * 2));
@@ -627,15 +718,85 @@ int snrf_render(snrf_ctx* ctx, const float* origins, const float* dirs, const fl
       C.bias = ctx->conv_b[0].as<float>();
       C.out_f16 = ctx->hid_f16.as<__half>();
       C.m = n_rays; C.n = 256; C.taps = 9; C.relu = 1; C.out_mode = 1;
-      LAUNCH(launch_tapgemm(C, ctx->engine == 1, ctx->sm_count, s));
+      LAUNCH(launch_tapgemm(C, ctx->engine == 1, ctx->sm_count, cs.out));
       C.a = ctx->hid_f16.as<__half>();
       C.w = ctx->conv_w[1].as<__half>();
       C.bias = ctx->conv_b[1].as<float>();
       C.out_f16 = nullptr;
       C.out_f32 = sam;
       C.relu = 0; C.out_mode = 2;
-      LAUNCH(launch_tapgemm(C, ctx->engine == 1, ctx->sm_count, s));
+      LAUNCH(launch_tapgemm(C, ctx->engine == 1, ctx->sm_count, cs.out));
     }
+  }
+  return SNRF_OK;
+}
+
+int snrf_render(snrf_ctx* ctx, const float* origins, const float* dirs, const float* nears, const float* fars,
+                int64_t n_rays, uint32_t flags, const snrf_render_opts* opts, float* rgb, float* depth, float* acc,
+                float* prop_depth, float* sam, float* clipseg, const snrf_debug_out* dbg, void* stream) {
+  if (!ctx) return SNRF_E_INVALID;
+  if (n_rays < 0) return fail(ctx, SNRF_E_INVALID, "negative ray count");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CK(cudaSetDevice(ctx->device));
+  const ChunkStreams cs = {s, s, s, 0, 0};
+  return render_chunk(ctx, origins, dirs, nears, fars, n_rays, flags, opts, rgb, depth, acc, prop_depth, sam, clipseg, dbg, cs);
+}
+
+int snrf_render_frame(snrf_ctx* ctx, const float* origins, const float* dirs, const float* nears, const float* fars,
+                      int64_t n_rays, int64_t chunk, uint32_t flags, const snrf_render_opts* opts, float* rgb,
+                      float* depth, float* acc, float* prop_depth, float* sam, float* clipseg, void* stream) {
+  if (!ctx) return SNRF_E_INVALID;
+  if (n_rays < 0 || chunk <= 0) return fail(ctx, SNRF_E_INVALID, "bad ray count / chunk size");
+  if ((flags & SNRF_PATCH) && chunk % 16 != 0) return fail(ctx, SNRF_E_INVALID, "chunk must be a multiple of 16 with SNRF_PATCH");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CK(cudaSetDevice(ctx->device));
+  if (!ctx->aux_ready) {
+    int lo = 0, hi = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CK(cudaStreamCreateWithPriority(&ctx->aux_feat, cudaStreamNonBlocking, hi));
+    CK(cudaStreamCreateWithPriority(&ctx->aux_out, cudaStreamNonBlocking, hi));
+    ctx->aux_ready = true;
+  }
+  const bool feats = (flags & (SNRF_WANT_SAM | SNRF_WANT_CLIPSEG)) != 0;
+  const bool pipelined = feats && n_rays > chunk && (ctx->pipeline == 2 || (ctx->pipeline == 1 && ctx->rep[0].local));
+  const int p2 = (flags & SNRF_PATCH) ? 16 : 1;
+  // the aux streams start after everything already queued on the caller's stream
+  if (pipelined) {
+    CK(cudaEventRecord(ctx->ev_join, s));
+    CK(cudaStreamWaitEvent(ctx->aux_feat, ctx->ev_join, 0));
+    CK(cudaStreamWaitEvent(ctx->aux_out, ctx->ev_join, 0));
+  }
+  // with replicated outputs the output-layer kernel is throttled by NVLink, not by the SMs: keep its footprint small
+  // (multicast: one store reaches every rank, a handful of SMs saturate the link; peer pointers: n_peers stores)
+  int out_grid = 0;
+  if (pipelined && ctx->rep[0].local) {
+    out_grid = ctx->rep[0].mc ? 8 : 24;
+    if (const char* e = getenv("SNRF_OUT_GRID")) out_grid = atoi(e);
+  }
+  int64_t c = 0;
+  for (int64_t i = 0; i < n_rays; i += chunk, ++c) {
+    const int64_t n = n_rays - i < chunk ? n_rays - i : chunk;
+    const int slot = pipelined ? static_cast<int>(c & 1) : 0;
+    ChunkStreams cs = {s, pipelined ? ctx->aux_feat : s, pipelined ? ctx->aux_out : s, slot, out_grid};
+    if (pipelined && c >= 2) {
+      CK(cudaStreamWaitEvent(s, ctx->ev_feat_done[slot], 0));             // sam_t / sam_w of this slot are free again
+      CK(cudaStreamWaitEvent(ctx->aux_feat, ctx->ev_out_done[slot], 0));  // hbar of this slot is free again
+    }
+    int rc = render_chunk(ctx, origins + 3 * i, dirs + 3 * i, nears ? nears + i : nullptr, fars ? fars + i : nullptr, n,
+                          flags, opts, rgb + 3 * i, depth + i, acc ? acc + i : nullptr,
+                          prop_depth ? prop_depth + i : nullptr, sam ? sam + (i / p2) * 256 : nullptr,
+                          clipseg ? clipseg + i * 192 : nullptr, nullptr, cs);
+    if (rc) return rc;
+    if (pipelined) {
+      CK(cudaEventRecord(ctx->ev_feat_done[slot], ctx->aux_feat));
+      CK(cudaEventRecord(ctx->ev_out_done[slot], ctx->aux_out));
+    }
+  }
+  if (pipelined) {  // join: the caller's stream continues only when every chunk's outputs are complete
+    CK(cudaEventRecord(ctx->ev_join, ctx->aux_feat));
+    CK(cudaStreamWaitEvent(s, ctx->ev_join, 0));
+    CK(cudaEventRecord(ctx->ev_join2, ctx->aux_out));
+    CK(cudaStreamWaitEvent(s, ctx->ev_join2, 0));
   }
   return SNRF_OK;
 }

@@ -53,6 +53,34 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// ---- output stores of the fused tile all-gather -------------------------------------------------------------------
+// One 16-byte store per destination: the local frame buffer, then either the NVSwitch multicast alias (the switch
+// replicates the store into every rank's buffer) or each peer-mapped alias over NVLink.
+__device__ __forceinline__ void st_mc_v4(float* p, float4 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};\n" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ void st_mc_v2(float* p, float2 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v2.f32 [%0], {%1,%2};\n" ::"l"(p), "f"(v.x), "f"(v.y) : "memory");
+}
+__device__ __forceinline__ void store_out4(const GemmParams& P, int64_t off, float4 v) {
+  if (P.out_mc) {
+    st_mc_v4(P.out_mc + off, v);
+  } else {
+    *reinterpret_cast<float4*>(P.out_f32 + off) = v;
+    for (int p = 0; p < P.n_peers; ++p) *reinterpret_cast<float4*>(P.out_peer[p] + off) = v;
+  }
+}
+__device__ __forceinline__ void store_out2(const GemmParams& P, int64_t off, float2 v) {
+  if (P.out_mc) {
+    st_mc_v2(P.out_mc + off, v);
+  } else {
+    *reinterpret_cast<float2*>(P.out_f32 + off) = v;
+    for (int p = 0; p < P.n_peers; ++p) *reinterpret_cast<float2*>(P.out_peer[p] + off) = v;
+  }
+}
+
 template <bool TC>
 __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const GemmParams P) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -163,6 +191,40 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const GemmParams P
       const int r = quarter * 32 + lane;
       const int64_t row = row0 + r;
       const int cols_per_warp = P.n / 4;  // 64 or 48
+      if (P.out_mode == 0) {
+        // fp32 rows leave through a shared-memory transpose (the A tile is free once the MMAs have committed):
+        // TMEM hands each thread one row, but stores should be contiguous along a row - 16 B per lane, consecutive
+        // lanes on consecutive 16-B pieces - so that local L2 writes are full sectors and the replicated stores of
+        // the fused tile all-gather cross NVLink as 192-256 B bursts instead of 16 B packets.
+        float* stage = reinterpret_cast<float*>(s_a);
+        const int ld = cols_per_warp + 4;  // +4 floats: conflict-free float4 writes with one row per lane
+        const int n4 = cols_per_warp / 4;
+        for (int ph = 0; ph < 4; ++ph) {
+          if (cg == ph) {
+            for (int c = 0; c < cols_per_warp; c += 16) {
+              float v[16];
+              const int col0 = cg * cols_per_warp + c;
+              tmem_ld16(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + col0, v);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                v[i] += s_bias[col0 + i];
+                if (P.relu) v[i] = fmaxf(v[i], 0.f);
+              }
+              float4* dst = reinterpret_cast<float4*>(stage + r * ld + c);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            }
+          }
+          __syncthreads();
+          for (int i = tid; i < 128 * n4; i += kThreads) {
+            const int rr = i / n4, c4 = i - rr * n4;
+            const int64_t grow = row0 + rr;
+            if (grow < P.m)
+              store_out4(P, grow * P.n + ph * cols_per_warp + c4 * 4, *reinterpret_cast<const float4*>(stage + rr * ld + c4 * 4));
+          }
+          __syncthreads();
+        }
+      } else
       for (int c = 0; c < cols_per_warp; c += 16) {
         float v[16];
         const int col0 = cg * cols_per_warp + c;
@@ -174,9 +236,9 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const GemmParams P
         }
         if (P.out_mode == 0) {
           if (row < P.m) {
-            float4* dst = reinterpret_cast<float4*>(P.out_f32 + row * P.n + col0);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            for (int i = 0; i < 4; ++i)
+              store_out4(P, row * P.n + col0 + 4 * i, make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
           }
         } else if (P.out_mode == 1) {
           if (row < P.m) {
@@ -206,8 +268,8 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const GemmParams P
             c0 = fmaxf(c0, 0.f); c1 = fmaxf(c1, 0.f); c2 = fmaxf(c2, 0.f); c3 = fmaxf(c3, 0.f);
           }
           if (P.out_mode == 0) {
-            if (r_lo < P.m) *reinterpret_cast<float2*>(P.out_f32 + r_lo * P.n + col) = make_float2(c0, c1);
-            if (r_hi < P.m) *reinterpret_cast<float2*>(P.out_f32 + r_hi * P.n + col) = make_float2(c2, c3);
+            if (r_lo < P.m) store_out2(P, r_lo * P.n + col, make_float2(c0, c1));
+            if (r_hi < P.m) store_out2(P, r_hi * P.n + col, make_float2(c2, c3));
           } else if (P.out_mode == 1) {
             if (r_lo < P.m) *reinterpret_cast<uint32_t*>(P.out_f16 + r_lo * P.n + col) = f2_to_h2(c0, c1);
             if (r_hi < P.m) *reinterpret_cast<uint32_t*>(P.out_f16 + r_hi * P.n + col) = f2_to_h2(c2, c3);

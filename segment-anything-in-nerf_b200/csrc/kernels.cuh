@@ -17,6 +17,23 @@ constexpr uint32_t kFlagSamplesOnly = 1u;  // stop after the PDF resample (backs
 constexpr int kBgLastSample = 0;           // RGBRenderer background "last_sample" (renderers.py:102-103)
 constexpr int kBgFixed = 1;                // fixed colour (black / white / background_color_override_context)
 
+constexpr int kMaxPeers = 8;
+// Aliases of one output buffer in the other ranks' frame buffers (fused tile all-gather): one NVSwitch multicast
+// address (multimem.st reaches every rank, this one included) or up to 8 peer-mapped pointers.
+struct OutRep {
+  float* mc;
+  float* peer[kMaxPeers];
+  int n;
+};
+__device__ __forceinline__ void store_rep(float* local, const OutRep& R, int64_t off, float v) {
+  if (R.mc) {
+    asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;\n" ::"l"(R.mc + off), "f"(v) : "memory");
+  } else {
+    local[off] = v;
+    for (int p = 0; p < R.n; ++p) R.peer[p][off] = v;
+  }
+}
+
 struct MarchParams {
   const float* origins;  // [N,3]
   const float* dirs;     // [N,3]
@@ -40,6 +57,7 @@ struct MarchParams {
   float* depth;       // [N]
   float* acc;         // [N] or null
   float* prop_depth;  // [N] or null
+  OutRep rep[4];      // replication of rgb / depth / acc / prop_depth into the other ranks' frame buffers
   float* sam_t;       // [N,k] 2 x midpoint of the picked samples, or null
   float* sam_w;       // [N,k] sharpened, renormalised weights
   float* dbg_w0;      // [N,64] proposal weights, or null
@@ -76,6 +94,12 @@ struct GemmParams {
   int taps;            // 1 (plain GEMM) or 9 (3x3 conv over 4x4 patches of 16 consecutive rows)
   int relu;
   int out_mode;
+  // Fused tile all-gather (out_mode 0 only): besides out_f32, every output row is stored into the frame buffers of
+  // the other ranks at the same byte offset - either through one NVSwitch multicast address (multimem.st) or through
+  // n_peers peer-mapped pointers (plain st.global over NVLink).  All null / 0 = single-GPU behaviour.
+  float* out_mc;        // multicast alias of out_f32 (covers every rank, including this one), or null
+  float* out_peer[8];   // peer aliases of out_f32 on the other ranks
+  int n_peers;
 };
 cudaError_t launch_tapgemm(const GemmParams& P, bool tcgen05, int sm_count, cudaStream_t stream);
 

@@ -75,6 +75,27 @@ class Renderer:
     def launch_count(self) -> int:
         return int(self.lib.snrf_launch_count(self.h))
 
+    REPLICATED = {"sam": 0, "rgb": 1, "depth": 2, "accumulation": 3, "prop_depth_0": 4}
+
+    def set_replication(self, name: str, frame: Optional[torch.Tensor], peer_ptrs: Sequence[int] = (),
+                        multicast_ptr: int = 0) -> None:
+        """Fused tile all-gather: rows of output ``name`` rendered into (slices of) ``frame`` are also stored at the
+        same offset of the other ranks' frame buffers - through ``multicast_ptr`` (NVSwitch multicast alias) or
+        ``peer_ptrs`` (peer-mapped aliases on the other ranks).  ``frame=None`` switches it off."""
+        which = self.REPLICATED[name]
+        if frame is None:
+            self._check(self.lib.snrf_set_replication(self.h, which, None, 0, None, None, 0))
+            return
+        arr = (C.c_void_p * max(len(peer_ptrs), 1))(*[C.c_void_p(p) for p in peer_ptrs])
+        self._check(self.lib.snrf_set_replication(
+            self.h, which, frame.data_ptr(), frame.numel() * frame.element_size(),
+            C.c_void_p(multicast_ptr) if multicast_ptr else None, arr, len(peer_ptrs)))
+
+    def set_pipeline(self, mode: int) -> None:
+        """Chunk pipelining of ``render_frame`` over the library's internal streams: 0 off, 1 auto (default: only
+        when outputs are replicated to other ranks), 2 always."""
+        self._check(self.lib.snrf_set_pipeline(self.h, int(mode)))
+
     def set_timing(self, enable: bool) -> None:
         self._check(self.lib.snrf_set_timing(self.h, int(enable)))
 
@@ -238,9 +259,18 @@ class Renderer:
                 out["sam"] = torch.empty(n, cfg.sam_out, device=dev)
             if cfg.distill_sam and cfg.use_clipseg_feature and "clipseg" in get_feature:
                 out["clipseg"] = torch.empty(n, cfg.clipseg_out, device=dev)
-        for i in range(0, n, chunk):
-            self.render(o[i:i + chunk], d[i:i + chunk], get_feature=get_feature, fast=fast,
-                        out={k: v[i:i + chunk] for k, v in out.items()})
+        flags = 0
+        if "sam" in out:
+            flags |= L.WANT_SAM
+        if "clipseg" in out:
+            flags |= L.WANT_CLIPSEG
+        for k, v in out.items():
+            assert v.is_cuda and v.is_contiguous() and v.dtype == torch.float32 and v.shape[0] == n, k
+        opts = self._opts(None)
+        self._check(self.lib.snrf_render_frame(
+            self.h, o.data_ptr(), d.data_ptr(), None, None, n, chunk, flags, C.byref(opts), out["rgb"].data_ptr(),
+            out["depth"].data_ptr(), _ptr(out.get("accumulation")), _ptr(out.get("prop_depth_0")), _ptr(out.get("sam")),
+            _ptr(out.get("clipseg")), self.stream))
         return out
 
     def sample(self, origins, directions, nears=None, fars=None):
