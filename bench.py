@@ -244,7 +244,7 @@ def run_native(args):
     from samnerf_b200.tiles import all_gather_tiles, ray_block
 
     assert ray_block(rank, world, H, W) == (lo, lo + n_loc)
-    r.set_pipeline(0 if args.no_pipeline else 1)
+    r.set_pipeline(args.pipeline)
 
     def frame():
         r.render_frame(o_dev, d_dev, get_feature=("sam",), chunk=chunk, out=mine)
@@ -358,7 +358,7 @@ def run_native(args):
                        "l2": "256 MiB buffer zeroed between timed frames (untimed); tables 158 MB + outputs 668 MB > 126 MB L2",
                        "tiles": (f"{world} row blocks of {H // world} rows; 256-d features exchanged by {gather_mode}, "
                                  "frame ends with a symmetric-memory barrier") if world > 1 else "single GPU",
-                       "chunk": chunk, "pipeline": "chunks pipelined over 3 streams" if (world > 1 and symm is not None and not args.no_pipeline) else "sequential"},
+                       "chunk": chunk, "pipeline": "chunks pipelined over 3 streams" if (args.pipeline == 2 or (args.pipeline == 1 and world > 1 and symm is not None)) else "sequential"},
             "roofline": {"bound": "hbm", "kernel": "sam_kernel (feature-field gather + MLP layer 1 + weighted sum)",
                          "achieved": ach, "peak": peak, "unit": "GB/s", "frac": (ach / peak) if ach else None,
                          "traffic": ncu_traffic(rays_per_launch), "peak_source": peak_src,
@@ -395,7 +395,8 @@ def main():
     ap.add_argument("--gather", choices=["auto", "mc", "peer", "nccl"], default="auto",
                     help="N > 1: how the feature tiles are exchanged (fused multicast / peer stores, or NCCL)")
     ap.add_argument("--chunk", type=int, default=0, help="rays per chunk (default: 32768, finer with N > 1)")
-    ap.add_argument("--no-pipeline", action="store_true", help="run the chunks strictly one after another on one stream")
+    ap.add_argument("--pipeline", type=int, default=1, choices=[0, 1, 2],
+                    help="chunk pipelining over 3 streams: 0 off, 1 auto (only with replicated outputs, N > 1), 2 always")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-rays", type=int, default=16384)
     ap.add_argument("--ref-rays", type=int, default=4096)

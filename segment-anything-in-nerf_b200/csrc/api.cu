@@ -375,7 +375,9 @@ int snrf_upload_proposal(snrf_ctx* ctx, const float* params, int64_t n, const sn
   CK(ctx->prop_w2_rm.ensure(256 * 2));
   CK(cudaMemsetAsync(ctx->prop_w1f.p, 0, 16 * 17 * 4, s));
   LAUNCH(launch_f32_to_f16(src + n_net, ctx->prop_table.as<__half>(), n_grid, s));
-  LAUNCH(launch_pack_prop(src, 16, src + 256, ctx->prop_w1f.as<float>(), ctx->prop_w2f.as<float>(), s));
+  CK(ctx->wfrag.ensure(kMarchFragTiles * 256));
+  LAUNCH(launch_pack_frag(src, 16, nullptr, ctx->wfrag.as<uint2>() + kFragProp1 * 32, 2, 1, s));
+  LAUNCH(launch_pack_frag(src + 256, 16, nullptr, ctx->wfrag.as<uint2>() + kFragProp2 * 32, 1, 1, s));
   LAUNCH(launch_f32_to_f16(src, ctx->prop_w1_rm.as<__half>(), 256, s));
   LAUNCH(launch_f32_to_f16(src + 256, ctx->prop_w2_rm.as<__half>(), 256, s));
   CK(cudaStreamSynchronize(s));
@@ -544,8 +546,6 @@ static int fill_march(snrf_ctx* ctx, MarchParams& M, const float* origins, const
   M.far_default = o->far_plane;
   M.prop = ctx->prop_grid;
   M.field = ctx->field_grid;
-  M.prop_w1 = ctx->prop_w1f.as<float>();
-  M.prop_w2 = ctx->prop_w2f.as<float>();
   M.wfrag = ctx->wfrag.as<uint2>();
   M.pdf_u = ctx->pdf_u.as<float>();
   M.hist_padding = o->hist_padding;
@@ -593,6 +593,7 @@ struct ChunkStreams {
   cudaStream_t march, feat, out;
   int slot;        // which copy of the per-chunk scratch (sam_t / sam_w / hbar) to use
   int out_grid;    // CTA cap of the output-layer kernel (0 = one per SM)
+  bool small_cta;  // 8-warp / 145 KB feature kernel that shares an SM with march CTAs
 };
 
 // offset-preserving aliases of an output pointer in the other ranks' frame buffers (snrf_set_replication)
@@ -683,7 +684,7 @@ static int render_chunk(snrf_ctx* ctx, const float* origins, const float* dirs, 
     S.w1 = f.w1_core.as<__half>();
     S.hbar = hbar.as<__half>();
     S.dbg_feat = (which == 0 && dbg) ? reinterpret_cast<__half*>(dbg->sam_feat) : nullptr;
-    TIMED_LAUNCH(1, cs.feat, launch_sam(S, ctx->engine == 1, ctx->sm_count, cs.feat));
+    TIMED_LAUNCH(1, cs.feat, launch_sam(S, ctx->engine == 1, cs.small_cta, ctx->sm_count, cs.feat));
     if (cs.out != cs.feat) {
       CK(cudaEventRecord(ctx->ev_feat[slot][which], cs.feat));
       CK(cudaStreamWaitEvent(cs.out, ctx->ev_feat[slot][which], 0));
@@ -738,7 +739,7 @@ int snrf_render(snrf_ctx* ctx, const float* origins, const float* dirs, const fl
   if (n_rays < 0) return fail(ctx, SNRF_E_INVALID, "negative ray count");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   CK(cudaSetDevice(ctx->device));
-  const ChunkStreams cs = {s, s, s, 0, 0};
+  const ChunkStreams cs = {s, s, s, 0, 0, false};
   return render_chunk(ctx, origins, dirs, nears, fars, n_rays, flags, opts, rgb, depth, acc, prop_depth, sam, clipseg, dbg, cs);
 }
 
@@ -770,14 +771,15 @@ int snrf_render_frame(snrf_ctx* ctx, const float* origins, const float* dirs, co
   // (multicast: one store reaches every rank, a handful of SMs saturate the link; peer pointers: n_peers stores)
   int out_grid = 0;
   if (pipelined && ctx->rep[0].local) {
-    out_grid = ctx->rep[0].mc ? 8 : 24;
+    out_grid = 32;
     if (const char* e = getenv("SNRF_OUT_GRID")) out_grid = atoi(e);
   }
   int64_t c = 0;
   for (int64_t i = 0; i < n_rays; i += chunk, ++c) {
     const int64_t n = n_rays - i < chunk ? n_rays - i : chunk;
     const int slot = pipelined ? static_cast<int>(c & 1) : 0;
-    ChunkStreams cs = {s, pipelined ? ctx->aux_feat : s, pipelined ? ctx->aux_out : s, slot, out_grid};
+    ChunkStreams cs = {s, pipelined ? ctx->aux_feat : s, pipelined ? ctx->aux_out : s, slot, out_grid,
+                       pipelined && getenv("SNRF_CORESIDENT") != nullptr};
     if (pipelined && c >= 2) {
       CK(cudaStreamWaitEvent(s, ctx->ev_feat_done[slot], 0));             // sam_t / sam_w of this slot are free again
       CK(cudaStreamWaitEvent(ctx->aux_feat, ctx->ev_out_done[slot], 0));  // hbar of this slot is free again

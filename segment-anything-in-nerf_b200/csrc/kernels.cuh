@@ -11,7 +11,9 @@ constexpr int kFragBase2 = 16;   // base MLP  64 -> 16 : 2 x 4
 constexpr int kFragHead1 = 24;   // head MLP  32 -> 64 : 8 x 2   (input columns permuted: [pad, geo(15), SH(16)])
 constexpr int kFragHead2 = 40;   // head MLP  64 -> 64 : 8 x 4
 constexpr int kFragHead3 = 72;   // head MLP  64 -> 8  : 1 x 4   (only rgb = outputs 0..2 are used)
-constexpr int kMarchFragTiles = 76;
+constexpr int kFragProp1 = 76;   // proposal MLP 16 -> 16 : 2 x 1   (input columns 10..15 are tcnn's zero padding)
+constexpr int kFragProp2 = 78;   // proposal MLP 16 -> 8  : 1 x 1   (only output 0, the density, is used)
+constexpr int kMarchFragTiles = 79;
 
 constexpr uint32_t kFlagSamplesOnly = 1u;  // stop after the PDF resample (backs ProposalNetworkSampler)
 constexpr int kBgLastSample = 0;           // RGBRenderer background "last_sample" (renderers.py:102-103)
@@ -43,8 +45,6 @@ struct MarchParams {
   float near_default, far_default;
   GridDev prop;          // 5 levels x 2
   GridDev field;         // 16 levels x 2
-  const float* prop_w1;  // [16][17] fp32 (fp16-representable): hidden x input, row stride 17
-  const float* prop_w2;  // [16] density row of the output layer
   const uint2* wfrag;    // kMarchFragTiles x 32 fragment words
   const float* pdf_u;    // [33] eval-mode PDF sample positions
   float hist_padding;
@@ -80,7 +80,7 @@ struct SamParams {
   __half* hbar;        // [N,256] fp16: sum_k w_k * fp16(relu(W1 x_k))
   __half* dbg_feat;    // [N,16,192] encoder output, or null
 };
-cudaError_t launch_sam(const SamParams& P, bool tcgen05, int sm_count, cudaStream_t stream);
+cudaError_t launch_sam(const SamParams& P, bool tcgen05, bool small_cta, int sm_count, cudaStream_t stream);
 
 // ---- kernel C/D: tap GEMM  out = act(sum_t A_t[M,256] x W_t[N,256]^T + bias) ----------------------
 struct GemmParams {

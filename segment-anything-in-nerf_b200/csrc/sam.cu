@@ -19,12 +19,6 @@
 namespace snrf {
 namespace {
 
-#ifndef SNRF_SAM_UNROLL
-#define SNRF_SAM_UNROLL 2
-#endif
-constexpr int kGatherUnroll = SNRF_SAM_UNROLL;  // levels in flight per lane (4 x 16-byte loads each)
-constexpr int kWarps = 16;
-constexpr int kThreads = kWarps * 32;
 constexpr int kRaysPerTile = 8;
 constexpr int kK = 16;      // samples per ray
 constexpr int kIn = 192;    // encoder width
@@ -32,7 +26,10 @@ constexpr int kHid = 256;   // hidden width
 constexpr uint32_t kSBO = kIn * 16;                 // bytes between 8-row groups
 constexpr uint32_t kW1Bytes = kHid * kIn * 2;       // 98304
 constexpr uint32_t kATileBytes = 128 * kIn * 2;     // 49152
-constexpr uint32_t kSmemBytes = kW1Bytes + 2 * kATileBytes + 2 * 128 * 4 + 64;
+// NW = 16 warps: two A tiles + two TMEM buffers (the MMA/epilogue of tile i-1 overlaps the gather of tile i), 193 KB.
+// NW = 8 warps: one A tile, 145 KB and <= 32 K registers, so that two march CTAs fit on the same SM beside it when
+// the frame pipeline runs both kernels at once (snrf_render_frame): one warp gathers both encodings of its ray.
+constexpr uint32_t smem_bytes(int nw) { return kW1Bytes + (nw == 16 ? 2 : 1) * kATileBytes + 2 * 128 * 4 + 64; }
 
 // reduce v[0..31] over the 16 lanes of each half-warp; on return v[0], v[1] hold the sums of columns
 // (base, base+1) with base = 16*b0 + 8*b1 + 4*b2 + 2*b3 (b_i = bit i of the lane).  30 shuffles.
@@ -102,12 +99,14 @@ __device__ __forceinline__ void gather_f8(const GridDev& G, int k0, float x, flo
   }
 }
 
-template <bool TC, uint32_t M0, uint32_t M1>
-__global__ void __launch_bounds__(kThreads, 1) sam_kernel(const SamParams P) {
+template <bool TC, uint32_t M0, uint32_t M1, int NW>
+__global__ void __launch_bounds__(NW * 32, NW == 8 ? 2 : 1) sam_kernel(const SamParams P) {  // <= 128 registers
+  constexpr int kThreads = NW * 32;
+  constexpr int NBUF = NW == 16 ? 2 : 1;
   extern __shared__ __align__(128) unsigned char smem[];
   unsigned char* s_w1 = smem;
   unsigned char* s_a = smem + kW1Bytes;
-  float* s_sw = reinterpret_cast<float*>(smem + kW1Bytes + 2 * kATileBytes);  // [2][128]
+  float* s_sw = reinterpret_cast<float*>(smem + kW1Bytes + NBUF * kATileBytes);  // [2][128]
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_sw + 256);                  // [2]
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 2);
 
@@ -124,7 +123,7 @@ __global__ void __launch_bounds__(kThreads, 1) sam_kernel(const SamParams P) {
       mbar_init(smem_u32(&s_bar[1]), 1);
       asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
-    if (warp == 0) tmem_alloc(smem_u32(s_tmem), 512);
+    if (warp == 0) tmem_alloc(smem_u32(s_tmem), 256 * NBUF);
     fence_async_smem();
     tc_fence_before();
   }
@@ -135,21 +134,22 @@ __global__ void __launch_bounds__(kThreads, 1) sam_kernel(const SamParams P) {
   }
 
   const int64_t n_tiles = (P.n_rays + kRaysPerTile - 1) / kRaysPerTile;
-  const int r_loc = warp & 7, e = warp >> 3;
+  const int r_loc = warp & 7, e = warp >> 3;  // NW = 8: e == 0 and the warp gathers both encodings
   const int s16 = lane >> 1, xb = lane & 1;
 
   // ---- epilogue of one tile out of TMEM (tcgen05 engine) ---------------------------------------
   auto epilogue_tc = [&](int64_t tile, int buf, uint32_t parity) {
     mbar_wait(smem_u32(&s_bar[buf]), parity);
     tc_fence_after();
+    constexpr int kColsPerWarp = kHid / (NW / 4);  // 64 (16 warps) or 128 (8 warps)
     const int quarter = warp & 3, cq = warp >> 2;
     const int row = quarter * 32 + lane;
     const float wgt = s_sw[buf * 128 + row];
     const int64_t ray = tile * kRaysPerTile + (row >> 4);
 #pragma unroll 1
-    for (int chunk = 0; chunk < 2; ++chunk) {
+    for (int chunk = 0; chunk < kColsPerWarp / 32; ++chunk) {
       float v[32];
-      const int col0 = cq * 64 + chunk * 32;
+      const int col0 = cq * kColsPerWarp + chunk * 32;
       tmem_ld32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * 256 + col0, v);
 #pragma unroll
       for (int i = 0; i < 32; ++i) v[i] = round_f16(fmaxf(v[i], 0.f)) * wgt;
@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(kThreads, 1) sam_kernel(const SamParams P) {
   int64_t prev_tile = -1;
   int it = 0;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-    const int buf = it & 1;
+    const int buf = NBUF == 2 ? (it & 1) : 0;
     unsigned char* a_tile = s_a + buf * kATileBytes;
     const int64_t ray = tile * kRaysPerTile + r_loc;
     const int row = r_loc * kK + s16;
@@ -177,15 +177,14 @@ __global__ void __launch_bounds__(kThreads, 1) sam_kernel(const SamParams P) {
       const float pz = __fadd_rn(P.origins[3 * ray + 2], __fmul_rn(P.dirs[3 * ray + 2], tm2) / 2.f);
       float x, y, z, sel;
       contract_normalize(px, py, pz, false, false, x, y, z, sel);
-      if (e == 0)
-        gather_f8<M0>(P.enc[0], 0, x, y, z, xb, row, a_tile, P.dbg_feat ? P.dbg_feat + (ray * kK + s16) * kIn : nullptr);
-      else
-        gather_f8<M1>(P.enc[1], 96, x, y, z, xb, row, a_tile, P.dbg_feat ? P.dbg_feat + (ray * kK + s16) * kIn : nullptr);
+      __half* dbg_row = P.dbg_feat ? P.dbg_feat + (ray * kK + s16) * kIn : nullptr;
+      if (NW == 8 || e == 0) gather_f8<M0>(P.enc[0], 0, x, y, z, xb, row, a_tile, dbg_row);
+      if (NW == 8 || e == 1) gather_f8<M1>(P.enc[1], 96, x, y, z, xb, row, a_tile, dbg_row);
     } else {
       // tail tile: keep the rows finite so the (discarded) accumulator rows are well defined
       if (e == 0 && xb == 0) s_sw[buf * 128 + row] = 0.f;
-      for (int l = 0; l < 12; ++l)
-        *reinterpret_cast<uint2*>(a_tile + core_offset(row, e * 96 + l * 8 + xb * 4, kIn)) = make_uint2(0u, 0u);
+      for (int l = (NW == 8 ? 0 : e * 12); l < (NW == 8 ? 24 : e * 12 + 12); ++l)
+        *reinterpret_cast<uint2*>(a_tile + core_offset(row, l * 8 + xb * 4, kIn)) = make_uint2(0u, 0u);
     }
     if (TC) fence_async_smem();
     __syncthreads();
@@ -203,9 +202,14 @@ __global__ void __launch_bounds__(kThreads, 1) sam_kernel(const SamParams P) {
         umma_commit(smem_u32(&s_bar[buf]));
       }
       __syncwarp();
-      if (it > 0) epilogue_tc(prev_tile, buf ^ 1, static_cast<uint32_t>(((it - 1) >> 1) & 1));
-      prev_tile = tile;
-    } else {
+      if (NBUF == 2) {
+        if (it > 0) epilogue_tc(prev_tile, buf ^ 1, static_cast<uint32_t>(((it - 1) >> 1) & 1));
+        prev_tile = tile;
+      } else {
+        epilogue_tc(tile, 0, static_cast<uint32_t>(it & 1));
+        __syncthreads();  // the single A tile and TMEM buffer are reused by the next tile
+      }
+    } else if (NW == 16) {
       // ---------------- legacy engine: warp = (ray, 128-column half), mma.sync m16n8k16 ----------
       const int nh = warp >> 3;
       float acc[16][4];
@@ -243,9 +247,9 @@ __global__ void __launch_bounds__(kThreads, 1) sam_kernel(const SamParams P) {
     }
   }
   if (TC) {
-    if (it > 0) epilogue_tc(prev_tile, (it - 1) & 1, static_cast<uint32_t>(((it - 1) >> 1) & 1));
+    if (NBUF == 2 && it > 0) epilogue_tc(prev_tile, (it - 1) & 1, static_cast<uint32_t>(((it - 1) >> 1) & 1));
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem_base, 512);
+    if (warp == 0) tmem_dealloc(tmem_base, 256 * NBUF);
   }
 }
 
@@ -253,31 +257,34 @@ __global__ void __launch_bounds__(kThreads, 1) sam_kernel(const SamParams P) {
 // 128..512 -> all 12 levels hashed
 constexpr uint32_t kEnc0MaskStd = 0xE00u, kEnc1MaskStd = 0xFFFu;
 
-template <bool TC, uint32_t M0, uint32_t M1>
+template <bool TC, uint32_t M0, uint32_t M1, int NW>
 static cudaError_t launch_one(const SamParams& P, int grid, cudaStream_t stream) {
   static bool configured = false;
-  auto* k = sam_kernel<TC, M0, M1>;
+  auto* k = sam_kernel<TC, M0, M1, NW>;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(NW));
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  k<<<grid, kThreads, kSmemBytes, stream>>>(P);
+  k<<<grid, NW * 32, smem_bytes(NW), stream>>>(P);
   return cudaGetLastError();
 }
 
 }  // namespace
 
-cudaError_t launch_sam(const SamParams& P, bool tcgen05, int sm_count, cudaStream_t stream) {
+cudaError_t launch_sam(const SamParams& P, bool tcgen05, bool small_cta, int sm_count, cudaStream_t stream) {
   if (P.n_rays <= 0) return cudaSuccess;
   const int64_t n_tiles = (P.n_rays + kRaysPerTile - 1) / kRaysPerTile;
   const int grid = static_cast<int>(n_tiles < sm_count ? n_tiles : sm_count);  // persistent: one CTA per SM
   const bool std_cfg = hashed_mask(P.enc[0]) == kEnc0MaskStd && hashed_mask(P.enc[1]) == kEnc1MaskStd;
+  if (tcgen05 && small_cta)
+    return std_cfg ? launch_one<true, kEnc0MaskStd, kEnc1MaskStd, 8>(P, grid, stream)
+                   : launch_one<true, kRuntimeMask, kRuntimeMask, 8>(P, grid, stream);
   if (tcgen05)
-    return std_cfg ? launch_one<true, kEnc0MaskStd, kEnc1MaskStd>(P, grid, stream)
-                   : launch_one<true, kRuntimeMask, kRuntimeMask>(P, grid, stream);
-  return std_cfg ? launch_one<false, kEnc0MaskStd, kEnc1MaskStd>(P, grid, stream)
-                 : launch_one<false, kRuntimeMask, kRuntimeMask>(P, grid, stream);
+    return std_cfg ? launch_one<true, kEnc0MaskStd, kEnc1MaskStd, 16>(P, grid, stream)
+                   : launch_one<true, kRuntimeMask, kRuntimeMask, 16>(P, grid, stream);
+  return std_cfg ? launch_one<false, kEnc0MaskStd, kEnc1MaskStd, 16>(P, grid, stream)
+                 : launch_one<false, kRuntimeMask, kRuntimeMask, 16>(P, grid, stream);
 }
 
 }  // namespace snrf
