@@ -104,3 +104,36 @@ def test_errors_are_loud(full):
         r._check(rc)
     with pytest.raises(RuntimeError, match="divisible by 16"):
         r.render(o[:10], d[:10], get_feature=("sam",), patch=True)
+
+
+def test_frame_api_equals_chunk_loop(full):
+    """snrf_render_frame (sequential and 3-stream pipelined) == the per-chunk loop, bit for bit."""
+    cfg, r = full
+    o, d = test_rays(9000, seed=8)
+    o, d = o.cuda(), d.cuda()
+    ref = [r.render(o[i:i + 2048], d[i:i + 2048], get_feature=("sam",)) for i in range(0, 9000, 2048)]
+    for mode in (0, 2):
+        r.set_pipeline(mode)
+        out = r.render_frame(o, d, get_feature=("sam",), chunk=2048)
+        torch.cuda.synchronize()
+        for k in ("rgb", "depth", "accumulation", "prop_depth_0", "sam"):
+            assert torch.equal(out[k], torch.cat([x[k] for x in ref])), (k, mode)
+    r.set_pipeline(1)
+
+
+def test_replication_descriptor_is_validated(full):
+    import ctypes as C
+
+    cfg, r = full
+    t = torch.empty(16, 256, device="cuda")
+    assert r.lib.snrf_set_replication(r.h, 7, t.data_ptr(), t.numel() * 4, None, None, 0) != 0       # bad slot
+    assert r.lib.snrf_set_replication(r.h, 0, t.data_ptr(), t.numel() * 4, None, None, 9) != 0       # too many peers
+    assert r.lib.snrf_set_replication(r.h, 0, None, 0, None, None, 0) == 0                           # clear is fine
+    # replicating into a second buffer on the same device through the peer-pointer path mirrors the rows exactly
+    o, d = test_rays(256, seed=2)
+    frame, mirror = torch.zeros(256, 256, device="cuda"), torch.zeros(256, 256, device="cuda")
+    r.set_replication("sam", frame, peer_ptrs=[mirror.data_ptr()])
+    out = r.render(o, d, get_feature=("sam",), out={"sam": frame})
+    torch.cuda.synchronize()
+    r.set_replication("sam", None)
+    assert torch.equal(frame, mirror) and torch.isfinite(frame).any()
