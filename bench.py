@@ -271,8 +271,6 @@ def run_native(args):
         for p in range(1, world):
             if not torch.equal(allsums[0], allsums[p]) or float(allsums[0].min()) <= 0.0:
                 raise SystemExit(f"tile exchange ({gather_mode}) is wrong: rank 0 {allsums[0].tolist()} vs rank {p} {allsums[p].tolist()}")
-    r.kernel_times()
-    r.set_timing(True)
     launches0 = r.launch_count
     clocks = ClockSampler(local)
     if rank == 0:
@@ -285,10 +283,21 @@ def run_native(args):
         frame()
         e.record()
     barrier()
-    clk = clocks.stop() if rank == 0 else None
-    r.set_timing(False)
-    ktimes = r.kernel_times()
     launches = r.launch_count - launches0
+    # Per-kernel durations for the roofline: the same K steps again with CUDA events around every launch of the
+    # three hot kernels (on the launching stream).  Kept out of the region that produces `value` because 60 event
+    # pairs per frame cost ~2 % of it; clocks are sampled across both passes.
+    r.kernel_times()
+    r.set_timing(True)
+    r.set_pipeline(0)  # serial launches, so an event pair brackets exactly one kernel
+    for _ in range(args.steps):
+        flush.zero_()
+        frame()
+    barrier()
+    r.set_timing(False)
+    r.set_pipeline(args.pipeline)
+    ktimes = r.kernel_times()
+    clk = clocks.stop() if rank == 0 else None
     total_ms = sum(s.elapsed_time(e) for s, e in ev)
     t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
     if world > 1:
@@ -367,6 +376,7 @@ def run_native(args):
                                          "is bound by the L1 tag stage and issue, not HBM (DESIGN.md section 4 B)",
                          "algorithmic_bytes_per_launch": BYTES_PER_RAY["sam"] * rays_per_launch,
                          "avg_launch_ms": f_ms / max(f_cnt, 1), "launches_timed": f_cnt,
+                         "timing_note": "CUDA events around each launch, instrumented repeat of the K timed steps (same inputs, L2 flushed)",
                          "path": {"bytes_per_ray": path_bytes, "achieved": value * 1e6 * path_bytes / 1e9 / world,
                                   "frac": value * 1e6 * path_bytes / 1e9 / world / peak},
                          "kernel_share_ms_per_step": {"march": m_ms / args.steps, "feature": f_ms / args.steps,
