@@ -205,8 +205,8 @@ def run_native(args):
     o_dev, d_dev = o_host.to(dev), d_host.to(dev)
     # reference chunk size on one GPU; with N ranks the tile is cut finer so that the NVLink exchange of chunk c
     # overlaps the compute of chunk c+1 (the chunk size is caller-tunable in the reference too, eval_utils.py:90-91)
-    chunk = args.chunk or (cfg.eval_num_rays_per_chunk if world == 1 else
-                           min(cfg.eval_num_rays_per_chunk, max(4096, (n_loc // 8 + 1023) // 1024 * 1024)))
+    # measured: 32768 is best up to 2 ranks, 16384 at 4 and 8 (profiles/r01_multi_gpu.txt)
+    chunk = args.chunk or (cfg.eval_num_rays_per_chunk if world <= 2 else 16384)
 
     # frame-sized outputs; with N > 1 each rank renders into its row block of the gathered frame (in-place all-gather)
     names = {"rgb": 3, "depth": 1, "accumulation": 1, "prop_depth_0": 1, "sam": cfg.sam_out}
@@ -224,13 +224,17 @@ def run_native(args):
                 big = symm_mem.empty(n_all * sum(names.values()), dtype=torch.float32, device=dev)
                 symm = symm_mem.rendezvous(big, dist.group.WORLD.group_name)
                 mc = int(getattr(symm, "multicast_ptr", 0) or 0) if args.gather in ("auto", "mc") else 0
+                if args.gather == "dma":
+                    r.set_replication_mode("dma")
                 off = 0
                 for k, c in names.items():
                     full[k] = big[off:off + n_all * c].view(n_all, c)
                     peers = [int(symm.buffer_ptrs[p]) + off * 4 for p in range(world) if p != rank]
                     r.set_replication(k, full[k], () if mc else peers, mc + off * 4 if mc else 0)
                     off += n_all * c
-                gather_mode = "fused multimem.st (NVSwitch multicast)" if mc else "fused peer stores (NVLink P2P)"
+                gather_mode = ("fused multimem.st (NVSwitch multicast)" if mc else
+                               "copy engines (cudaMemcpyAsync to peer buffers per chunk)" if args.gather == "dma" else
+                               "fused peer stores (NVLink P2P)")
             except Exception as e:  # no symmetric memory on this box: say so and use NCCL
                 if rank == 0:
                     print(f"[bench] symmetric memory unavailable ({type(e).__name__}: {e}); using NCCL all-gather", file=sys.stderr)
@@ -402,7 +406,7 @@ def main():
     ap.add_argument("--impl", choices=["native", "reference"], default="native")
     ap.add_argument("--regime", choices=["scene", "init"], default="scene")
     ap.add_argument("--engine", choices=["tcgen05", "mma_sync"], default="tcgen05")
-    ap.add_argument("--gather", choices=["auto", "mc", "peer", "nccl"], default="auto",
+    ap.add_argument("--gather", choices=["auto", "mc", "peer", "dma", "nccl"], default="auto",
                     help="N > 1: how the feature tiles are exchanged (fused multicast / peer stores, or NCCL)")
     ap.add_argument("--chunk", type=int, default=0, help="rays per chunk (default: 32768, finer with N > 1)")
     ap.add_argument("--pipeline", type=int, default=1, choices=[0, 1, 2],

@@ -166,6 +166,10 @@ int snrf_set_pipeline(snrf_ctx* ctx, int enable);
  * synchronises the ranks after the frame (e.g. a symmetric-memory barrier).  local_base NULL clears. */
 int snrf_set_replication(snrf_ctx* ctx, int which, void* local_base, int64_t bytes, void* mc_base,
                          void* const* peer_bases_host, int n_peers);
+/* How snrf_render_frame moves replicated outputs: 0 (default) = the kernels' own stores (multimem.st through
+ * mc_base, else st.global through the peer pointers); 1 = copy engines: kernels write locally and each chunk's rows
+ * are pushed to every peer pointer with cudaMemcpyAsync on side streams, so the exchange costs no SM time at all. */
+int snrf_set_replication_mode(snrf_ctx* ctx, int mode);
 
 /* number of kernels this library has launched on ctx since creation (bench.py's gpu_launches) */
 int64_t snrf_launch_count(snrf_ctx* ctx);

@@ -71,6 +71,7 @@ SYMBOLS = {
     "snrf_render_frame": (_I, [_P, _P, _P, _P, _P, _L, _L, _U, C.POINTER(RenderOpts), _P, _P, _P, _P, _P, _P, _P]),
     "snrf_set_pipeline": (_I, [_P, _I]),
     "snrf_set_replication": (_I, [_P, _I, _P, _L, _P, C.POINTER(C.c_void_p), _I]),
+    "snrf_set_replication_mode": (_I, [_P, _I]),
     "snrf_launch_count": (_L, [_P]),
     "snrf_set_timing": (_I, [_P, _I]),
     "snrf_kernel_times": (_I, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),

@@ -86,6 +86,9 @@ struct snrf_ctx {
   int64_t k_count[3] = {0, 0, 0};
   // fused tile all-gather (snrf_set_replication): 0 sam, 1 rgb, 2 depth, 3 accumulation, 4 prop_depth
   Replication rep[5];
+  int rep_mode = 0;  // 0: the kernels' own stores (multimem.st / peer pointers); 1: copy engines (cudaMemcpyAsync per peer)
+  cudaStream_t copy_stream[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_copy[4] = {nullptr, nullptr, nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
   // frame-level pipelining (snrf_render_frame)
   int pipeline = 1;  // 0 off, 1 auto (only when outputs are replicated to other ranks), 2 always
   bool aux_ready = false;
@@ -317,6 +320,12 @@ int snrf_set_replication(snrf_ctx* ctx, int which, void* local_base, int64_t byt
   R.mc = reinterpret_cast<float*>(mc_base);
   R.n = n_peers;
   for (int i = 0; i < n_peers; ++i) R.peer[i] = reinterpret_cast<float*>(peer_bases_host[i]);
+  return SNRF_OK;
+}
+
+int snrf_set_replication_mode(snrf_ctx* ctx, int mode) {
+  if (!ctx || (mode != 0 && mode != 1)) return fail(ctx, SNRF_E_INVALID, "replication mode must be 0 (stores) or 1 (copy engines)");
+  ctx->rep_mode = mode;
   return SNRF_OK;
 }
 
@@ -602,6 +611,7 @@ static void replicate(const snrf_ctx* ctx, int which, const float* out, int64_t 
   *mc = nullptr;
   *n_peers = 0;
   const Replication& R = ctx->rep[which];
+  if (ctx->rep_mode == 1) return;  // copy-engine mode: kernels write locally, snrf_render_frame pushes the rows
   const char* lo = reinterpret_cast<const char*>(R.local);
   const char* p = reinterpret_cast<const char*>(out);
   if (!R.local || !out || p < lo || p + n_floats * sizeof(float) > lo + R.bytes) return;
@@ -756,10 +766,17 @@ int snrf_render_frame(snrf_ctx* ctx, const float* origins, const float* dirs, co
     CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
     CK(cudaStreamCreateWithPriority(&ctx->aux_feat, cudaStreamNonBlocking, hi));
     CK(cudaStreamCreateWithPriority(&ctx->aux_out, cudaStreamNonBlocking, hi));
+    for (int i = 0; i < 4; ++i) {
+      CK(cudaStreamCreateWithFlags(&ctx->copy_stream[i], cudaStreamNonBlocking));
+      CK(cudaEventCreateWithFlags(&ctx->ev_copy[i], cudaEventDisableTiming));
+    }
+    CK(cudaEventCreateWithFlags(&ctx->ev_out[0], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ctx->ev_out[1], cudaEventDisableTiming));
     ctx->aux_ready = true;
   }
   const bool feats = (flags & (SNRF_WANT_SAM | SNRF_WANT_CLIPSEG)) != 0;
   const bool pipelined = feats && n_rays > chunk && (ctx->pipeline == 2 || (ctx->pipeline == 1 && ctx->rep[0].local));
+  const bool dma = ctx->rep_mode == 1 && ctx->rep[0].local && ctx->rep[0].n > 0;
   const int p2 = (flags & SNRF_PATCH) ? 16 : 1;
   // the aux streams start after everything already queued on the caller's stream
   if (pipelined) {
@@ -770,7 +787,7 @@ int snrf_render_frame(snrf_ctx* ctx, const float* origins, const float* dirs, co
   // with replicated outputs the output-layer kernel is throttled by NVLink, not by the SMs: keep its footprint small
   // (multicast: one store reaches every rank, a handful of SMs saturate the link; peer pointers: n_peers stores)
   int out_grid = 0;
-  if (pipelined && ctx->rep[0].local) {
+  if (pipelined && ctx->rep[0].local && !dma) {
     out_grid = 32;
     if (const char* e = getenv("SNRF_OUT_GRID")) out_grid = atoi(e);
   }
@@ -792,6 +809,46 @@ int snrf_render_frame(snrf_ctx* ctx, const float* origins, const float* dirs, co
     if (pipelined) {
       CK(cudaEventRecord(ctx->ev_feat_done[slot], ctx->aux_feat));
       CK(cudaEventRecord(ctx->ev_out_done[slot], ctx->aux_out));
+    }
+    // copy-engine exchange: as soon as this chunk's feature rows exist, DMA them into every peer's frame buffer
+    if (dma && sam && (flags & SNRF_WANT_SAM) && !(flags & SNRF_PATCH)) {
+      const Replication& R = ctx->rep[0];
+      float* src = sam + i * 256;
+      const char* lo = reinterpret_cast<const char*>(R.local);
+      const char* p = reinterpret_cast<const char*>(src);
+      if (p >= lo && p + n * 256 * sizeof(float) <= lo + R.bytes) {
+        const int64_t off = (p - lo) / static_cast<int64_t>(sizeof(float));
+        cudaStream_t so = pipelined ? ctx->aux_out : s;
+        CK(cudaEventRecord(ctx->ev_out[c & 1], so));
+        for (int q = 0; q < R.n; ++q) {
+          cudaStream_t cp = ctx->copy_stream[q & 3];
+          CK(cudaStreamWaitEvent(cp, ctx->ev_out[c & 1], 0));
+          CK(cudaMemcpyAsync(R.peer[q] + off, src, n * 256 * sizeof(float), cudaMemcpyDeviceToDevice, cp));
+        }
+      }
+    }
+  }
+  if (dma) {
+    // the small per-ray outputs (24 B/ray) go once per frame, after the last march
+    float* outs[4] = {rgb, depth, acc, prop_depth};
+    const int64_t widths[4] = {3, 1, 1, 1};
+    CK(cudaEventRecord(ctx->ev_join, s));
+    for (int w = 0; w < 4; ++w) {
+      const Replication& R = ctx->rep[w + 1];
+      if (!outs[w] || !R.local) continue;
+      const char* lo = reinterpret_cast<const char*>(R.local);
+      const char* p = reinterpret_cast<const char*>(outs[w]);
+      if (p < lo || p + n_rays * widths[w] * sizeof(float) > lo + R.bytes) continue;
+      const int64_t off = (p - lo) / static_cast<int64_t>(sizeof(float));
+      for (int q = 0; q < R.n; ++q) {
+        cudaStream_t cp = ctx->copy_stream[q & 3];
+        CK(cudaStreamWaitEvent(cp, ctx->ev_join, 0));
+        CK(cudaMemcpyAsync(R.peer[q] + off, outs[w], n_rays * widths[w] * sizeof(float), cudaMemcpyDeviceToDevice, cp));
+      }
+    }
+    for (int q = 0; q < 4; ++q) {  // the caller's stream resumes after every copy has been queued and finished
+      CK(cudaEventRecord(ctx->ev_copy[q], ctx->copy_stream[q]));
+      CK(cudaStreamWaitEvent(s, ctx->ev_copy[q], 0));
     }
   }
   if (pipelined) {  // join: the caller's stream continues only when every chunk's outputs are complete

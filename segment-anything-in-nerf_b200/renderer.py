@@ -91,6 +91,10 @@ class Renderer:
             self.h, which, frame.data_ptr(), frame.numel() * frame.element_size(),
             C.c_void_p(multicast_ptr) if multicast_ptr else None, arr, len(peer_ptrs)))
 
+    def set_replication_mode(self, mode: str) -> None:
+        """``stores``: the kernels' own multimem.st / peer stores (default); ``dma``: copy engines push each chunk."""
+        self._check(self.lib.snrf_set_replication_mode(self.h, {"stores": 0, "dma": 1}[mode]))
+
     def set_pipeline(self, mode: int) -> None:
         """Chunk pipelining of ``render_frame`` over the library's internal streams: 0 off, 1 auto (default: only
         when outputs are replicated to other ranks), 2 always."""

@@ -1,4 +1,4 @@
-"""Two-rank render on two GPUs: fused tile all-gather (multicast or peer stores) == single-GPU frame.
+"""Two-rank render on two GPUs: tile all-gather (multicast stores, peer stores, copy engines) == single-GPU frame.
 Needs >= 2 CUDA devices (skipped on the 1-GPU test box; run with `gpurun --gpus 2 -- pytest tests/test_multi_gpu.py -m gpu`)."""
 import os
 import subprocess
@@ -32,6 +32,8 @@ big = symm_mem.empty(H * W * sum(names.values()), dtype=torch.float32, device=de
 big.fill_(-7.0)
 hdl = symm_mem.rendezvous(big, dist.group.WORLD.group_name)
 mc = int(hdl.multicast_ptr or 0) if mode == "mc" else 0
+if mode == "dma":
+    r.set_replication_mode("dma")
 if mode == "mc" and not mc:
     print("SKIP no multicast"); dist.destroy_process_group(); sys.exit(0)
 full, off = {}, 0
@@ -52,7 +54,7 @@ dist.destroy_process_group()
 '''
 
 
-@pytest.mark.parametrize("mode", ["peer", "mc"])
+@pytest.mark.parametrize("mode", ["peer", "mc", "dma"])
 def test_fused_tile_all_gather(mode, tmp_path):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
