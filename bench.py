@@ -8,8 +8,10 @@
 One "step" = one 800x800 frame of the `samnerf_distill` model (SURVEY.md 8 d config 3): 640 000 rays, every ray
 rendered to rgb / median depth / accumulation / proposal depth AND the 256-d SAM feature (k = 16 top samples,
 sharpening 10, patch 1), in the reference's chunks of 32 768 rays, through `libsnrf` (C ABI).  With N > 1 the frame is
-cut into N contiguous row blocks ("screen tiles"), one per rank, followed by one NCCL all-gather of the rendered tiles:
-total work is fixed, so scaling is "strong".  Synthetic scene-like parameters (seed 0), synthetic orbit camera.
+cut into N contiguous row blocks ("screen tiles"), one per rank, and the rendered tiles are exchanged into every
+rank's frame buffer (symmetric memory): by copy engines per chunk (default), by the kernels' own multicast / peer
+stores, or by an NCCL all-gather (--gather).  Total work is fixed, so scaling is "strong".  Synthetic scene-like
+parameters (seed 0), synthetic orbit camera.
 
 `--impl reference` times the reference's own CPU path: the reference is Python + the CUDA-only tinycudann, so its CPU
 implementation is the oracle port (oracle/samnerf_oracle.py, validated against the reference's own modules by
@@ -223,8 +225,8 @@ def run_native(args):
 
                 big = symm_mem.empty(n_all * sum(names.values()), dtype=torch.float32, device=dev)
                 symm = symm_mem.rendezvous(big, dist.group.WORLD.group_name)
-                mc = int(getattr(symm, "multicast_ptr", 0) or 0) if args.gather in ("auto", "mc") else 0
-                if args.gather == "dma":
+                mc = int(getattr(symm, "multicast_ptr", 0) or 0) if args.gather == "mc" else 0
+                if args.gather in ("dma", "auto"):
                     r.set_replication_mode("dma")
                 off = 0
                 for k, c in names.items():
@@ -233,7 +235,7 @@ def run_native(args):
                     r.set_replication(k, full[k], () if mc else peers, mc + off * 4 if mc else 0)
                     off += n_all * c
                 gather_mode = ("fused multimem.st (NVSwitch multicast)" if mc else
-                               "copy engines (cudaMemcpyAsync to peer buffers per chunk)" if args.gather == "dma" else
+                               "copy engines (cudaMemcpyAsync to peer buffers per chunk)" if args.gather in ("dma", "auto") else
                                "fused peer stores (NVLink P2P)")
             except Exception as e:  # no symmetric memory on this box: say so and use NCCL
                 if rank == 0:
@@ -371,7 +373,7 @@ def run_native(args):
                        "l2": "256 MiB buffer zeroed between timed frames (untimed); tables 158 MB + outputs 668 MB > 126 MB L2",
                        "tiles": (f"{world} row blocks of {H // world} rows; 256-d features exchanged by {gather_mode}, "
                                  "frame ends with a symmetric-memory barrier") if world > 1 else "single GPU",
-                       "chunk": chunk, "pipeline": "chunks pipelined over 3 streams" if (args.pipeline == 2 or (args.pipeline == 1 and world > 1 and symm is not None)) else "sequential"},
+                       "chunk": chunk, "pipeline": "chunks pipelined over 3 streams" if (args.pipeline == 2 or (args.pipeline == 1 and world > 1 and symm is not None and args.gather in ("mc", "peer"))) else "sequential"},
             "roofline": {"bound": "hbm", "kernel": "sam_kernel (feature-field gather + MLP layer 1 + weighted sum)",
                          "achieved": ach, "peak": peak, "unit": "GB/s", "frac": (ach / peak) if ach else None,
                          "traffic": ncu_traffic(rays_per_launch), "peak_source": peak_src,

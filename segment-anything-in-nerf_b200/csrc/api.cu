@@ -775,8 +775,10 @@ int snrf_render_frame(snrf_ctx* ctx, const float* origins, const float* dirs, co
     ctx->aux_ready = true;
   }
   const bool feats = (flags & (SNRF_WANT_SAM | SNRF_WANT_CLIPSEG)) != 0;
-  const bool pipelined = feats && n_rays > chunk && (ctx->pipeline == 2 || (ctx->pipeline == 1 && ctx->rep[0].local));
   const bool dma = ctx->rep_mode == 1 && ctx->rep[0].local && ctx->rep[0].n > 0;
+  // auto: pipeline only when a kernel's own replicated stores are NVLink-bound; with copy engines the kernels run
+  // back to back on one stream (cross-stream hops cost ~20 us per chunk and buy nothing when the exchange is off the SMs)
+  const bool pipelined = feats && n_rays > chunk && (ctx->pipeline == 2 || (ctx->pipeline == 1 && ctx->rep[0].local && !dma));
   const int p2 = (flags & SNRF_PATCH) ? 16 : 1;
   // the aux streams start after everything already queued on the caller's stream
   if (pipelined) {
