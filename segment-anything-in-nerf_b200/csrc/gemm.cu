@@ -296,7 +296,11 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const GemmParams P
 }  // namespace
 
 cudaError_t launch_tapgemm(const GemmParams& P, bool tcgen05, int sm_count, cudaStream_t stream) {
-  static bool configured = false;
+  // function attributes are per device: remember which devices of this process have been configured
+  static bool configured_dev[64] = {false};
+  int dev_id = 0;
+  if (cudaGetDevice(&dev_id) != cudaSuccess || dev_id < 0 || dev_id >= 64) return cudaErrorInvalidDevice;
+  bool& configured = configured_dev[dev_id];
   if (!configured) {
     cudaError_t e =
         cudaFuncSetAttribute(tapgemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);

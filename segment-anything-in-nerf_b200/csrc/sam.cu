@@ -259,7 +259,11 @@ constexpr uint32_t kEnc0MaskStd = 0xE00u, kEnc1MaskStd = 0xFFFu;
 
 template <bool TC, uint32_t M0, uint32_t M1, int NW>
 static cudaError_t launch_one(const SamParams& P, int grid, cudaStream_t stream) {
-  static bool configured = false;
+  // function attributes are per device: remember which devices of this process have been configured
+  static bool configured_dev[64] = {false};
+  int dev_id = 0;
+  if (cudaGetDevice(&dev_id) != cudaSuccess || dev_id < 0 || dev_id >= 64) return cudaErrorInvalidDevice;
+  bool& configured = configured_dev[dev_id];
   auto* k = sam_kernel<TC, M0, M1, NW>;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(NW));
