@@ -377,9 +377,23 @@ class SAMModel:
         self.renderer_mean = MeanRenderer(r)
 
     def load_state_dict(self, state_dict: Dict[str, torch.Tensor], strict: bool = False):
-        """Accepts the reference's pipeline keys (with or without the ``_model.`` prefix, base_pipeline.py:366-375)."""
-        sd = {k[len("_model."):] if k.startswith("_model.") else k: v for k, v in state_dict.items()}
-        self.renderer.load_params(sd)
+        """Accepts the reference's pipeline keys (with or without the ``module.`` / ``_model.`` prefixes,
+        base_pipeline.py:109-115,366-375); tensors off the hot path are ignored."""
+        from .checkpoint import params_from_state_dict
+
+        self.renderer.load_params(params_from_state_dict(state_dict))
+
+    @classmethod
+    def from_checkpoint(cls, path: str, device: int = 0, engine: str = "tcgen05", base: Optional[SAMNeRFConfig] = None):
+        """Build the model from a reference training checkpoint (``step-*.ckpt`` file or its directory; layout
+        nerfstudio/engine/trainer.py:389-400): the configuration is inferred from the tensors it carries."""
+        from .checkpoint import load_checkpoint
+
+        cfg, params, step = load_checkpoint(path, base)
+        model = cls(cfg, device=device, engine=engine)
+        model.renderer.load_params(params)
+        model.step = step
+        return model
 
     def eval(self):
         return self
