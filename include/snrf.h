@@ -171,6 +171,39 @@ int snrf_set_replication(snrf_ctx* ctx, int which, void* local_base, int64_t byt
  * are pushed to every peer pointer with cudaMemcpyAsync on side streams, so the exchange costs no SM time at all. */
 int snrf_set_replication_mode(snrf_ctx* ctx, int mode);
 
+/* ---- camera ray generation fused in front of the render -------------------------------
+ * Replaces Cameras.generate_rays(camera_indices=i, keep_shape=True) for one camera
+ * (nerfstudio/cameras/cameras.py:312-482,490-726; distortion: camera_utils.py:298-401) and the pixel sub-grid
+ * the feature map is rendered on (samnerf/sam_model.py:368-379), so that a frame call takes ~100 bytes of camera
+ * instead of 24 bytes per ray. */
+#define SNRF_CAM_PERSPECTIVE 1 /* CameraType.PERSPECTIVE, cameras.py:42-47 */
+#define SNRF_CAM_FISHEYE 2
+#define SNRF_CAM_EQUIRECTANGULAR 3
+
+typedef struct snrf_camera {
+  float fx, fy, cx, cy;
+  int32_t width, height;
+  int32_t camera_type;    /* SNRF_CAM_*                                            */
+  int32_t has_distortion; /* 0: distortion_params is None                          */
+  float distortion[6];    /* k1 k2 k3 k4 p1 p2 (camera_utils.py:320-325)           */
+  float c2w[12];          /* camera_to_worlds, row-major 3x4                       */
+} snrf_camera;
+
+/* Rays through the pixel grid rows x cols of `cam` (HOST pointers; NULL = every row / column of the image, in
+ * which case n_rows / n_cols must equal height / width).  Ray order: row-major when patch <= 1, else patch-major
+ * over patch x patch blocks with row-major order inside a block (n_rows, n_cols divisible by patch) - the order
+ * sam_model.py:376-379 produces.  origins[n,3], dirs[n,3] (unit), pixel_area[n] or NULL; n = n_rows * n_cols. */
+int snrf_generate_rays(snrf_ctx* ctx, const snrf_camera* cam, const int32_t* rows_host, int n_rows,
+                       const int32_t* cols_host, int n_cols, int patch, float* origins, float* dirs,
+                       float* pixel_area, void* stream);
+/* snrf_generate_rays into library scratch followed by snrf_render_frame over those rays: one call per loop of
+ * SAMModel.get_outputs_for_camera_ray_bundle (sam_model.py:354-418).  With SNRF_PATCH in `flags` the ray order is
+ * patch-major with p = opts->patch_size and sam is [n/p^2, 256]. */
+int snrf_render_camera(snrf_ctx* ctx, const snrf_camera* cam, const int32_t* rows_host, int n_rows,
+                       const int32_t* cols_host, int n_cols, int64_t chunk, uint32_t flags,
+                       const snrf_render_opts* opts, float* rgb, float* depth, float* acc, float* prop_depth,
+                       float* sam, float* clipseg, void* stream);
+
 /* number of kernels this library has launched on ctx since creation (bench.py's gpu_launches) */
 int64_t snrf_launch_count(snrf_ctx* ctx);
 /* Bracket the three hot kernels of snrf_render with CUDA events on the launching stream (bench.py's roofline). */

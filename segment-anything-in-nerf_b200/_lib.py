@@ -13,7 +13,7 @@ import sys
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SNRF_LIB_PATH") or os.path.join(_HERE, "libsnrf.so")
 CSRC = os.path.join(_HERE, "csrc")
-SOURCES = ["api.cu", "march.cu", "sam.cu", "gemm.cu", "query.cu"]
+SOURCES = ["api.cu", "march.cu", "sam.cu", "gemm.cu", "query.cu", "raygen.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared",
@@ -45,6 +45,12 @@ class DebugOut(C.Structure):
                 ("sam_feat", C.c_void_p)]
 
 
+class Camera(C.Structure):
+    _fields_ = [("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float), ("width", C.c_int32),
+                ("height", C.c_int32), ("camera_type", C.c_int32), ("has_distortion", C.c_int32),
+                ("distortion", C.c_float * 6), ("c2w", C.c_float * 12)]
+
+
 # every symbol include/snrf.h declares: name -> (restype, argtypes)
 _P, _I, _L, _U, _F = C.c_void_p, C.c_int, C.c_int64, C.c_uint32, C.c_float
 SYMBOLS = {
@@ -72,6 +78,9 @@ SYMBOLS = {
     "snrf_set_pipeline": (_I, [_P, _I]),
     "snrf_set_replication": (_I, [_P, _I, _P, _L, _P, C.POINTER(C.c_void_p), _I]),
     "snrf_set_replication_mode": (_I, [_P, _I]),
+    "snrf_generate_rays": (_I, [_P, C.POINTER(Camera), _P, _I, _P, _I, _I, _P, _P, _P, _P]),
+    "snrf_render_camera": (_I, [_P, C.POINTER(Camera), _P, _I, _P, _I, _L, _U, C.POINTER(RenderOpts), _P, _P, _P, _P,
+                                _P, _P, _P]),
     "snrf_launch_count": (_L, [_P]),
     "snrf_set_timing": (_I, [_P, _I]),
     "snrf_kernel_times": (_I, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
@@ -81,7 +90,7 @@ SYMBOLS = {
 def build_library(force: bool = False, verbose: bool = False) -> str:
     """Compile ``csrc/*.cu`` for sm_100a into ``libsnrf.so`` next to this file (nvcc cross-compiles without a GPU)."""
     srcs = [os.path.join(CSRC, s) for s in SOURCES]
-    deps = srcs + [os.path.join(CSRC, h) for h in ("common.cuh", "kernels.cuh")] + [
+    deps = srcs + [os.path.join(CSRC, h) for h in ("common.cuh", "kernels.cuh", "raygen.cuh")] + [
         os.path.join(_HERE, "..", "include", "snrf.h")
     ]
     if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):

@@ -11,6 +11,7 @@
 
 #include "../../include/snrf.h"
 #include "kernels.cuh"
+#include "raygen.cuh"
 
 using namespace snrf;
 
@@ -98,6 +99,7 @@ struct snrf_ctx {
   // misc
   DevBuf pdf_u;
   DevBuf sam_t[2], sam_w[2], hbar[2][2], feat_f16, hid_f16, q_feat, q_h1, q_h2, q_sel, q_x;
+  DevBuf cam_rows, cam_cols, cam_o, cam_d;  // snrf_generate_rays / snrf_render_camera
 };
 
 namespace {
@@ -274,6 +276,7 @@ void snrf_ctx_destroy(snrf_ctx* ctx) {
                     &ctx->conv_w[1],  &ctx->conv_b[0],  &ctx->conv_b[1]};
   for (DevBuf* b : bufs) b->release();
   ctx->sam_t[1].release(); ctx->sam_w[1].release();
+  ctx->cam_rows.release(); ctx->cam_cols.release(); ctx->cam_o.release(); ctx->cam_d.release();
   ctx->hbar[0][1].release(); ctx->hbar[1][0].release(); ctx->hbar[1][1].release();
   if (ctx->aux_feat) cudaStreamDestroy(ctx->aux_feat);
   if (ctx->aux_out) cudaStreamDestroy(ctx->aux_out);
@@ -860,6 +863,87 @@ int snrf_render_frame(snrf_ctx* ctx, const float* origins, const float* dirs, co
     CK(cudaStreamWaitEvent(s, ctx->ev_join2, 0));
   }
   return SNRF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// camera ray generation
+// ---------------------------------------------------------------------------------------------------
+static int fill_raygen(snrf_ctx* ctx, RayGenParams& R, const snrf_camera* cam, const int32_t* rows_host, int n_rows,
+                       const int32_t* cols_host, int n_cols, int patch, cudaStream_t s) {
+  if (!cam) return fail(ctx, SNRF_E_INVALID, "null camera");
+  if (cam->camera_type < SNRF_CAM_PERSPECTIVE || cam->camera_type > SNRF_CAM_EQUIRECTANGULAR)
+    return fail(ctx, SNRF_E_INVALID, "Camera type %d not supported.", cam->camera_type);
+  if (cam->width <= 0 || cam->height <= 0 || n_rows < 0 || n_cols < 0)
+    return fail(ctx, SNRF_E_INVALID, "bad image / grid size");
+  if (!rows_host && n_rows != cam->height) return fail(ctx, SNRF_E_INVALID, "rows NULL needs n_rows == height");
+  if (!cols_host && n_cols != cam->width) return fail(ctx, SNRF_E_INVALID, "cols NULL needs n_cols == width");
+  if (patch > 1 && (n_rows % patch != 0 || n_cols % patch != 0))
+    return fail(ctx, SNRF_E_INVALID, "a %d x %d pixel grid does not divide into %d x %d patches", n_rows, n_cols, patch, patch);
+  for (int i = 0; rows_host && i < n_rows; ++i)
+    if (rows_host[i] < 0 || rows_host[i] >= cam->height) return fail(ctx, SNRF_E_INVALID, "row index %d outside the image", rows_host[i]);
+  for (int i = 0; cols_host && i < n_cols; ++i)
+    if (cols_host[i] < 0 || cols_host[i] >= cam->width) return fail(ctx, SNRF_E_INVALID, "column index %d outside the image", cols_host[i]);
+  memset(&R, 0, sizeof(R));
+  R.cam.fx = cam->fx; R.cam.fy = cam->fy; R.cam.cx = cam->cx; R.cam.cy = cam->cy;
+  R.cam.type = cam->camera_type;
+  R.cam.has_dist = cam->has_distortion != 0;
+  memcpy(R.cam.dist, cam->distortion, sizeof(R.cam.dist));
+  memcpy(R.cam.c2w, cam->c2w, sizeof(R.cam.c2w));
+  R.n_rows = n_rows;
+  R.n_cols = n_cols;
+  R.patch = patch > 1 ? patch : 1;
+  if (rows_host && n_rows > 0) {
+    CK(ctx->cam_rows.ensure(n_rows * sizeof(int32_t)));
+    CK(cudaMemcpyAsync(ctx->cam_rows.p, rows_host, n_rows * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    R.rows = ctx->cam_rows.as<int>();
+  }
+  if (cols_host && n_cols > 0) {
+    CK(ctx->cam_cols.ensure(n_cols * sizeof(int32_t)));
+    CK(cudaMemcpyAsync(ctx->cam_cols.p, cols_host, n_cols * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    R.cols = ctx->cam_cols.as<int>();
+  }
+  return SNRF_OK;
+}
+
+int snrf_generate_rays(snrf_ctx* ctx, const snrf_camera* cam, const int32_t* rows_host, int n_rows,
+                       const int32_t* cols_host, int n_cols, int patch, float* origins, float* dirs,
+                       float* pixel_area, void* stream) {
+  if (!ctx) return SNRF_E_INVALID;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CK(cudaSetDevice(ctx->device));
+  RayGenParams R;
+  int rc = fill_raygen(ctx, R, cam, rows_host, n_rows, cols_host, n_cols, patch, s);
+  if (rc) return rc;
+  if (static_cast<int64_t>(n_rows) * n_cols == 0) return SNRF_OK;
+  if (!origins || !dirs) return fail(ctx, SNRF_E_INVALID, "null output");
+  R.origins = origins;
+  R.dirs = dirs;
+  R.pixel_area = pixel_area;
+  LAUNCH(launch_raygen(R, s));
+  return SNRF_OK;
+}
+
+int snrf_render_camera(snrf_ctx* ctx, const snrf_camera* cam, const int32_t* rows_host, int n_rows,
+                       const int32_t* cols_host, int n_cols, int64_t chunk, uint32_t flags,
+                       const snrf_render_opts* opts, float* rgb, float* depth, float* acc, float* prop_depth,
+                       float* sam, float* clipseg, void* stream) {
+  if (!ctx) return SNRF_E_INVALID;
+  if (!opts) return fail(ctx, SNRF_E_INVALID, "null argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CK(cudaSetDevice(ctx->device));
+  const int patch = (flags & SNRF_PATCH) ? opts->patch_size : 1;
+  RayGenParams R;
+  int rc = fill_raygen(ctx, R, cam, rows_host, n_rows, cols_host, n_cols, patch, s);
+  if (rc) return rc;
+  const int64_t n = static_cast<int64_t>(n_rows) * n_cols;
+  if (n == 0) return SNRF_OK;
+  CK(ctx->cam_o.ensure(n * 3 * sizeof(float)));
+  CK(ctx->cam_d.ensure(n * 3 * sizeof(float)));
+  R.origins = ctx->cam_o.as<float>();
+  R.dirs = ctx->cam_d.as<float>();
+  LAUNCH(launch_raygen(R, s));
+  return snrf_render_frame(ctx, R.origins, R.dirs, nullptr, nullptr, n, chunk, flags, opts, rgb, depth, acc, prop_depth,
+                           sam, clipseg, stream);
 }
 
 int snrf_sample(snrf_ctx* ctx, const float* origins, const float* dirs, const float* nears, const float* fars,

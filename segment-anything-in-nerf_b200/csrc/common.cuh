@@ -11,7 +11,21 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+// Pure per-thread helpers are host+device so that tests/emu can run the bodies of the simple (one thread = one item)
+// kernels on the CPU against the oracle; device code generation is unaffected.
+#define SNRF_HD __host__ __device__ __forceinline__
+
 namespace snrf {
+
+// a*b+c WITHOUT fma contraction, so that device, host emulation and the torch oracle round alike
+SNRF_HD float mul_add_rn(float a, float b, float c) {
+#ifdef __CUDA_ARCH__
+  return __fadd_rn(__fmul_rn(a, b), c);
+#else
+  volatile float m = a * b;
+  return m + c;
+#endif
+}
 
 constexpr int kMaxLevels = 16;
 constexpr uint32_t kPrimeY = 2654435761u;
@@ -36,13 +50,13 @@ struct GridDev {
 // ---------------------------------------------------------------------------------------------
 // scalar helpers (op order mirrors the torch expressions the oracle evaluates)
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ float round_f16(float x) { return __half2float(__float2half_rn(x)); }
+SNRF_HD float round_f16(float x) { return __half2float(__float2half_rn(x)); }
 
-__device__ __forceinline__ float spacing_fn(float x) { return x < 1.f ? x / 2.f : 1.f - 1.f / (2.f * x); }
-__device__ __forceinline__ float spacing_fn_inv(float x) { return x < 0.5f ? 2.f * x : 1.f / (2.f - 2.f * x); }
+SNRF_HD float spacing_fn(float x) { return x < 1.f ? x / 2.f : 1.f - 1.f / (2.f * x); }
+SNRF_HD float spacing_fn_inv(float x) { return x < 0.5f ? 2.f * x : 1.f / (2.f - 2.f * x); }
 
 // torch.nan_to_num defaults: nan -> 0, +inf -> FLT_MAX, -inf -> -FLT_MAX
-__device__ __forceinline__ float nan_to_num(float x) {
+SNRF_HD float nan_to_num(float x) {
   if (x != x) return 0.f;
   if (x == INFINITY) return 3.402823466e+38f;
   if (x == -INFINITY) return -3.402823466e+38f;
@@ -51,7 +65,7 @@ __device__ __forceinline__ float nan_to_num(float x) {
 
 // contraction followed by (p+2)/4. `linf`: order=inf (density fields) else L2 (SAMField).
 // `use_selector`: density fields zero positions outside (0,1) and gate the density with it.
-__device__ __forceinline__ void contract_normalize(float px, float py, float pz, bool linf, bool use_selector,
+SNRF_HD void contract_normalize(float px, float py, float pz, bool linf, bool use_selector,
                                                    float& x, float& y, float& z, float& sel) {
   float mag;
   if (linf) {
@@ -81,11 +95,11 @@ __device__ __forceinline__ void contract_normalize(float px, float py, float pz,
 // Hashed levels always have a power-of-two size (2^log2_hashmap_size; checked at upload), so `% size` is a mask.
 // Dense levels: idx <= res + res^2 + res^3 < 2*size, and idx >= size only for the +1 corner of a coordinate on the
 // upper boundary, so `% size` is one conditional subtract; the final min() keeps non-finite inputs in bounds.
-__device__ __forceinline__ uint32_t wrap_dense(uint32_t idx, uint32_t size) {
+SNRF_HD uint32_t wrap_dense(uint32_t idx, uint32_t size) {
   return min(idx >= size ? idx - size : idx, size - 1u);
 }
 
-__device__ __forceinline__ uint32_t grid_index(const GridLevel& L, uint32_t gx, uint32_t gy, uint32_t gz) {
+SNRF_HD uint32_t grid_index(const GridLevel& L, uint32_t gx, uint32_t gy, uint32_t gz) {
   if (L.hashed) return ((gx ^ (gy * kPrimeY) ^ (gz * kPrimeZ)) & (L.size - 1u)) + L.offset;
   return wrap_dense(gx + gy * L.res + gz * L.res * L.res, L.size) + L.offset;
 }
@@ -95,12 +109,12 @@ __device__ __forceinline__ uint32_t grid_index(const GridLevel& L, uint32_t gx, 
 // any other configuration runs the kRuntimeMask instantiation, which reads GridLevel::hashed.
 constexpr uint32_t kRuntimeMask = 0x80000000u;
 template <uint32_t MASK>
-__device__ __forceinline__ bool level_hashed(const GridLevel& L, int l) {
+SNRF_HD bool level_hashed(const GridLevel& L, int l) {
   return (MASK & kRuntimeMask) ? (L.hashed != 0u) : (((MASK >> l) & 1u) != 0u);
 }
 
 // entry indices of the four (y,z) corners c = dy + 2*dz of a voxel for a fixed x coordinate
-__device__ __forceinline__ void corner_indices(const GridLevel& L, bool hashed, uint32_t gx, uint32_t gy, uint32_t gz,
+SNRF_HD void corner_indices(const GridLevel& L, bool hashed, uint32_t gx, uint32_t gy, uint32_t gz,
                                                uint32_t (&idx)[4]) {
   if (hashed) {
     const uint32_t m = L.size - 1u;

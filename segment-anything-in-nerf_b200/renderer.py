@@ -26,6 +26,38 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
 
+class Camera:
+    """One camera of the reference's ``Cameras`` dataclass (nerfstudio/cameras/cameras.py:61-140): intrinsics,
+    ``camera_to_worlds`` 3x4, ``CameraType`` value (1 perspective, 2 fisheye, 3 equirectangular) and the optional
+    six distortion parameters ``[k1 k2 k3 k4 p1 p2]``."""
+
+    def __init__(self, fx: float, fy: float, cx: float, cy: float, width: int, height: int, camera_to_world,
+                 camera_type: int = 1, distortion_params=None):
+        self.fx, self.fy, self.cx, self.cy = float(fx), float(fy), float(cx), float(cy)
+        self.width, self.height, self.camera_type = int(width), int(height), int(camera_type)
+        self.camera_to_world = torch.as_tensor(camera_to_world, dtype=torch.float32)[:3, :4].contiguous().cpu()
+        self.distortion_params = None if distortion_params is None else [float(v) for v in distortion_params]
+
+    def as_struct(self) -> L.Camera:
+        c = L.Camera()
+        c.fx, c.fy, c.cx, c.cy, c.width, c.height = self.fx, self.fy, self.cx, self.cy, self.width, self.height
+        c.camera_type = self.camera_type
+        c.has_distortion = int(self.distortion_params is not None)
+        for i, v in enumerate(self.distortion_params or [0.0] * 6):
+            c.distortion[i] = v
+        for i, v in enumerate(self.camera_to_world.flatten().tolist()):
+            c.c2w[i] = v
+        return c
+
+
+def _index_list(idx, n_default: int):
+    """(ctypes int32 array or None, length) for an optional list of pixel rows / columns."""
+    if idx is None:
+        return None, n_default
+    vals = [int(v) for v in torch.as_tensor(idx).flatten().tolist()]
+    return (C.c_int32 * max(len(vals), 1))(*vals), len(vals)
+
+
 class Renderer:
     """One ``snrf_ctx`` on one CUDA device."""
 
@@ -273,6 +305,56 @@ class Renderer:
         opts = self._opts(None)
         self._check(self.lib.snrf_render_frame(
             self.h, o.data_ptr(), d.data_ptr(), None, None, n, chunk, flags, C.byref(opts), out["rgb"].data_ptr(),
+            out["depth"].data_ptr(), _ptr(out.get("accumulation")), _ptr(out.get("prop_depth_0")), _ptr(out.get("sam")),
+            _ptr(out.get("clipseg")), self.stream))
+        return out
+
+    # ---- camera in front ----------------------------------------------------------
+    def generate_rays(self, cam: Camera, rows=None, cols=None, patch: int = 1, pixel_area: bool = False):
+        """``Cameras.generate_rays`` for one camera (cameras.py:312-482,490-726) over the pixel grid ``rows x cols``
+        (``None`` = the whole image), row-major or patch-major (``patch`` > 1, sam_model.py:376-379).
+        Returns ``origins[n,3], directions[n,3], pixel_area[n,1] | None`` on the device."""
+        r, n_rows = _index_list(rows, cam.height)
+        c, n_cols = _index_list(cols, cam.width)
+        n = n_rows * n_cols
+        o = torch.empty(n, 3, device=self.device)
+        d = torch.empty(n, 3, device=self.device)
+        a = torch.empty(n, 1, device=self.device) if pixel_area else None
+        st = cam.as_struct()
+        self._check(self.lib.snrf_generate_rays(self.h, C.byref(st), r, n_rows, c, n_cols, int(patch), o.data_ptr(),
+                                                d.data_ptr(), _ptr(a), self.stream))
+        return o, d, a
+
+    def render_camera(self, cam: Camera, rows=None, cols=None, get_feature: Sequence[str] = ("sam",), patch: bool = False,
+                      fast: bool = False, chunk: Optional[int] = None,
+                      out: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
+        """One loop of ``SAMModel.get_outputs_for_camera_ray_bundle`` (sam_model.py:354-418) from the camera itself:
+        rays are generated on the device and rendered chunk by chunk in the same call."""
+        cfg, dev = self.cfg, self.device
+        r, n_rows = _index_list(rows, cam.height)
+        c, n_cols = _index_list(cols, cam.width)
+        n = n_rows * n_cols
+        chunk = chunk or cfg.eval_num_rays_per_chunk
+        flags = 0
+        if out is None:
+            out = {"rgb": torch.empty(n, 3, device=dev), "depth": torch.empty(n, 1, device=dev)}
+            if not fast:
+                out["accumulation"] = torch.empty(n, 1, device=dev)
+                out["prop_depth_0"] = torch.empty(n, 1, device=dev)
+            if cfg.distill_sam and "sam" in get_feature:
+                out["sam"] = torch.empty(n // (cfg.patch_size**2) if patch else n, cfg.sam_out, device=dev)
+            if cfg.distill_sam and cfg.use_clipseg_feature and "clipseg" in get_feature:
+                out["clipseg"] = torch.empty(n, cfg.clipseg_out, device=dev)
+        if "sam" in out:
+            flags |= L.WANT_SAM | (L.PATCH if patch else 0)
+        if "clipseg" in out:
+            flags |= L.WANT_CLIPSEG
+        for k, v in out.items():
+            assert v.is_cuda and v.is_contiguous() and v.dtype == torch.float32, k
+        opts = self._opts(None)
+        st = cam.as_struct()
+        self._check(self.lib.snrf_render_camera(
+            self.h, C.byref(st), r, n_rows, c, n_cols, chunk, flags, C.byref(opts), out["rgb"].data_ptr(),
             out["depth"].data_ptr(), _ptr(out.get("accumulation")), _ptr(out.get("prop_depth_0")), _ptr(out.get("sam")),
             _ptr(out.get("clipseg")), self.stream))
         return out

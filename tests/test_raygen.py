@@ -1,0 +1,150 @@
+"""Camera ray generation: oracle vs the reference's own ``Cameras.generate_rays`` output, the
+kernel body (host emulation) vs the same golden vectors, and - on a GPU - the kernel and ``snrf_render_camera``."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import raygen_oracle as RO
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "raygen.npz")
+CASES = ["perspective", "perspective_distorted", "fisheye_distorted", "equirectangular"]
+# stated tolerance: unit directions agree to 2e-6 absolute (fp32 divide / sqrt / sin / cos rounding and, on the device,
+# fma contraction inside the Newton iteration); pixel areas to 1e-4 relative
+DIR_ATOL, AREA_RTOL = 2e-6, 1e-4
+
+
+def _case(name):
+    z = np.load(GOLDEN)
+    fx, fy, cx, cy, w, h, typ = z[f"{name}.camera"].tolist()
+    dist = z[f"{name}.dist"].tolist()
+    return dict(fx=fx, fy=fy, cx=cx, cy=cy, w=int(w), h=int(h), type=int(typ), dist=dist or None,
+                c2w=torch.from_numpy(z[f"{name}.c2w"]), origins=z[f"{name}.origins"], directions=z[f"{name}.directions"],
+                pixel_area=z[f"{name}.pixel_area"], sub_directions=z[f"{name}.sub_directions"])
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_matches_reference(name):
+    c = _case(name)
+    ys, xs = RO.full_image_pixels(c["h"], c["w"])
+    o, d, a = RO.generate_rays(c["fx"], c["fy"], c["cx"], c["cy"], c["c2w"], ys, xs, c["type"], c["dist"])
+    assert np.array_equal(o.numpy(), c["origins"])
+    np.testing.assert_allclose(d.numpy(), c["directions"], rtol=0, atol=1e-7)
+    np.testing.assert_allclose(a.numpy(), c["pixel_area"], rtol=1e-5, atol=0)
+
+
+def _emu_rays(c, rows, cols, patch, want_area=True):
+    from emu.build_emu import load
+
+    lib = load()
+    n_rows = len(rows) if rows is not None else c["h"]
+    n_cols = len(cols) if cols is not None else c["w"]
+    n = n_rows * n_cols
+    o, d, a = np.empty((n, 3), np.float32), np.empty((n, 3), np.float32), np.empty((n,), np.float32)
+    intr = np.array([c["fx"], c["fy"], c["cx"], c["cy"]], np.float32)
+    dist = np.array(c["dist"] or [0] * 6, np.float32)
+    c2w = np.ascontiguousarray(c["c2w"].numpy(), np.float32)
+    r = None if rows is None else np.ascontiguousarray(rows, np.int32)
+    cc = None if cols is None else np.ascontiguousarray(cols, np.int32)
+    p = lambda x: None if x is None else x.ctypes.data_as(C.c_void_p)
+    lib.emu_generate_rays(p(intr), c["type"], int(c["dist"] is not None), p(dist), p(c2w), p(r), n_rows, p(cc), n_cols, patch,
+                          p(o), p(d), p(a) if want_area else None)
+    return o, d, a
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_kernel_body_matches_reference(name):
+    """The __host__ __device__ body of raygen_kernel, run on the CPU, against the reference's output."""
+    c = _case(name)
+    o, d, a = _emu_rays(c, None, None, 1)
+    assert np.array_equal(o.reshape(c["h"], c["w"], 3), c["origins"])
+    np.testing.assert_allclose(d.reshape(c["h"], c["w"], 3), c["directions"], rtol=0, atol=DIR_ATOL)
+    np.testing.assert_allclose(a.reshape(c["h"], c["w"], 1), c["pixel_area"], rtol=AREA_RTOL, atol=0)
+    # explicit row / column lists (the LOOP B sub-grid)
+    ys = torch.linspace(0, c["h"] - 1, 4, dtype=torch.long).numpy()
+    xs = torch.linspace(0, c["w"] - 1, 8, dtype=torch.long).numpy()
+    _, d2, _ = _emu_rays(c, ys, xs, 1, want_area=False)
+    np.testing.assert_allclose(d2.reshape(4, 8, 3), c["sub_directions"], rtol=0, atol=DIR_ATOL)
+
+
+def test_kernel_body_patch_major_order():
+    """Ray order of the feature grid: (fh, p, fw, p) -> (fh, fw, p, p) flattened (sam_model.py:376-379)."""
+    c = _case("perspective")
+    fh, fw, p = 2, 3, 2
+    hind, wind = RO.feature_grid_pixels(c["h"], c["w"], fh, fw, p)
+    _, want, _ = RO.generate_rays(c["fx"], c["fy"], c["cx"], c["cy"], c["c2w"], hind, wind, c["type"], c["dist"])
+    rows = torch.linspace(0, c["h"] - 1, fh * p, dtype=torch.long).numpy()
+    cols = torch.linspace(0, c["w"] - 1, fw * p, dtype=torch.long).numpy()
+    _, got, _ = _emu_rays(c, rows, cols, p, want_area=False)
+    np.testing.assert_allclose(got, want.numpy(), rtol=0, atol=DIR_ATOL)
+
+
+def test_oracle_reproduces_the_synthetic_orbit_camera():
+    """bench.py's 800x800 frame comes from synthetic.orbit_rays; the camera path must give the same rays."""
+    from samnerf_b200.synthetic import look_at, orbit_rays
+
+    o_ref, d_ref = orbit_rays(40, 40, 40.0)
+    c2w = look_at((1.2, 0.0, 0.4))
+    ys, xs = RO.full_image_pixels(40, 40)
+    o, d, _ = RO.generate_rays(40.0, 40.0, 20.0, 20.0, c2w[:3, :4], ys, xs)
+    assert torch.equal(o.reshape(-1, 3), o_ref.reshape(-1, 3))
+    np.testing.assert_allclose(d.numpy().reshape(-1, 3), d_ref.numpy().reshape(-1, 3), rtol=0, atol=1e-6)
+
+
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.hw_unverified
+@pytest.mark.parametrize("name", CASES)
+def test_gpu_kernel_matches_oracle(name):
+    from samnerf_b200 import SAMNeRFConfig
+    from samnerf_b200.renderer import Camera, Renderer
+
+    c = _case(name)
+    r = Renderer(SAMNeRFConfig.tiny(), device=0)
+    cam = Camera(c["fx"], c["fy"], c["cx"], c["cy"], c["w"], c["h"], c["c2w"], c["type"], c["dist"])
+    o, d, a = r.generate_rays(cam, pixel_area=True)
+    torch.cuda.synchronize()
+    assert np.array_equal(o.cpu().numpy().reshape(c["h"], c["w"], 3), c["origins"])
+    np.testing.assert_allclose(d.cpu().numpy().reshape(c["h"], c["w"], 3), c["directions"], rtol=0, atol=DIR_ATOL)
+    np.testing.assert_allclose(a.cpu().numpy().reshape(c["h"], c["w"], 1), c["pixel_area"], rtol=AREA_RTOL, atol=0)
+    # a big image against the oracle, and the patch-major sub-grid
+    big = Camera(800.0, 790.0, 400.0, 401.5, 800, 800, c["c2w"], c["type"], c["dist"])
+    o, d, a = r.generate_rays(big, pixel_area=True)
+    ys, xs = RO.full_image_pixels(800, 800)
+    _, dw, aw = RO.generate_rays(800.0, 790.0, 400.0, 401.5, c["c2w"], ys, xs, c["type"], c["dist"])
+    np.testing.assert_allclose(d.cpu().numpy(), dw.numpy().reshape(-1, 3), rtol=0, atol=DIR_ATOL)
+    hind, wind = RO.feature_grid_pixels(800, 800, 64, 64, 4)
+    rows = torch.linspace(0, 799, 256, dtype=torch.long)
+    _, d2, _ = r.generate_rays(big, rows=rows, cols=rows, patch=4)
+    _, dw2, _ = RO.generate_rays(800.0, 790.0, 400.0, 401.5, c["c2w"], hind, wind, c["type"], c["dist"])
+    np.testing.assert_allclose(d2.cpu().numpy(), dw2.numpy(), rtol=0, atol=DIR_ATOL)
+
+
+@pytest.mark.gpu
+@pytest.mark.hw_unverified
+def test_gpu_render_camera_equals_render_frame():
+    from helpers import make_renderer, model_pair
+    from samnerf_b200.renderer import Camera
+    from samnerf_b200.synthetic import look_at
+
+    cfg, params, _ = model_pair("tiny", "scene", 5, False, 4)
+    r = make_renderer(cfg, params)
+    cam = Camera(60.0, 60.0, 32.0, 24.0, 64, 48, look_at((1.1, 0.6, 0.45))[:3, :4])
+    o, d, _ = r.generate_rays(cam)
+    ref = r.render_frame(o, d, get_feature=("sam",), chunk=1024)
+    out = r.render_camera(cam, get_feature=("sam",), chunk=1024)
+    torch.cuda.synchronize()
+    for k in ("rgb", "depth", "accumulation", "prop_depth_0", "sam"):
+        assert torch.equal(out[k], ref[k]), k
+    # patch-aggregated feature map on the strided sub-grid == the per-chunk shim path
+    rows = torch.linspace(0, 47, 12 * 4, dtype=torch.long)
+    cols = torch.linspace(0, 63, 16 * 4, dtype=torch.long)
+    o2, d2, _ = r.generate_rays(cam, rows=rows, cols=cols, patch=4)
+    want = r.render(o2, d2, get_feature=("sam",), patch=True)["sam"]
+    got = r.render_camera(cam, rows=rows, cols=cols, get_feature=("sam",), patch=True, chunk=1024)["sam"]
+    torch.cuda.synchronize()
+    assert torch.equal(got, want)
+    with pytest.raises(RuntimeError, match="outside the image"):
+        r.generate_rays(cam, rows=torch.tensor([0, 48]), cols=cols)
