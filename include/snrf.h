@@ -204,6 +204,23 @@ int snrf_render_camera(snrf_ctx* ctx, const snrf_camera* cam, const int32_t* row
                        const snrf_render_opts* opts, float* rgb, float* depth, float* acc, float* prop_depth,
                        float* sam, float* clipseg, void* stream);
 
+/* ---- training side of the feature-field branch (first slice) ---------------------------
+ * The `sam_field` parameter group (samnerf/sam_model.py:330-335) receives gradients only through
+ * SAMField.get_outputs at the k picked samples (positions detached, sam_field.py:116) and the MeanRenderer with
+ * detached weights (sam_model.py:258-277), so its forward / backward are closed over (origins, dirs, sam_t, sam_w) -
+ * the picks snrf_render reports through snrf_debug_out.  which: 0 = sam (n_out 256), 1 = clipseg (n_out 192). */
+/* out[N,n_out] = W2 . sum_k w_k fp16(relu(W1 x_k)); enc_f16: [N,16,192] fp16 encoder outputs, saved for the
+ * backward pass (may be NULL when no backward follows).  Same kernels as the render path. */
+int snrf_feature_forward(snrf_ctx* ctx, int which, const float* origins, const float* dirs, const float* sam_t,
+                         const float* sam_w, int64_t n_rays, float* out, void* enc_f16, void* stream);
+/* Given d_out[N,n_out], ACCUMULATE (+=, like torch's .grad) fp32 gradients in the reference's flat layouts:
+ * grad_net [256*192 + n_out*256] for sam_field.{sam,clipseg}_net.params (layer-1 matrix, then layer-2),
+ * grad_grid0 / grad_grid1 [entries*8] for sam_field.{clip,clipseg}_encs.{0,1}.params.  Any of the three may be
+ * NULL (that parameter is frozen).  Replaces tinycudann's autograd for these modules (sam_field.py:51,63,84,99). */
+int snrf_feature_backward(snrf_ctx* ctx, int which, const float* origins, const float* dirs, const float* sam_t,
+                          const float* sam_w, int64_t n_rays, const float* d_out, const void* enc_f16,
+                          float* grad_net, float* grad_grid0, float* grad_grid1, void* stream);
+
 /* number of kernels this library has launched on ctx since creation (bench.py's gpu_launches) */
 int64_t snrf_launch_count(snrf_ctx* ctx);
 /* Bracket the three hot kernels of snrf_render with CUDA events on the launching stream (bench.py's roofline). */

@@ -40,8 +40,24 @@ PRIME_Z = 805459861
 MASK32 = 0xFFFFFFFF
 
 
+class _RoundF16(torch.autograd.Function):
+    """fp16 rounding with a straight-through fp32 gradient (a plain ``.half().float()`` round trip would also round
+    the *gradient* to fp16 on the way back, which is neither tcnn's loss-scaled fp16 backward nor useful as a
+    reference; the stated gradient contract is "fp32 gradient of the rounded forward pass")."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.to(torch.float16).to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
 def f16(x: torch.Tensor) -> torch.Tensor:
     """Round to fp16 and come back to fp32 (models a ``__half`` store)."""
+    if x.requires_grad:
+        return _RoundF16.apply(x)
     return x.to(torch.float16).to(torch.float32)
 
 

@@ -13,7 +13,7 @@ import sys
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SNRF_LIB_PATH") or os.path.join(_HERE, "libsnrf.so")
 CSRC = os.path.join(_HERE, "csrc")
-SOURCES = ["api.cu", "march.cu", "sam.cu", "gemm.cu", "query.cu", "raygen.cu"]
+SOURCES = ["api.cu", "march.cu", "sam.cu", "gemm.cu", "query.cu", "raygen.cu", "backward.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared",
@@ -81,6 +81,8 @@ SYMBOLS = {
     "snrf_generate_rays": (_I, [_P, C.POINTER(Camera), _P, _I, _P, _I, _I, _P, _P, _P, _P]),
     "snrf_render_camera": (_I, [_P, C.POINTER(Camera), _P, _I, _P, _I, _L, _U, C.POINTER(RenderOpts), _P, _P, _P, _P,
                                 _P, _P, _P]),
+    "snrf_feature_forward": (_I, [_P, _I, _P, _P, _P, _P, _L, _P, _P, _P]),
+    "snrf_feature_backward": (_I, [_P, _I, _P, _P, _P, _P, _L, _P, _P, _P, _P, _P, _P]),
     "snrf_launch_count": (_L, [_P]),
     "snrf_set_timing": (_I, [_P, _I]),
     "snrf_kernel_times": (_I, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
@@ -90,7 +92,7 @@ SYMBOLS = {
 def build_library(force: bool = False, verbose: bool = False) -> str:
     """Compile ``csrc/*.cu`` for sm_100a into ``libsnrf.so`` next to this file (nvcc cross-compiles without a GPU)."""
     srcs = [os.path.join(CSRC, s) for s in SOURCES]
-    deps = srcs + [os.path.join(CSRC, h) for h in ("common.cuh", "kernels.cuh", "raygen.cuh")] + [
+    deps = srcs + [os.path.join(CSRC, h) for h in ("common.cuh", "kernels.cuh", "raygen.cuh", "backward.cuh")] + [
         os.path.join(_HERE, "..", "include", "snrf.h")
     ]
     if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):

@@ -12,6 +12,7 @@
 #include "../../include/snrf.h"
 #include "kernels.cuh"
 #include "raygen.cuh"
+#include "backward.cuh"
 
 using namespace snrf;
 
@@ -100,6 +101,7 @@ struct snrf_ctx {
   DevBuf pdf_u;
   DevBuf sam_t[2], sam_w[2], hbar[2][2], feat_f16, hid_f16, q_feat, q_h1, q_h2, q_sel, q_x;
   DevBuf cam_rows, cam_cols, cam_o, cam_d;  // snrf_generate_rays / snrf_render_camera
+  DevBuf bwd_scratch, bwd_sink;             // snrf_feature_backward
 };
 
 namespace {
@@ -277,6 +279,7 @@ void snrf_ctx_destroy(snrf_ctx* ctx) {
   for (DevBuf* b : bufs) b->release();
   ctx->sam_t[1].release(); ctx->sam_w[1].release();
   ctx->cam_rows.release(); ctx->cam_cols.release(); ctx->cam_o.release(); ctx->cam_d.release();
+  ctx->bwd_scratch.release(); ctx->bwd_sink.release();
   ctx->hbar[0][1].release(); ctx->hbar[1][0].release(); ctx->hbar[1][1].release();
   if (ctx->aux_feat) cudaStreamDestroy(ctx->aux_feat);
   if (ctx->aux_out) cudaStreamDestroy(ctx->aux_out);
@@ -944,6 +947,97 @@ int snrf_render_camera(snrf_ctx* ctx, const snrf_camera* cam, const int32_t* row
   LAUNCH(launch_raygen(R, s));
   return snrf_render_frame(ctx, R.origins, R.dirs, nullptr, nullptr, n, chunk, flags, opts, rgb, depth, acc, prop_depth,
                            sam, clipseg, stream);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// training side of the feature-field branch
+// ---------------------------------------------------------------------------------------------------
+int snrf_feature_forward(snrf_ctx* ctx, int which, const float* origins, const float* dirs, const float* sam_t,
+                         const float* sam_w, int64_t n_rays, float* out, void* enc_f16, void* stream) {
+  if (!ctx) return SNRF_E_INVALID;
+  if (which < 0 || which > 1 || n_rays < 0) return fail(ctx, SNRF_E_INVALID, "bad argument");
+  if (n_rays == 0) return SNRF_OK;
+  if (!origins || !dirs || !sam_t || !sam_w || !out) return fail(ctx, SNRF_E_INVALID, "null argument");
+  FeatureNet& f = ctx->feat[which];
+  if (!f.have_grid[0] || !f.have_grid[1] || !f.have_net)
+    return fail(ctx, SNRF_E_STATE, "%s parameters not uploaded", which == 0 ? "sam_field" : "clipseg");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CK(cudaSetDevice(ctx->device));
+  DevBuf& hbar = ctx->hbar[0][which];
+  CK(hbar.ensure(n_rays * 256 * 2));
+  SamParams S;
+  memset(&S, 0, sizeof(S));
+  S.origins = origins;
+  S.dirs = dirs;
+  S.sam_t = sam_t;
+  S.sam_w = sam_w;
+  S.n_rays = n_rays;
+  S.enc[0] = f.grid[0];
+  S.enc[1] = f.grid[1];
+  S.w1 = f.w1_core.as<__half>();
+  S.hbar = hbar.as<__half>();
+  S.dbg_feat = reinterpret_cast<__half*>(enc_f16);
+  TIMED_LAUNCH(1, s, launch_sam(S, ctx->engine == 1, false, ctx->sm_count, s));
+  GemmParams G;
+  memset(&G, 0, sizeof(G));
+  G.a = hbar.as<__half>();
+  G.w = f.w2_core.as<__half>();
+  G.m = n_rays;
+  G.n = f.n_out;
+  G.taps = 1;
+  G.out_f32 = out;
+  G.out_mode = 0;
+  TIMED_LAUNCH(2, s, launch_tapgemm(G, ctx->engine == 1, ctx->sm_count, s));
+  return SNRF_OK;
+}
+
+int snrf_feature_backward(snrf_ctx* ctx, int which, const float* origins, const float* dirs, const float* sam_t,
+                          const float* sam_w, int64_t n_rays, const float* d_out, const void* enc_f16,
+                          float* grad_net, float* grad_grid0, float* grad_grid1, void* stream) {
+  if (!ctx) return SNRF_E_INVALID;
+  if (which < 0 || which > 1 || n_rays < 0) return fail(ctx, SNRF_E_INVALID, "bad argument");
+  if (n_rays == 0) return SNRF_OK;
+  if (!origins || !dirs || !sam_t || !sam_w || !d_out || !enc_f16) return fail(ctx, SNRF_E_INVALID, "null argument");
+  FeatureNet& f = ctx->feat[which];
+  if (!f.have_grid[0] || !f.have_grid[1] || !f.have_net)
+    return fail(ctx, SNRF_E_STATE, "%s parameters not uploaded", which == 0 ? "sam_field" : "clipseg");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CK(cudaSetDevice(ctx->device));
+  CK(ctx->bwd_scratch.ensure(feat_bwd_scratch_floats(n_rays) * sizeof(float)));
+  FeatBwdParams B;
+  memset(&B, 0, sizeof(B));
+  B.origins = origins;
+  B.dirs = dirs;
+  B.sam_t = sam_t;
+  B.sam_w = sam_w;
+  B.d_out = d_out;
+  B.x = reinterpret_cast<const __half*>(enc_f16);
+  B.w1 = f.w1_rm.as<__half>();
+  B.w2 = f.w2_rm.as<__half>();
+  B.n_rays = n_rays;
+  B.n_out = f.n_out;
+  B.enc[0] = f.grid[0];
+  B.enc[1] = f.grid[1];
+  B.d_hbar = ctx->bwd_scratch.as<float>();
+  // a frozen parameter's gradient goes to a sink so that the kernels stay branch-free
+  const size_t n_net = 256 * 192 + static_cast<size_t>(f.n_out) * 256;
+  const size_t n_g0 = static_cast<size_t>(f.grid[0].lv[11].offset + f.grid[0].lv[11].size) * 8;
+  const size_t n_g1 = static_cast<size_t>(f.grid[1].lv[11].offset + f.grid[1].lv[11].size) * 8;
+  size_t sink = 0;
+  if (!grad_net) sink = n_net;
+  if (!grad_grid0 && n_g0 > sink) sink = n_g0;
+  if (!grad_grid1 && n_g1 > sink) sink = n_g1;
+  if (sink) CK(ctx->bwd_sink.ensure(sink * sizeof(float)));
+  float* sinkp = ctx->bwd_sink.as<float>();
+  B.g_w1 = grad_net ? grad_net : sinkp;
+  B.g_w2 = grad_net ? grad_net + 256 * 192 : sinkp;
+  B.g_table[0] = grad_grid0 ? grad_grid0 : sinkp;
+  B.g_table[1] = grad_grid1 ? grad_grid1 : sinkp;
+  int64_t launched = 0;
+  const cudaError_t e = launch_feat_backward(B, s, &launched);
+  ctx->launches += launched;
+  if (e != cudaSuccess) return fail(ctx, SNRF_E_CUDA, "feature backward failed: %s", cudaGetErrorString(e));
+  return SNRF_OK;
 }
 
 int snrf_sample(snrf_ctx* ctx, const float* origins, const float* dirs, const float* nears, const float* fars,

@@ -17,13 +17,32 @@
 
 namespace snrf {
 
-// a*b+c WITHOUT fma contraction, so that device, host emulation and the torch oracle round alike
+// a*b and a*b+c WITHOUT fma contraction, so that device, host emulation and the torch oracle round alike
+SNRF_HD float mul_rn(float a, float b) {
+#ifdef __CUDA_ARCH__
+  return __fmul_rn(a, b);
+#else
+  volatile float m = a * b;
+  return m;
+#endif
+}
 SNRF_HD float mul_add_rn(float a, float b, float c) {
 #ifdef __CUDA_ARCH__
   return __fadd_rn(__fmul_rn(a, b), c);
 #else
   volatile float m = a * b;
   return m + c;
+#endif
+}
+// Frustums.get_positions for a sample stored as tm2 = start + end: o + d * (start + end) / 2 (rays.py:48-57),
+// op for op what march.cu / sam.cu compute
+SNRF_HD float sample_coord(float o, float d, float tm2) {
+#ifdef __CUDA_ARCH__
+  return __fadd_rn(o, __fmul_rn(d, tm2) / 2.f);
+#else
+  volatile float m = d * tm2;
+  volatile float h = m / 2.f;
+  return o + h;
 #endif
 }
 

@@ -14,8 +14,10 @@ Same class names, argument meaning and return keys as the reference modules they
     samnerf/sam_model.py:126,179                                MeanRenderer, SAMModel
 
 Every method that computes something calls into the CUDA library (through ``renderer.Renderer``); nothing here
-falls back to PyTorch math.  Inference (eval-mode) semantics only - training-mode jitter and autograd are a
-"next" row (SURVEY.md section 8 f).
+falls back to PyTorch math.  Inference (eval-mode) semantics everywhere; the first training slice (SURVEY.md section 8
+f-1) is ``SAMModel.train()``: the ``sam_field`` parameter group is trained through ``snrf_feature_forward`` /
+``snrf_feature_backward`` behind a ``torch.autograd.Function`` while the geometry (proposal + nerfacto fields) stays
+frozen and deterministic (no jitter); their backward is the remaining part of that row.
 """
 from __future__ import annotations
 
@@ -27,7 +29,7 @@ from typing import Callable, Dict, List, Optional, Sequence, Tuple
 import torch
 
 from .config import SAMNeRFConfig, get_feature_size
-from .renderer import Renderer
+from .renderer import Camera, Renderer
 
 
 class FieldHeadNames(Enum):
@@ -349,6 +351,29 @@ class MeanRenderer:
 
 
 # ------------------------------------------------------------------------------------------------
+# training side of the feature branch
+# ------------------------------------------------------------------------------------------------
+class _FeatureBranchFn(torch.autograd.Function):
+    """``MeanRenderer(SAMField.get_outputs(sam_samples))`` (sam_model.py:256-277, sam_field.py:112-140) with
+    libsnrf's forward and backward kernels.  The flat parameters are inputs only so that autograd routes their
+    gradients; the values used are the ones uploaded to the library (``SAMModel._sync_params``)."""
+
+    @staticmethod
+    def forward(ctx, net, grid0, grid1, renderer, which, origins, directions, sam_t, sam_w):
+        out, enc = renderer.feature_forward(which, origins, directions, sam_t, sam_w, save_for_backward=True)
+        ctx.renderer, ctx.which = renderer, which
+        ctx.save_for_backward(origins, directions, sam_t, sam_w, enc)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        origins, directions, sam_t, sam_w, enc = ctx.saved_tensors
+        want = [k for k, need in zip(("net", "grid0", "grid1"), ctx.needs_input_grad[:3]) if need]
+        g = ctx.renderer.feature_backward(ctx.which, origins, directions, sam_t, sam_w, enc, d_out.contiguous(), want=want)
+        return g.get("net"), g.get("grid0"), g.get("grid1"), None, None, None, None, None, None
+
+
+# ------------------------------------------------------------------------------------------------
 # the model
 # ------------------------------------------------------------------------------------------------
 class SAMModel:
@@ -381,7 +406,106 @@ class SAMModel:
         base_pipeline.py:109-115,366-375); tensors off the hot path are ignored."""
         from .checkpoint import params_from_state_dict
 
-        self.renderer.load_params(params_from_state_dict(state_dict))
+        self._loaded = params_from_state_dict(state_dict)
+        self.renderer.load_params(self._loaded)
+        self.params = {}  # trainable copies are (re)built by train()
+
+    # ---- training (first slice of SURVEY 8 f-1: the sam_field / conv parameter groups) -------------
+    def train(self, mode: bool = True):
+        """Training mode: the ``sam_field`` tensors become fp32 ``nn.Parameter``s on the device whose gradients
+        come from libsnrf's backward kernels; the conv head (patch_size > 1) runs as a torch module so that autograd
+        covers it.  The collider switches to its training near plane (scene_colliders.py:185).  Geometry is
+        frozen and sampled deterministically - its backward / jitter are not built yet."""
+        self.training = bool(mode)
+        self.collider.training = self.training
+        if not self.training:
+            self._sync_params(eval_conv=True)
+            return self
+        if not self.config.distill_sam:
+            raise RuntimeError("training needs distill_sam (the only trainable group built so far is sam_field)")
+        loaded = getattr(self, "_loaded", None)
+        if loaded is None:
+            raise RuntimeError("load_state_dict() before train(): the fp32 master copies come from there")
+        dev = self.renderer.device
+        if not getattr(self, "params", None):
+            self.params, self._uploaded = {}, {}
+            for which in ("sam", "clipseg"):
+                for name in Renderer.FEATURE_PARAMS[which]:
+                    if name in loaded:
+                        self.params[name] = torch.nn.Parameter(loaded[name].to(dev, torch.float32).reshape(-1).clone())
+                        self._uploaded[name] = self.params[name]._version
+            if "conv_head.0.weight" in loaded:
+                k = self.config.kernel_size
+                self.conv_head = torch.nn.Sequential(
+                    torch.nn.Conv2d(256, 256, k, stride=1, padding=(k - 1) // 2), torch.nn.ReLU(inplace=True),
+                    torch.nn.Conv2d(256, 256, k, stride=1, padding=(k - 1) // 2)).to(dev)
+                self.conv_head.load_state_dict({n[len("conv_head."):]: v for n, v in loaded.items() if n.startswith("conv_head.")})
+                self._conv_uploaded = [p._version for p in self.conv_head.parameters()]
+        return self
+
+    def eval(self):
+        return self.train(False)
+
+    def get_param_groups(self) -> Dict[str, List[torch.nn.Parameter]]:
+        """sam_model.py:330-335 - the groups built so far (``proposal_networks`` / ``fields`` are frozen)."""
+        groups = {"sam_field": list(getattr(self, "params", {}).values())}
+        if getattr(self, "conv_head", None) is not None:
+            groups["conv"] = list(self.conv_head.parameters())
+        return groups
+
+    def state_dict(self) -> Dict[str, torch.Tensor]:
+        """Hot-path tensors under the reference's names (trained values where training has happened)."""
+        sd = dict(getattr(self, "_loaded", {}))
+        for name, p in getattr(self, "params", {}).items():
+            sd[name] = p.detach().cpu().clone()
+        if getattr(self, "conv_head", None) is not None:
+            for n, v in self.conv_head.state_dict().items():
+                sd["conv_head." + n] = v.detach().cpu().clone()
+        return sd
+
+    def _sync_params(self, eval_conv: bool = False) -> None:
+        """Push parameters an optimiser step has changed (tensor version counters) back into the library's packed
+        fp16 copies - the re-upload SURVEY 8 b asks for."""
+        r = self.renderer
+        for which in ("sam", "clipseg"):
+            names = Renderer.FEATURE_PARAMS[which]
+            changed = {}
+            for slot, name in zip(("net", "grid0", "grid1"), names):
+                p = getattr(self, "params", {}).get(name)
+                if p is not None and p._version != self._uploaded[name]:
+                    changed[slot] = p
+                    self._uploaded[name] = p._version
+            if changed:
+                r.upload_feature_params(which, **changed)
+        conv = getattr(self, "conv_head", None)
+        if eval_conv and conv is not None:
+            versions = [p._version for p in conv.parameters()]
+            if versions != self._conv_uploaded:
+                sd = conv.state_dict()
+                r.upload_conv_head(*[sd[k] for k in ("0.weight", "0.bias", "2.weight", "2.bias")])
+                self._conv_uploaded = versions
+
+    def _get_outputs_training(self, ray_bundle: RayBundle, get_feature, fast: bool):
+        cfg, r = self.config, self.renderer
+        self._sync_params()
+        bg = _resolve_background(self.renderer_rgb.background_color)
+        with torch.no_grad():
+            out = r.render(ray_bundle.origins, ray_bundle.directions, ray_bundle.nears, ray_bundle.fars, get_feature=(),
+                           fast=fast, background=bg, picks=True)
+        sam_t, sam_w = out.pop("_sam_t"), out.pop("_sam_w")
+        o = r._prep(ray_bundle.origins, 3)
+        d = r._prep(ray_bundle.directions, 3)
+        for which in ("sam", "clipseg"):
+            names = Renderer.FEATURE_PARAMS[which]
+            if which not in get_feature or names[0] not in self.params:
+                continue
+            feat = _FeatureBranchFn.apply(*[self.params[n] for n in names], r, which, o, d, sam_t, sam_w)
+            if which == "sam" and cfg.patch_size > 1:  # sam_model.py:260-265
+                p = cfg.patch_size
+                feat = feat.reshape(-1, p, p, feat.shape[-1]).permute(0, 3, 1, 2)
+                feat = self.conv_head(feat).mean(dim=[2, 3])
+            out[which] = feat
+        return out
 
     @classmethod
     def from_checkpoint(cls, path: str, device: int = 0, engine: str = "tcgen05", base: Optional[SAMNeRFConfig] = None):
@@ -395,9 +519,6 @@ class SAMModel:
         model.step = step
         return model
 
-    def eval(self):
-        return self
-
     # sam_model.py:303-314
     def forward(self, ray_bundle: RayBundle, **kwargs):
         if self.collider is not None:
@@ -410,6 +531,8 @@ class SAMModel:
     def get_outputs(self, ray_bundle: RayBundle, get_rgbsigma=True, get_feature=("sam", "dino", "clipseg"), fast=False):
         cfg = self.config
         feats = [f for f in get_feature if f in ("sam", "clipseg")] if cfg.distill_sam else []
+        if self.training:
+            return self._get_outputs_training(ray_bundle, feats, fast)
         bg = _resolve_background(self.renderer_rgb.background_color)
         out = self.renderer.render(
             ray_bundle.origins, ray_bundle.directions, ray_bundle.nears, ray_bundle.fars, get_feature=feats,
@@ -454,4 +577,25 @@ class SAMModel:
                 for i in range(0, len(cb), chunk):
                     feats.append(self.forward(cb[i:i + chunk], get_feature=["clipseg"])["clipseg"])
                 outputs["clipseg"] = torch.cat(feats).view(32, 32, -1)
+        return outputs
+
+    @torch.no_grad()
+    def get_outputs_for_camera(self, camera: Camera, fast: bool = False) -> Dict[str, torch.Tensor]:
+        """``get_outputs_for_camera_ray_bundle(cameras.generate_rays(i, keep_shape=True))`` without the ray bundle
+        (SURVEY.md 8 f-2): the three loops of sam_model.py:354-406 each become one ``snrf_render_camera`` call that
+        generates its rays on the device - LOOP A every pixel, LOOP B the ``fh*p x fw*p`` strided sub-grid in
+        patch-major order through the conv head, LOOP C the 32 x 32 ClipSeg grid."""
+        cfg, r = self.config, self.renderer
+        h, w = camera.height, camera.width
+        outputs = {k: v.view(h, w, -1) for k, v in r.render_camera(camera, get_feature=(), fast=fast).items()}
+        if cfg.distill_sam:
+            fh, fw = get_feature_size(h, w)
+            p = cfg.patch_size
+            hi = torch.linspace(0, h - 1, fh * p, dtype=torch.long)
+            wi = torch.linspace(0, w - 1, fw * p, dtype=torch.long)
+            outputs["sam"] = r.render_camera(camera, rows=hi, cols=wi, get_feature=("sam",), patch=p > 1)["sam"].view(fh, fw, -1)
+            if cfg.use_clipseg_feature:
+                hi = torch.linspace(0, h - 1, 32, dtype=torch.long)
+                wi = torch.linspace(0, w - 1, 32, dtype=torch.long)
+                outputs["clipseg"] = r.render_camera(camera, rows=hi, cols=wi, get_feature=("clipseg",))["clipseg"].view(32, 32, -1)
         return outputs

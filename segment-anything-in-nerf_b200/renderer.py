@@ -181,10 +181,14 @@ class Renderer:
             else:
                 self.have_clipseg = True
         if "conv_head.0.weight" in params:
-            ts = [params[k].detach().to(torch.float32).contiguous()
-                  for k in ("conv_head.0.weight", "conv_head.0.bias", "conv_head.2.weight", "conv_head.2.bias")]
-            self._check(lib.snrf_upload_conv_head(self.h, *[x.data_ptr() for x in ts], s))
-            self.have_conv = True
+            self.upload_conv_head(*[params[k] for k in ("conv_head.0.weight", "conv_head.0.bias", "conv_head.2.weight",
+                                                        "conv_head.2.bias")])
+
+    def upload_conv_head(self, w0: torch.Tensor, b0: torch.Tensor, w2: torch.Tensor, b2: torch.Tensor) -> None:
+        """``conv_head.{0,2}.{weight,bias}`` (sam_model.py:202-208), host or device tensors."""
+        ts = [t.detach().to(torch.float32).contiguous() for t in (w0, b0, w2, b2)]
+        self._check(self.lib.snrf_upload_conv_head(self.h, *[x.data_ptr() for x in ts], self.stream))
+        self.have_conv = True
 
     # ------------------------------------------------------------------------------------------
     def _opts(self, background=None) -> L.RenderOpts:
@@ -218,6 +222,7 @@ class Renderer:
         background=None,
         debug: bool = False,
         out: Optional[Dict[str, torch.Tensor]] = None,
+        picks: bool = False,
     ) -> Dict[str, torch.Tensor]:
         """One chunk of rays: ``SAMModel.forward`` in eval mode (samnerf/sam_model.py:226-314).
         ``out``: optional preallocated CUDA output tensors (e.g. row slices of frame buffers) to write into."""
@@ -268,6 +273,14 @@ class Renderer:
             if flags & L.WANT_SAM:
                 out["_sam_feat"] = torch.empty(n, k, cfg.sam_in, device=dev, dtype=torch.float16)
                 dbg.sam_feat = out["_sam_feat"].data_ptr()
+        if picks and not debug:
+            # the top-k picks only (what the training side of the feature branch needs): 2 x midpoint t and the
+            # sharpened, renormalised weights of the k samples (sam_model.py:244-255)
+            k = cfg.num_sam_samples
+            out["_sam_t"] = torch.empty(n, k, device=dev)
+            out["_sam_w"] = torch.empty(n, k, device=dev)
+            dbg = L.DebugOut()
+            dbg.sam_t, dbg.sam_w = out["_sam_t"].data_ptr(), out["_sam_w"].data_ptr()
         opts = self._opts(background)
         rc = self.lib.snrf_render(
             self.h, o.data_ptr(), d.data_ptr(), _ptr(nr), _ptr(fr), n, flags, C.byref(opts),
@@ -358,6 +371,67 @@ class Renderer:
             out["depth"].data_ptr(), _ptr(out.get("accumulation")), _ptr(out.get("prop_depth_0")), _ptr(out.get("sam")),
             _ptr(out.get("clipseg")), self.stream))
         return out
+
+    # ---- training side of the feature-field branch --------------------------------
+    FEATURE_PARAMS = {
+        "sam": ("sam_field.sam_net.params", "sam_field.clip_encs.0.params", "sam_field.clip_encs.1.params"),
+        "clipseg": ("sam_field.clipseg_net.params", "sam_field.clipseg_encs.0.params", "sam_field.clipseg_encs.1.params"),
+    }
+
+    def upload_feature_params(self, which: str, net: Optional[torch.Tensor] = None, grid0: Optional[torch.Tensor] = None,
+                              grid1: Optional[torch.Tensor] = None) -> None:
+        """Re-upload (fp32 -> packed fp16) whichever of the branch's flat parameter tensors changed, e.g. after an
+        optimiser step (host or device tensors)."""
+        cfg, w, s = self.cfg, {"sam": 0, "clipseg": 1}[which], self.stream
+        for i, t in enumerate((grid0, grid1)):
+            if t is not None:
+                t = t.detach().to(torch.float32).contiguous().view(-1)
+                d = grid_desc(cfg.sam_grids[i])
+                self._check(self.lib.snrf_upload_feature_grid(self.h, w, i, t.data_ptr(), t.numel(), C.byref(d), s))
+        if net is not None:
+            t = net.detach().to(torch.float32).contiguous().view(-1)
+            n_out = cfg.sam_out if which == "sam" else cfg.clipseg_out
+            self._check(self.lib.snrf_upload_feature_net(self.h, w, t.data_ptr(), t.numel(), n_out, s))
+
+    def feature_forward(self, which: str, origins, directions, sam_t, sam_w, save_for_backward: bool = True):
+        """``MeanRenderer(SAMField.get_outputs(picked samples))`` from the picks of a render (``_sam_t`` / ``_sam_w``
+        of ``render(debug=True)``): returns ``out[N,n_out]`` and the fp16 encoder outputs ``[N,16,192]`` the
+        backward pass needs (``None`` when not saved)."""
+        o, d = self._prep(origins, 3), self._prep(directions, 3)
+        t, w = self._prep(sam_t, 16), self._prep(sam_w, 16)
+        n = o.shape[0]
+        n_out = self.cfg.sam_out if which == "sam" else self.cfg.clipseg_out
+        out = torch.empty(n, n_out, device=self.device)
+        enc = torch.empty(n, 16, self.cfg.sam_in, device=self.device, dtype=torch.float16) if save_for_backward else None
+        self._check(self.lib.snrf_feature_forward(self.h, {"sam": 0, "clipseg": 1}[which], o.data_ptr(), d.data_ptr(),
+                                                  t.data_ptr(), w.data_ptr(), n, out.data_ptr(), _ptr(enc), self.stream))
+        return out, enc
+
+    def feature_backward(self, which: str, origins, directions, sam_t, sam_w, enc: torch.Tensor, d_out: torch.Tensor,
+                         grads: Optional[Dict[str, torch.Tensor]] = None, want: Sequence[str] = ("net", "grid0", "grid1")):
+        """Gradients of the branch's flat fp32 parameters, accumulated (+=) into ``grads`` (``net`` / ``grid0`` /
+        ``grid1``; missing ones are created as zeros).  Only the entries in ``want`` are computed and returned."""
+        cfg = self.cfg
+        o, d = self._prep(origins, 3), self._prep(directions, 3)
+        t, w = self._prep(sam_t, 16), self._prep(sam_w, 16)
+        n = o.shape[0]
+        n_out = cfg.sam_out if which == "sam" else cfg.clipseg_out
+        g = d_out.to(device=self.device, dtype=torch.float32).reshape(n, n_out).contiguous()
+        assert enc.is_cuda and enc.dtype == torch.float16 and enc.is_contiguous() and enc.numel() == n * 16 * cfg.sam_in
+        sizes = {"net": cfg.sam_hidden * cfg.sam_in + n_out * cfg.sam_hidden,
+                 "grid0": cfg.sam_grids[0].n_params, "grid1": cfg.sam_grids[1].n_params}
+        grads = {} if grads is None else grads
+        res = {}
+        for k in want:
+            if k not in grads:
+                grads[k] = torch.zeros(sizes[k], device=self.device)
+            gk = grads[k]
+            assert gk.is_cuda and gk.dtype == torch.float32 and gk.is_contiguous() and gk.numel() == sizes[k], k
+            res[k] = gk
+        self._check(self.lib.snrf_feature_backward(
+            self.h, {"sam": 0, "clipseg": 1}[which], o.data_ptr(), d.data_ptr(), t.data_ptr(), w.data_ptr(), n,
+            g.data_ptr(), enc.data_ptr(), _ptr(res.get("net")), _ptr(res.get("grid0")), _ptr(res.get("grid1")), self.stream))
+        return res
 
     def sample(self, origins, directions, nears=None, fars=None):
         """Proposal weights ``[N,64]``, nerf bin edges ``[N,33]`` and proposal median depth ``[N,1]``."""

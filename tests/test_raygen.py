@@ -148,3 +148,27 @@ def test_gpu_render_camera_equals_render_frame():
     assert torch.equal(got, want)
     with pytest.raises(RuntimeError, match="outside the image"):
         r.generate_rays(cam, rows=torch.tensor([0, 48]), cols=cols)
+
+
+@pytest.mark.gpu
+@pytest.mark.hw_unverified
+def test_gpu_model_from_camera_equals_model_from_ray_bundle():
+    """SAMModel.get_outputs_for_camera == get_outputs_for_camera_ray_bundle on the rays of the same camera."""
+    from helpers import model_pair
+    from samnerf_b200.nerfstudio_api import RayBundle, SAMModel
+    from samnerf_b200.renderer import Camera
+    from samnerf_b200.synthetic import look_at
+
+    cfg, params, _ = model_pair("tiny", "scene", 6, True, 4)
+    m = SAMModel(cfg)
+    m.load_state_dict(params)
+    cam = Camera(32.0, 32.0, 16.0, 12.0, 32, 24, look_at((1.1, 0.6, 0.45))[:3, :4])
+    o, d, _ = m.renderer.generate_rays(cam)
+    bundle = RayBundle(origins=o.view(24, 32, 3), directions=d.view(24, 32, 3), pixel_area=torch.ones(24, 32, 1, device=o.device),
+                       camera_indices=torch.zeros(24, 32, 1, dtype=torch.long, device=o.device))
+    want = m.get_outputs_for_camera_ray_bundle(bundle)
+    got = m.get_outputs_for_camera(cam)
+    torch.cuda.synchronize()
+    assert set(got) == set(want)
+    for k in want:
+        assert torch.equal(got[k], want[k]), k
