@@ -197,6 +197,8 @@ def run_native(args):
     params = make_synthetic_params(cfg, args.regime, 0)
     r = Renderer(cfg, device=local, engine=args.engine)
     r.load_params(params)
+    if args.early_termination > 0:
+        r.set_early_termination(args.early_termination)  # opt-in, not the reference's exact arithmetic: see config
     o_all, d_all = frame_rays()
     n_all = o_all.shape[0]
     assert H % world == 0
@@ -373,6 +375,7 @@ def run_native(args):
                        "l2": "256 MiB buffer zeroed between timed frames (untimed); tables 158 MB + outputs 668 MB > 126 MB L2",
                        "tiles": (f"{world} row blocks of {H // world} rows; 256-d features exchanged by {gather_mode}, "
                                  "frame ends with a symmetric-memory barrier") if world > 1 else "single GPU",
+                       "early_termination": args.early_termination or None,
                        "chunk": chunk, "pipeline": "chunks pipelined over 3 streams" if (args.pipeline == 2 or (args.pipeline == 1 and world > 1 and symm is not None and args.gather in ("mc", "peer"))) else "sequential"},
             "roofline": {"bound": "hbm", "kernel": "sam_kernel (feature-field gather + MLP layer 1 + weighted sum)",
                          "achieved": ach, "peak": peak, "unit": "GB/s", "frac": (ach / peak) if ach else None,
@@ -413,6 +416,9 @@ def main():
     ap.add_argument("--chunk", type=int, default=0, help="rays per chunk (default: 32768, finer with N > 1)")
     ap.add_argument("--pipeline", type=int, default=1, choices=[0, 1, 2],
                     help="chunk pipelining over 3 streams: 0 off, 1 auto (only with replicated outputs, N > 1), 2 always")
+    ap.add_argument("--early-termination", type=float, default=0.0,
+                    help="opt-in transmittance threshold below which a ray's last 16 nerf samples are skipped "
+                         "(0 = exact, the default and the headline configuration)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-rays", type=int, default=16384)
     ap.add_argument("--ref-rays", type=int, default=4096)

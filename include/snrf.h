@@ -57,6 +57,12 @@ const char* snrf_last_error(snrf_ctx* ctx); /* valid until the next call on ctx;
 /* tensor-core engine for the 192->256->{256,192} feature MLP and the conv head:
  * 1 = tcgen05.mma + TMEM (default), 0 = mma.sync (the recompiled-legacy comparison path). */
 int snrf_set_engine(snrf_ctx* ctx, int engine);
+/* Early termination of the nerfacto field along a ray (opt-in, default 0 = exact): when the transmittance left after
+ * the first 16 of the 32 nerf samples is below eps, the remaining 16 samples are not evaluated and get weight 0.
+ * Bounds: |rgb|, |accumulation| move by <= eps; the median depth and the top-k features are unaffected for
+ * eps < 0.5 up to the eps-weighted tail; per-sample debug outputs of skipped samples read 0.  The reference never
+ * terminates early, hence opt-in. */
+int snrf_set_early_termination(snrf_ctx* ctx, float eps);
 /* eval-mode PDF sample positions u[33] = linspace(0, 1-1/33, 33) + 1/66 (ray_samplers.py:325-327).  The
  * library computes the same table itself; a host may override it so that both sides share the bits. */
 int snrf_set_pdf_u(snrf_ctx* ctx, const float* u_host, int n);

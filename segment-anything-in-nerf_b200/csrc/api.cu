@@ -65,6 +65,7 @@ struct snrf_ctx {
   int device = 0;
   int sm_count = 148;
   int engine = 1;
+  float et_eps = 0.f;  // snrf_set_early_termination
   std::string err;
   int64_t launches = 0;
   // proposal field
@@ -301,6 +302,12 @@ const char* snrf_last_error(snrf_ctx* ctx) { return ctx ? ctx->err.c_str() : g_n
 int snrf_set_engine(snrf_ctx* ctx, int engine) {
   if (!ctx || (engine != 0 && engine != 1)) return fail(ctx, SNRF_E_INVALID, "engine must be 0 (mma.sync) or 1 (tcgen05)");
   ctx->engine = engine;
+  return SNRF_OK;
+}
+
+int snrf_set_early_termination(snrf_ctx* ctx, float eps) {
+  if (!ctx || !(eps >= 0.f) || eps >= 0.5f) return fail(ctx, SNRF_E_INVALID, "early-termination threshold must be in [0, 0.5)");
+  ctx->et_eps = eps;
   return SNRF_OK;
 }
 
@@ -570,6 +577,7 @@ static int fill_march(snrf_ctx* ctx, MarchParams& M, const float* origins, const
   M.bg[2] = o->bg[2];
   M.k_sam = o->k_sam;
   M.sharpen = o->sharpen;
+  M.et_eps = ctx->et_eps;
   return SNRF_OK;
 }
 

@@ -65,6 +65,7 @@ struct MarchParams {
   float* dbg_weights; // [N,32]
   float* dbg_density; // [N,32]
   float* dbg_rgb;     // [N,32,3]
+  float et_eps;       // early-termination transmittance threshold, 0 = exact (see march_kernel<.., ET>)
 };
 cudaError_t launch_march(const MarchParams& P, int sm_count, cudaStream_t stream);
 

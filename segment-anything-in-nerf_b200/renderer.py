@@ -142,6 +142,11 @@ class Renderer:
         self._check(self.lib.snrf_kernel_times(self.h, ms, cnt))
         return {k: (ms[i], cnt[i]) for i, k in enumerate(("march", "feature", "tapgemm"))}
 
+    def set_early_termination(self, eps: float) -> None:
+        """Opt-in: skip the second half of a ray's nerfacto samples once the transmittance is below ``eps``
+        (0 = exact, the default).  See ``snrf_set_early_termination`` for the error bounds."""
+        self._check(self.lib.snrf_set_early_termination(self.h, float(eps)))
+
     def set_engine(self, engine: str) -> None:
         """``tcgen05`` (default) or ``mma_sync`` (the recompiled-legacy comparison path)."""
         self.engine = engine

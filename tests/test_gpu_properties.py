@@ -137,3 +137,30 @@ def test_replication_descriptor_is_validated(full):
     torch.cuda.synchronize()
     r.set_replication("sam", None)
     assert torch.equal(frame, mirror) and torch.isfinite(frame).any()
+
+
+@pytest.mark.hw_unverified
+def test_early_termination_stays_within_its_bounds(full):
+    """Opt-in early termination (snrf_set_early_termination): rgb / accumulation within eps, depth and features
+    unchanged up to the eps-weighted tail; switching it off restores the exact bits."""
+    cfg, r = full
+    o, d = test_rays(6000, seed=12)
+    o, d = o.cuda(), d.cuda()
+    exact = r.render(o, d, get_feature=("sam",))
+    eps = 1e-4
+    r.set_early_termination(eps)
+    try:
+        et = r.render(o, d, get_feature=("sam",))
+        torch.cuda.synchronize()
+    finally:
+        r.set_early_termination(0.0)
+    assert float((et["rgb"] - exact["rgb"]).abs().max()) <= 2 * eps
+    assert float((et["accumulation"] - exact["accumulation"]).abs().max()) <= 2 * eps
+    assert float((et["depth"] == exact["depth"]).float().mean()) > 0.999
+    ok = torch.isfinite(exact["sam"]).all(-1) & torch.isfinite(et["sam"]).all(-1)
+    rel = torch.linalg.norm(et["sam"][ok] - exact["sam"][ok], dim=-1) / torch.linalg.norm(exact["sam"][ok], dim=-1).clamp_min(1e-6)
+    assert float((rel < 1e-3).float().mean()) > 0.999
+    again = r.render(o, d, get_feature=("sam",))
+    assert torch.equal(again["rgb"], exact["rgb"]) and torch.equal(again["sam"], exact["sam"])
+    with pytest.raises(RuntimeError, match="threshold"):
+        r.set_early_termination(0.7)
