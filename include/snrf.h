@@ -227,6 +227,26 @@ int snrf_feature_backward(snrf_ctx* ctx, int which, const float* origins, const 
                           const float* sam_w, int64_t n_rays, const float* d_out, const void* enc_f16,
                           float* grad_net, float* grad_grid0, float* grad_grid1, void* stream);
 
+/* Backward of the density fields at arbitrary sample positions - the counterpart of snrf_query_density /
+ * snrf_query_rgb, i.e. what tinycudann's autograd does for HashMLPDensityField (density_fields.py:92-125) and
+ * TCNNNerfactoField (nerfacto_field.py:157-175,228-351) while torch autograd handles weights, compositing and the
+ * losses on [N,S] tensors.  which: 0 = proposal field, 1 = nerfacto field.  xyz[n,3] world positions; dirs[n,3]
+ * (nerfacto with d_rgb, else NULL); d_density[n] / d_rgb[n,3]: upstream gradients, either may be NULL.
+ * grad_base: flat fp32 gradient of proposal_networks.0.mlp_base.params / field.mlp_base.params (MLP matrices, then the
+ * grid), grad_head: of field.mlp_head.params (needed with d_rgb).  Gradients are ACCUMULATED (+=).
+ * trunc_exp backward is g * exp(clamp(x, -15, 15)) (activations.py:33-37). */
+int snrf_field_backward(snrf_ctx* ctx, int which, const float* xyz, const float* dirs, int64_t n,
+                        const float* d_density, const float* d_rgb, float* grad_base, float* grad_head, void* stream);
+
+/* Backward of the two ray-wise ops that carry gradients in training (torch autograd in the reference):
+ * mode 0  RaySamples.get_weights (rays.py:141-163): a = deltas[N,S], b = densities[N,S], g = dL/dweights[N,S]
+ *         -> out_a = dL/ddensities[N,S] (out_b unused; deltas are detached, ray_samplers.py:357);  S <= 64
+ * mode 3  RGBRenderer.combine_rgb (renderers.py:69-112): a = rgb[N,S,3], b = weights[N,S], g = dL/drgb_out[N,3]
+ *         -> out_a = dL/drgb[N,S,3], out_b = dL/dweights[N,S]; bg_mode / bg_host as in snrf_ray_op.
+ * Outputs are WRITTEN (not accumulated). */
+int snrf_ray_op_backward(snrf_ctx* ctx, int mode, const float* a, const float* b, const float* g, float* out_a,
+                         float* out_b, int64_t n, int S, int bg_mode, const float* bg_host, void* stream);
+
 /* number of kernels this library has launched on ctx since creation (bench.py's gpu_launches) */
 int64_t snrf_launch_count(snrf_ctx* ctx);
 /* Bracket the three hot kernels of snrf_render with CUDA events on the launching stream (bench.py's roofline). */

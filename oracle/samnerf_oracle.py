@@ -34,6 +34,25 @@ def contract(x: torch.Tensor, order: Optional[float]) -> torch.Tensor:
     return torch.where(mag < 1, x, (2 - (1 / mag)) * (x / mag))
 
 
+class _TruncExp(torch.autograd.Function):
+    """``trunc_exp`` - nerfstudio/field_components/activations.py:24-40: forward ``exp(x)``, backward
+    ``g * exp(clamp(x, -15, 15))``."""
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.save_for_backward(x)
+        return torch.exp(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        return g * torch.exp(x.clamp(-15, 15))
+
+
+def trunc_exp(x: torch.Tensor) -> torch.Tensor:
+    return _TruncExp.apply(x) if x.requires_grad else torch.exp(x)
+
+
 def spacing_fn(x: torch.Tensor) -> torch.Tensor:
     """UniformLinDispPiecewiseSampler spacing - nerfstudio/model_components/ray_samplers.py:242."""
     return torch.where(x < 1, x / 2, 1 - 1 / (2 * x))
@@ -64,15 +83,17 @@ def median_depth(weights: torch.Tensor, starts: torch.Tensor, ends: torch.Tensor
     return torch.gather(steps, dim=-1, index=idx)
 
 
-def composite_rgb(rgb: torch.Tensor, weights: torch.Tensor, background=None) -> torch.Tensor:
-    """``RGBRenderer.forward`` in eval mode with ``background_color="last_sample"`` (or a fixed RGB override)
-    - renderers.py:69-140; nerfacto.py:77,220.  ``rgb[N,S,3]``, ``weights[N,S]`` -> ``[N,3]``."""
-    rgb = torch.nan_to_num(rgb)
+def composite_rgb(rgb: torch.Tensor, weights: torch.Tensor, background=None, training: bool = False) -> torch.Tensor:
+    """``RGBRenderer.forward`` with ``background_color="last_sample"`` (or a fixed RGB override)
+    - renderers.py:69-140; nerfacto.py:77,220.  ``rgb[N,S,3]``, ``weights[N,S]`` -> ``[N,3]``.
+    Eval mode adds ``nan_to_num`` on the samples and the final clamp (renderers.py:132-139); training has neither."""
+    if not training:
+        rgb = torch.nan_to_num(rgb)
     comp = torch.sum(weights[..., None] * rgb, dim=-2)
     acc = torch.sum(weights[..., None], dim=-2)
     bg = rgb[..., -1, :] if background is None else torch.as_tensor(background, dtype=torch.float32)
     comp = comp + bg * (1.0 - acc)
-    return torch.clamp(comp, 0.0, 1.0)
+    return comp if training else torch.clamp(comp, 0.0, 1.0)
 
 
 def get_feature_size(h: int, w: int, largesize: int = 64) -> Tuple[int, int]:
@@ -140,7 +161,7 @@ class Oracle:
         if pad:
             enc = torch.cat([enc, torch.zeros(enc.shape[0], pad)], dim=-1)  # grid encodings pad with 0
         h = T.mlp_forward(enc, self.prop_w)[:, 0]
-        return (torch.exp(h) * sel).view(shp)
+        return (trunc_exp(h) * sel).view(shp)
 
     def field_density(self, positions: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
         """``TCNNNerfactoField.get_density`` - nerfstudio/fields/nerfacto_field.py:242-266.
@@ -149,7 +170,7 @@ class Oracle:
         x, sel = self._normalized(positions.reshape(-1, 3), float("inf"))
         enc = T.hash_grid_encode(x, self.field_table, self.field_levels, self.cfg.field_grid.n_features)
         h = T.mlp_forward(enc, self.base_w)
-        density = torch.exp(h[:, 0]) * sel
+        density = trunc_exp(h[:, 0]) * sel
         return density.view(shp), h[:, 1 : 1 + self.cfg.geo_feat_dim].reshape(*shp, -1)
 
     def field_rgb(self, directions: torch.Tensor, geo: torch.Tensor) -> torch.Tensor:

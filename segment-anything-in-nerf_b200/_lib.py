@@ -84,6 +84,8 @@ SYMBOLS = {
                                 _P, _P, _P]),
     "snrf_feature_forward": (_I, [_P, _I, _P, _P, _P, _P, _L, _P, _P, _P]),
     "snrf_feature_backward": (_I, [_P, _I, _P, _P, _P, _P, _L, _P, _P, _P, _P, _P, _P]),
+    "snrf_field_backward": (_I, [_P, _I, _P, _P, _L, _P, _P, _P, _P, _P]),
+    "snrf_ray_op_backward": (_I, [_P, _I, _P, _P, _P, _P, _P, _L, _I, _I, _P, _P]),
     "snrf_launch_count": (_L, [_P]),
     "snrf_set_timing": (_I, [_P, _I]),
     "snrf_kernel_times": (_I, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),

@@ -1048,6 +1048,58 @@ int snrf_feature_backward(snrf_ctx* ctx, int which, const float* origins, const 
   return SNRF_OK;
 }
 
+int snrf_field_backward(snrf_ctx* ctx, int which, const float* xyz, const float* dirs, int64_t n,
+                        const float* d_density, const float* d_rgb, float* grad_base, float* grad_head, void* stream) {
+  if (!ctx) return SNRF_E_INVALID;
+  if (which < 0 || which > 1 || n < 0) return fail(ctx, SNRF_E_INVALID, "bad argument");
+  if (n == 0) return SNRF_OK;
+  if (!xyz || !grad_base || (!d_density && !d_rgb)) return fail(ctx, SNRF_E_INVALID, "null argument");
+  if (d_rgb && (which != 1 || !dirs || !grad_head))
+    return fail(ctx, SNRF_E_INVALID, "d_rgb needs the nerfacto field (which = 1), dirs and grad_head");
+  if (which == 0 ? !ctx->have_prop : !(ctx->have_base && (ctx->have_head || !d_rgb)))
+    return fail(ctx, SNRF_E_STATE, "field parameters not uploaded");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CK(cudaSetDevice(ctx->device));
+  CK(ctx->bwd_scratch.ensure(field_bwd_scratch_bytes(n)));
+  FieldBwdParams B;
+  memset(&B, 0, sizeof(B));
+  B.xyz = xyz;
+  B.dirs = dirs;
+  B.d_density = d_density;
+  B.d_rgb = d_rgb;
+  B.n = n;
+  B.which = which;
+  B.grid = which == 0 ? ctx->prop_grid : ctx->field_grid;
+  B.w1 = which == 0 ? ctx->prop_w1_rm.as<__half>() : ctx->base_w1_rm.as<__half>();
+  B.w2 = which == 0 ? ctx->prop_w2_rm.as<__half>() : ctx->base_w2_rm.as<__half>();
+  B.wh1 = ctx->head_w1_rm.as<__half>();
+  B.wh2 = ctx->head_w2_rm.as<__half>();
+  B.wh3 = ctx->head_w3_rm.as<__half>();
+  B.g_base = grad_base;
+  B.g_head = grad_head;
+  int64_t launched = 0;
+  const cudaError_t e = launch_field_backward(B, ctx->bwd_scratch.p, s, &launched);
+  ctx->launches += launched;
+  if (e != cudaSuccess) return fail(ctx, SNRF_E_CUDA, "field backward failed: %s", cudaGetErrorString(e));
+  return SNRF_OK;
+}
+
+int snrf_ray_op_backward(snrf_ctx* ctx, int mode, const float* a, const float* b, const float* g, float* out_a,
+                         float* out_b, int64_t n, int S, int bg_mode, const float* bg_host, void* stream) {
+  if (!ctx) return SNRF_E_INVALID;
+  if ((mode != 0 && mode != 3) || !a || !b || !g || !out_a || S <= 0 || n < 0) return fail(ctx, SNRF_E_INVALID, "bad argument");
+  if (mode == 0 && S > kMaxRaySamples) return fail(ctx, SNRF_E_INVALID, "get_weights backward supports up to %d samples per ray", kMaxRaySamples);
+  if (mode == 3 && !out_b) return fail(ctx, SNRF_E_INVALID, "missing output for dL/dweights");
+  if (n == 0) return SNRF_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CK(cudaSetDevice(ctx->device));
+  if (mode == 0)
+    LAUNCH(launch_weights_bwd(a, b, g, out_a, n, S, s));
+  else
+    LAUNCH(launch_rgb_bwd(a, b, g, bg_mode == SNRF_BG_FIXED ? 1 : 0, bg_host, out_a, out_b, n, S, s));
+  return SNRF_OK;
+}
+
 int snrf_sample(snrf_ctx* ctx, const float* origins, const float* dirs, const float* nears, const float* fars,
                 int64_t n_rays, const snrf_render_opts* opts, float* prop_weights, float* edges, float* prop_depth,
                 void* stream) {

@@ -1,48 +1,130 @@
-// Kernels F1-F5 - backward of the feature-field branch (see backward.cuh for the math and the reference lines).
-// First, simple version: one thread per output item, fp32 throughout, atomics for the reductions.  The dominant
-// cost is the table scatter (16 x 24 x 8 corners x 8 features = 24 576 fp32 atomics per ray, ~98 KB of
-// read-modify-write traffic per ray against 49 KB gathered by the forward pass); the fused tensor-core version that
-// mirrors sam.cu is the next step once this one is parity-green on hardware.
+// Kernels F* (feature branch) and D* (density fields) - the backward passes of backward.cuh.  First, simple version:
+// one thread per output item, fp32 throughout, atomics for the reductions; forward activations are recomputed with
+// the component-query kernels of query.cu.  The dominant cost of the feature branch is the table scatter
+// (16 x 24 x 8 corners x 8 features = 24 576 fp32 atomics per ray, ~98 KB of read-modify-write traffic per ray against
+// 49 KB gathered by the forward pass); the fused tensor-core version that mirrors sam.cu is the next step once this
+// one is parity-green on hardware.
+#include <string.h>
+
 #include "backward.cuh"
+#include "kernels.cuh"
 
 namespace snrf {
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kSlabRows = 256;  // rows reduced per thread before one atomicAdd (weight gradients)
+inline unsigned blocks_for(int64_t items) { return static_cast<unsigned>((items + kThreads - 1) / kThreads); }
 
-__global__ void bwd_dhbar_kernel(const FeatBwdParams P, int64_t items) {
+__global__ void mlp_dgrad_kernel(const float* dY, int ldy, int ny, const __half* W, int ldw, const __half* X, int ldx,
+                                 float* dX, int lddx, int nx, int64_t items) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i < items) bwd_dhbar_one(P, i);
-}
-__global__ void bwd_hidden_kernel(const FeatBwdParams P, int64_t items) {
-  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i < items) bwd_hidden_one(P, i);
-}
-__global__ void bwd_dx_kernel(const FeatBwdParams P, int64_t items) {
-  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i < items) bwd_dx_one(P, i);
+  if (i < items) mlp_dgrad_one(dY, ldy, ny, W, ldw, X, ldx, dX, lddx, nx, i);
 }
 template <typename TB>
-__global__ void bwd_wgrad_kernel(const float* A, int na, const TB* B, int nb, int64_t rows, float* C, int64_t items) {
+__global__ void mlp_wgrad_kernel(const float* A, int lda, int na, const TB* B, int ldb, int nb, int64_t rows, float* C,
+                                 int ldc, int64_t items) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i < items) bwd_wgrad_one<TB>(A, na, B, nb, rows, kSlabRows, C, i);
+  if (i < items) mlp_wgrad_one<TB>(A, lda, na, B, ldb, nb, rows, C, ldc, i);
 }
-__global__ void bwd_scatter_kernel(const FeatBwdParams P, int64_t items) {
+template <int F>
+__global__ void grid_scatter_kernel(const GridDev G, bool linf, bool selector, const float* xyz, const float* dX, int lddx,
+                                    int col0, float* g_table, int64_t items) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i < items) bwd_scatter_one(P, i);
+  if (i < items) grid_scatter_one<F>(G, linf, selector, xyz, dX, lddx, col0, g_table, i);
+}
+__global__ void feat_hidden_kernel(const FeatBwdParams P, int64_t items) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < items) feat_hidden_one(P, i);
+}
+__global__ void feat_positions_kernel(const FeatBwdParams P, int64_t items) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < items) feat_positions_one(P, i);
+}
+__global__ void sigmoid_bwd_kernel(const float* d_rgb, const __half* pre, int ldp, float* d_pre, int64_t items) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < items) sigmoid_bwd_one(d_rgb, pre, ldp, d_pre, i);
+}
+__global__ void density_bwd_kernel(const float* d_density, const __half* o, int ldo, const float* sel, const float* d_geo,
+                                   int ldg, int col_geo, float* d_o, int n_o, int64_t items) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < items) density_bwd_one(d_density, o, ldo, sel, d_geo, ldg, col_geo, d_o, n_o, i);
 }
 
-inline unsigned blocks_for(int64_t items) { return static_cast<unsigned>((items + kThreads - 1) / kThreads); }
+__global__ void weights_bwd_kernel(const float* deltas, const float* dens, const float* g_w, float* d_dens, int S, int64_t n) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) weights_bwd_one(deltas, dens, g_w, d_dens, S, i);
+}
+__global__ void rgb_bwd_kernel(const float* rgb, const float* w, const float* g_out, int bg_fixed, float bg0, float bg1,
+                               float bg2, float* d_rgb, float* d_w, int S, int64_t items) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < items) rgb_bwd_one(rgb, w, g_out, bg_fixed, bg0, bg1, bg2, d_rgb, d_w, S, i);
+}
+
+// executor of the backward chains of backward.cuh: every step is one kernel launch on `s`
+struct DeviceExec {
+  cudaStream_t s;
+  void dgrad(const float* dY, int ldy, int ny, const __half* W, int ldw, const __half* X, int ldx, float* dX, int lddx,
+             int nx, int64_t rows) {
+    const int64_t items = rows * nx;
+    mlp_dgrad_kernel<<<blocks_for(items), kThreads, 0, s>>>(dY, ldy, ny, W, ldw, X, ldx, dX, lddx, nx, items);
+  }
+  void wgrad_h(const float* A, int lda, int na, const __half* B, int ldb, int nb, int64_t rows, float* C, int ldc) {
+    const int64_t items = mlp_wgrad_items(rows, na, nb);
+    mlp_wgrad_kernel<__half><<<blocks_for(items), kThreads, 0, s>>>(A, lda, na, B, ldb, nb, rows, C, ldc, items);
+  }
+  void wgrad_f(const float* A, int lda, int na, const float* B, int ldb, int nb, int64_t rows, float* C, int ldc) {
+    const int64_t items = mlp_wgrad_items(rows, na, nb);
+    mlp_wgrad_kernel<float><<<blocks_for(items), kThreads, 0, s>>>(A, lda, na, B, ldb, nb, rows, C, ldc, items);
+  }
+  void scatter2(const GridDev& G, bool linf, bool sel, const float* xyz, const float* dX, int lddx, int col0, float* g,
+                int64_t points) {
+    const int64_t items = points * G.n_levels;
+    grid_scatter_kernel<2><<<blocks_for(items), kThreads, 0, s>>>(G, linf, sel, xyz, dX, lddx, col0, g, items);
+  }
+  void scatter8(const GridDev& G, bool linf, bool sel, const float* xyz, const float* dX, int lddx, int col0, float* g,
+                int64_t points) {
+    const int64_t items = points * G.n_levels;
+    grid_scatter_kernel<8><<<blocks_for(items), kThreads, 0, s>>>(G, linf, sel, xyz, dX, lddx, col0, g, items);
+  }
+  void feat_hidden(const FeatBwdParams& P, int64_t items) { feat_hidden_kernel<<<blocks_for(items), kThreads, 0, s>>>(P, items); }
+  void feat_positions(const FeatBwdParams& P, int64_t items) { feat_positions_kernel<<<blocks_for(items), kThreads, 0, s>>>(P, items); }
+  void sigmoid_bwd(const float* d_rgb, const __half* pre, int ldp, float* d_pre, int64_t items) {
+    sigmoid_bwd_kernel<<<blocks_for(items), kThreads, 0, s>>>(d_rgb, pre, ldp, d_pre, items);
+  }
+  void density_bwd(const float* d_density, const __half* o, int ldo, const float* sel, const float* d_geo, int ldg,
+                   int col_geo, float* d_o, int n_o, int64_t items) {
+    density_bwd_kernel<<<blocks_for(items), kThreads, 0, s>>>(d_density, o, ldo, sel, d_geo, ldg, col_geo, d_o, n_o, items);
+  }
+};
 
 }  // namespace
 
-size_t feat_bwd_scratch_floats(int64_t n_rays) {
-  const int64_t b = n_rays < kBwdBlockRays ? n_rays : kBwdBlockRays;
-  return static_cast<size_t>(b) * (2 * kBwdHid + kBwdK * kBwdHid + kBwdK * kBwdIn);
+cudaError_t launch_weights_bwd(const float* deltas, const float* dens, const float* g_w, float* d_dens, int64_t n, int S,
+                               cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  if (S < 1 || S > kMaxRaySamples) return cudaErrorInvalidValue;
+  weights_bwd_kernel<<<blocks_for(n), kThreads, 0, stream>>>(deltas, dens, g_w, d_dens, S, n);
+  return cudaGetLastError();
+}
+cudaError_t launch_rgb_bwd(const float* rgb, const float* w, const float* g_out, int bg_fixed, const float* bg,
+                           float* d_rgb, float* d_w, int64_t n, int S, cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  if (S < 1) return cudaErrorInvalidValue;
+  const int64_t items = n * S;
+  rgb_bwd_kernel<<<blocks_for(items), kThreads, 0, stream>>>(rgb, w, g_out, bg_fixed, bg ? bg[0] : 0.f, bg ? bg[1] : 0.f,
+                                                            bg ? bg[2] : 0.f, d_rgb, d_w, S, items);
+  return cudaGetLastError();
 }
 
-// P.d_hbar must point at feat_bwd_scratch_floats(P.n_rays) floats; hbar / dh / dx are carved out of it here.
+// ---------------------------------------------------------------------------------------------
+// feature branch
+// ---------------------------------------------------------------------------------------------
+size_t feat_bwd_scratch_floats(int64_t n_rays) {
+  const int64_t b = n_rays < kBwdBlockRays ? n_rays : kBwdBlockRays;
+  return static_cast<size_t>(b) * (2 * kBwdHid + kBwdK * kBwdHid + kBwdK * kBwdIn + kBwdK * 3);
+}
+
+// P.d_hbar must point at feat_bwd_scratch_floats(P.n_rays) floats; hbar / dh / dx / xyz are carved out of it here.
 cudaError_t launch_feat_backward(const FeatBwdParams& P0, cudaStream_t stream, int64_t* launches) {
   float* scratch = P0.d_hbar;
   for (int64_t r0 = 0; r0 < P0.n_rays; r0 += kBwdBlockRays) {
@@ -59,20 +141,97 @@ cudaError_t launch_feat_backward(const FeatBwdParams& P0, cudaStream_t stream, i
     P.hbar = P.d_hbar + n * kBwdHid;
     P.dh = P.hbar + n * kBwdHid;
     P.dx = P.dh + n * kBwdK * kBwdHid;
-    const int64_t rows = n * kBwdK;
-    int64_t items = n * kBwdHid;
-    bwd_dhbar_kernel<<<blocks_for(items), kThreads, 0, stream>>>(P, items);
-    bwd_hidden_kernel<<<blocks_for(items), kThreads, 0, stream>>>(P, items);
-    items = rows * kBwdIn;
-    bwd_dx_kernel<<<blocks_for(items), kThreads, 0, stream>>>(P, items);
-    items = ((rows + kSlabRows - 1) / kSlabRows) * kBwdHid * kBwdIn;
-    bwd_wgrad_kernel<__half><<<blocks_for(items), kThreads, 0, stream>>>(P.dh, kBwdHid, P.x, kBwdIn, rows, P.g_w1, items);
-    items = ((n + kSlabRows - 1) / kSlabRows) * P.n_out * kBwdHid;
-    bwd_wgrad_kernel<float><<<blocks_for(items), kThreads, 0, stream>>>(P.d_out, P.n_out, P.hbar, kBwdHid, n, P.g_w2, items);
-    items = rows * 24;
-    bwd_scatter_kernel<<<blocks_for(items), kThreads, 0, stream>>>(P, items);
-    if (launches) *launches += 6;
+    P.xyz = P.dx + n * kBwdK * kBwdIn;
+    DeviceExec ex{stream};
+    feat_backward_chain(P, ex);
+    if (launches) *launches += kFeatBwdLaunches;
     const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}
+
+// ---------------------------------------------------------------------------------------------
+// density fields
+// ---------------------------------------------------------------------------------------------
+namespace {
+// per-sample scratch: fp16 x[32] h1[64] o[16] hx[32] g1[64] g2[64] pre3[16] geo[16] = 304 halfs,
+//                     fp32 sel[1] dens[1] d_pre3[4] d_g2[64] d_g1[64] d_hx[32] d_o[16] d_h1[64] d_x[32] = 278 floats
+constexpr size_t kFieldHalfs = 304, kFieldFloats = 278;
+}  // namespace
+
+size_t field_bwd_scratch_bytes(int64_t n) {
+  const int64_t b = n < kFieldBwdBlock ? n : kFieldBwdBlock;
+  return static_cast<size_t>(b) * (kFieldHalfs * 2 + kFieldFloats * 4) + 256;
+}
+
+cudaError_t launch_field_backward(const FieldBwdParams& P0, void* scratch, cudaStream_t s, int64_t* launches) {
+  const bool nerfacto = P0.which == 1;
+  const int width = nerfacto ? 32 : 10, hidden = nerfacto ? 64 : 16, k_w = nerfacto ? 32 : 16;
+  for (int64_t r0 = 0; r0 < P0.n; r0 += kFieldBwdBlock) {
+    const int64_t n = P0.n - r0 < kFieldBwdBlock ? P0.n - r0 : kFieldBwdBlock;
+    FieldBwdParams P = P0;
+    P.xyz += 3 * r0;
+    if (P.dirs) P.dirs += 3 * r0;
+    if (P.d_density) P.d_density += r0;
+    if (P.d_rgb) P.d_rgb += 3 * r0;
+    P.n = n;
+    // carve: floats first (alignment), then halfs
+    float* f = reinterpret_cast<float*>(scratch);
+    P.sel = f;            f += n;
+    float* dens = f;      f += n;
+    P.d_pre3 = f;         f += n * 4;
+    P.d_g2 = f;           f += n * 64;
+    P.d_g1 = f;           f += n * 64;
+    P.d_hx = f;           f += n * 32;
+    P.d_o = f;            f += n * 16;
+    P.d_h1 = f;           f += n * 64;
+    P.d_x = f;            f += n * 32;
+    __half* h = reinterpret_cast<__half*>(f);
+    P.x = h;              h += n * 32;
+    P.h1 = h;             h += n * 64;
+    P.o = h;              h += n * 16;
+    P.hx = h;             h += n * 32;
+    P.g1 = h;             h += n * 64;
+    P.g2 = h;             h += n * 64;
+    P.pre3 = h;           h += n * 16;
+    __half* geo = h;
+    // ---- forward recomputation with the component-query kernels (query.cu) -----------------------
+    QueryParams Q;
+    memset(&Q, 0, sizeof(Q));
+    Q.xyz = P.xyz;
+    Q.n = n;
+    Q.grid[0] = P.grid;
+    Q.n_grids = 1;
+    Q.linf = 1;
+    Q.selector = 1;
+    Q.feat = P.x;
+    Q.sel = P.sel;
+    cudaError_t e = launch_encode(Q, s);
+    if (e != cudaSuccess) return e;
+    e = launch_dense(P.x, width, width, P.w1, k_w, 0.f, P.h1, hidden, hidden, 1, n, s);
+    if (e != cudaSuccess) return e;
+    e = launch_dense(P.h1, hidden, hidden, P.w2, hidden, 0.f, P.o, 16, 16, 0, n, s);
+    if (e != cudaSuccess) return e;
+    if (launches) *launches += 3;
+    const bool colour = nerfacto && P.d_rgb != nullptr;
+    if (colour) {
+      e = launch_density_finish(P.o, 16, P.sel, dens, geo, 15, n, s);
+      if (e != cudaSuccess) return e;
+      e = launch_head_input(P.dirs, geo, P.hx, n, s);
+      if (e != cudaSuccess) return e;
+      e = launch_dense(P.hx, 32, 32, P.wh1, 32, 1.f, P.g1, 64, 64, 1, n, s);
+      if (e != cudaSuccess) return e;
+      e = launch_dense(P.g1, 64, 64, P.wh2, 64, 0.f, P.g2, 64, 64, 1, n, s);
+      if (e != cudaSuccess) return e;
+      e = launch_dense(P.g2, 64, 64, P.wh3, 64, 0.f, P.pre3, 16, 16, 0, n, s);
+      if (e != cudaSuccess) return e;
+      if (launches) *launches += 5;
+    }
+    DeviceExec ex{s};
+    field_backward_chain(P, ex);
+    if (launches) *launches += colour ? 13 : 6;
+    e = cudaGetLastError();
     if (e != cudaSuccess) return e;
   }
   return cudaSuccess;

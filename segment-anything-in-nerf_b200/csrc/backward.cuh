@@ -1,13 +1,19 @@
-// Backward pass of the feature-field branch (first slice): gradients of
-//     out[r] = W2 . sum_k w[r,k] * fp16(relu(W1 x[r,k])),     x[r,k] = concat(enc0, enc1)(contract_L2(pos[r,k]))
-// with respect to W1, W2 and the two hash tables, given d_out.  Positions and weights carry no gradient:
-// SAMField detaches the positions (samnerf/sam_field.py:116) and MeanRenderer is fed sam_weights.detach()
-// (samnerf/sam_model.py:258-277), so this branch is the whole backward of the `sam_field` parameter group
-// (samnerf/sam_model.py:330-335).  What tinycudann's autograd does for the reference - CutlassMLP backward
-// (dL/dW = dY^T X, dL/dX = dY W) and the grid backward that scatters dL/dx * trilinear weight into the 8 corners
-// with atomicAdd (in-tree statement of the same scatter: nerfstudio/field_components/cuda/csrc/
-// temporal_gridencoder.cu:283-370) - restated here in fp32 (tcnn: fp16 with loss scaling; fp32 is the more exact
-// reading, and the gradients land directly in the flat fp32 layout of `params.grad`).
+// Backward passes of the field evaluations on the hot path.
+//
+// The reference trains through tinycudann's autograd: every tcnn module (sam_field.py:51,63,84,99;
+// nerfacto_field.py:157-175,228-240; density_fields.py:92-100) is a torch.autograd.Function whose backward is
+// CutlassMLP / FullyFusedMLP backward (dL/dW = dY^T X, dL/dX = dY W through the ReLU masks) followed by the grid
+// backward that scatters dL/dx * trilinear weight into the 8 corners with atomicAdd (in-tree statement of that
+// scatter: nerfstudio/field_components/cuda/csrc/temporal_gridencoder.cu:283-370), while torch autograd handles the
+// compositing and the losses on [N,S] tensors.  Restated here in fp32 (tcnn: fp16 with loss scaling; fp32 is the more
+// exact reading, and the gradients land directly in the flat fp32 layout of `params.grad`):
+//
+//   feature branch   out[r] = W2 . sum_k w[r,k] fp16(relu(W1 x[r,k])), x = concat(enc0, enc1)(contract_L2(pos))
+//                    positions detached (sam_field.py:116), weights detached (sam_model.py:258-277)
+//   nerfacto field   density = trunc_exp(o[0]) * sel, geo = o[1:16], o = W2 relu(W1 enc(contract_inf(pos)))
+//                    rgb = sigmoid(Wh3 relu(Wh2 relu(Wh1 [SH(dir), geo, 1])))        (nerfacto_field.py:242-351)
+//   proposal field   density = trunc_exp((W2 relu(W1 [enc, 0pad]))[0]) * sel          (density_fields.py:102-125)
+//   trunc_exp backward: g * exp(clamp(x, -15, 15))                                    (activations.py:33-37)
 //
 // First version: every kernel is "one thread = one output item", no shared memory, no warp intrinsics, so that the
 // bodies below run unchanged on the CPU in tests/emu against torch autograd through the oracle.  Rounding points of
@@ -17,9 +23,10 @@
 
 namespace snrf {
 
-constexpr int kBwdK = 16;     // picked samples per ray
-constexpr int kBwdIn = 192;   // encoder width (2 x 12 levels x 8 features)
-constexpr int kBwdHid = 256;  // hidden width
+constexpr int kBwdK = 16;     // picked samples per ray (feature branch)
+constexpr int kBwdIn = 192;   // feature encoder width (2 x 12 levels x 8 features)
+constexpr int kBwdHid = 256;  // feature hidden width
+constexpr int kSlabRows = 256;  // rows reduced per thread before one atomicAdd (weight gradients)
 
 SNRF_HD void atomic_add_f32(float* p, float v) {
 #ifdef __CUDA_ARCH__
@@ -29,6 +36,86 @@ SNRF_HD void atomic_add_f32(float* p, float v) {
 #endif
 }
 
+template <typename T>
+SNRF_HD float ld_f32(const T* p);
+template <>
+SNRF_HD float ld_f32<float>(const float* p) { return *p; }
+template <>
+SNRF_HD float ld_f32<__half>(const __half* p) { return __half2float(*p); }
+
+// ---------------------------------------------------------------------------------------------
+// generic MLP pieces
+// ---------------------------------------------------------------------------------------------
+// dX[row,i] = (sum_{j<ny} dY[row,j] * W[j,i]) * (X ? X[row,i] > 0 : 1)                 item = (row, i), i < nx
+// (X = the layer's saved post-ReLU input: relu'(pre) = [X > 0])
+SNRF_HD void mlp_dgrad_one(const float* dY, int ldy, int ny, const __half* W, int ldw, const __half* X, int ldx,
+                           float* dX, int lddx, int nx, int64_t item) {
+  const int64_t row = item / nx;
+  const int i = static_cast<int>(item % nx);
+  const float* g = dY + row * ldy;
+  float a = 0.f;
+  for (int j = 0; j < ny; ++j) a += g[j] * __half2float(W[static_cast<size_t>(j) * ldw + i]);
+  if (X && !(__half2float(X[row * ldx + i]) > 0.f)) a = 0.f;
+  dX[row * lddx + i] = a;
+}
+
+// C[a,b] += sum_{row in slab} A[row,a] * B[row,b]                                       item = (slab, a, b)
+// Non-finite rows (e.g. rays whose top-k weights are 0/0 = NaN, sam_model.py:248) poison the sum exactly as they do
+// in the reference's dense autograd; nothing is filtered here.
+template <typename TB>
+SNRF_HD void mlp_wgrad_one(const float* A, int lda, int na, const TB* B, int ldb, int nb, int64_t rows, float* C, int ldc,
+                           int64_t item) {
+  const int b = static_cast<int>(item % nb);
+  const int a = static_cast<int>((item / nb) % na);
+  const int64_t slab = item / (static_cast<int64_t>(na) * nb);
+  const int64_t r0 = slab * kSlabRows;
+  const int64_t r1 = r0 + kSlabRows < rows ? r0 + kSlabRows : rows;
+  float acc = 0.f;
+  for (int64_t r = r0; r < r1; ++r) acc += A[r * lda + a] * ld_f32<TB>(B + r * ldb + b);
+  atomic_add_f32(C + static_cast<size_t>(a) * ldc + b, acc);
+}
+SNRF_HD int64_t mlp_wgrad_items(int64_t rows, int na, int nb) {
+  return ((rows + kSlabRows - 1) / kSlabRows) * na * nb;
+}
+
+// ---------------------------------------------------------------------------------------------
+// hash-grid scatter: grad[idx(corner), f] += w(corner) * dX[pt, col0 + F*l + f]          item = (point, level)
+// positions are world-space; contraction / (p+2)/4 / selector exactly as the forward pass
+// ---------------------------------------------------------------------------------------------
+template <int F>
+SNRF_HD void grid_scatter_one(const GridDev& G, bool linf, bool selector, const float* xyz, const float* dX, int lddx,
+                              int col0, float* g_table, int64_t item) {
+  const int l = static_cast<int>(item % G.n_levels);
+  const int64_t pt = item / G.n_levels;
+  const float* d = dX + pt * lddx + col0 + l * F;
+  float g[F];
+  bool any = false;
+  for (int f = 0; f < F; ++f) {
+    g[f] = d[f];
+    any = any || g[f] != 0.f;
+  }
+  if (!any) return;  // dead units / zero-weight samples contribute nothing
+  float x, y, z, sel;
+  contract_normalize(xyz[3 * pt], xyz[3 * pt + 1], xyz[3 * pt + 2], linf, selector, x, y, z, sel);
+  const GridLevel& L = G.lv[l];
+  const float qx = mul_add_rn(x, L.scale, 0.5f), qy = mul_add_rn(y, L.scale, 0.5f), qz = mul_add_rn(z, L.scale, 0.5f);
+  const float fx = floorf(qx), fy = floorf(qy), fz = floorf(qz);
+  const float rx = qx - fx, ry = qy - fy, rz = qz - fz;
+  const uint32_t gx = static_cast<uint32_t>(static_cast<int>(fx)), gy = static_cast<uint32_t>(static_cast<int>(fy)),
+                 gz = static_cast<uint32_t>(static_cast<int>(fz));
+  for (int c = 0; c < 8; ++c) {
+    float w = (c & 1) ? rx : 1.f - rx;
+    w *= (c & 2) ? ry : 1.f - ry;
+    w *= (c & 4) ? rz : 1.f - rz;
+    const uint32_t idx = grid_index(L, gx + (c & 1), gy + ((c >> 1) & 1), gz + (c >> 2));
+    float* t = g_table + static_cast<size_t>(idx) * F;
+    for (int f = 0; f < F; ++f) atomic_add_f32(t + f, w * g[f]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// feature branch
+// ---------------------------------------------------------------------------------------------
 struct FeatBwdParams {
   // inputs
   const float* origins;   // [N,3]
@@ -47,25 +134,16 @@ struct FeatBwdParams {
   float* hbar;            // [N,256]
   float* dh;              // [N*16,256]
   float* dx;              // [N*16,192]
+  float* xyz;             // [N*16,3]
   // outputs, accumulated (+=)
   float* g_w1;            // [256,192]
   float* g_w2;            // [n_out,256]
   float* g_table[2];      // [entries*8] each
 };
 
-// K1: d_hbar[r,j] = sum_o d_out[r,o] * W2[o,j]                                     item = (ray, j)
-SNRF_HD void bwd_dhbar_one(const FeatBwdParams& P, int64_t item) {
-  const int64_t r = item / kBwdHid;
-  const int j = static_cast<int>(item % kBwdHid);
-  const float* g = P.d_out + r * P.n_out;
-  float a = 0.f;
-  for (int o = 0; o < P.n_out; ++o) a += g[o] * __half2float(P.w2[static_cast<size_t>(o) * kBwdHid + j]);
-  P.d_hbar[item] = a;
-}
-
-// K2: recompute h[r,k,j] = W1[j,:] . x[r,k,:]; hbar[r,j] = fp16(sum_k w_k * fp16(relu(h)));
-//     dh[r,k,j] = h > 0 ? w_k * d_hbar[r,j] : 0                                   item = (ray, j)
-SNRF_HD void bwd_hidden_one(const FeatBwdParams& P, int64_t item) {
+// F1: recompute h[r,k,j] = W1[j,:] . x[r,k,:]; hbar[r,j] = fp16(sum_k w_k * fp16(relu(h)));
+//     dh[r,k,j] = h > 0 ? w_k * d_hbar[r,j] : 0   (d_hbar from mlp_dgrad_one)          item = (ray, j)
+SNRF_HD void feat_hidden_one(const FeatBwdParams& P, int64_t item) {
   const int64_t r = item / kBwdHid;
   const int j = static_cast<int>(item % kBwdHid);
   const __half* wr = P.w1 + static_cast<size_t>(j) * kBwdIn;
@@ -82,82 +160,167 @@ SNRF_HD void bwd_hidden_one(const FeatBwdParams& P, int64_t item) {
   P.hbar[item] = round_f16(hb);
 }
 
-// K3: dx[row,i] = sum_j dh[row,j] * W1[j,i]                                        item = (row, i)
-SNRF_HD void bwd_dx_one(const FeatBwdParams& P, int64_t item) {
-  const int64_t row = item / kBwdIn;
-  const int i = static_cast<int>(item % kBwdIn);
-  const float* d = P.dh + row * kBwdHid;
-  float a = 0.f;
-  for (int j = 0; j < kBwdHid; ++j) a += d[j] * __half2float(P.w1[static_cast<size_t>(j) * kBwdIn + i]);
-  P.dx[item] = a;
-}
-
-// K4: C[a,b] += sum_{row in slab} A[row,a] * B[row,b]   (weight gradients)          item = (slab, a, b)
-//     W1: A = dh [R,256], B = x (fp16) [R,192];  W2: A = d_out [N,n_out], B = hbar [N,256]
-template <typename TB>
-SNRF_HD float ld_f32(const TB* p);
-template <>
-SNRF_HD float ld_f32<float>(const float* p) { return *p; }
-template <>
-SNRF_HD float ld_f32<__half>(const __half* p) { return __half2float(*p); }
-
-template <typename TB>
-SNRF_HD void bwd_wgrad_one(const float* A, int na, const TB* B, int nb, int64_t rows, int slab_rows, float* C,
-                           int64_t item) {
-  const int b = static_cast<int>(item % nb);
-  const int a = static_cast<int>((item / nb) % na);
-  const int64_t slab = item / (static_cast<int64_t>(na) * nb);
-  const int64_t r0 = slab * slab_rows;
-  const int64_t r1 = r0 + slab_rows < rows ? r0 + slab_rows : rows;
-  float acc = 0.f;
-  for (int64_t r = r0; r < r1; ++r) acc += A[r * na + a] * ld_f32<TB>(B + r * nb + b);
-  // non-finite rows (rays whose top-k weights are 0/0 = NaN, sam_model.py:248) poison the sum exactly as they do in
-  // the reference's dense autograd; nothing is filtered here
-  atomic_add_f32(C + static_cast<size_t>(a) * nb + b, acc);
-}
-
-// K5: scatter dx into the hash tables: grad[idx(corner), f] += w(corner) * dx[row, 96*e + 8*l + f]
-//                                                                               item = (row, encoding e, level l)
-SNRF_HD void bwd_scatter_one(const FeatBwdParams& P, int64_t item) {
-  const int l = static_cast<int>(item % 12);
-  const int e = static_cast<int>((item / 12) % 2);
-  const int64_t row = item / 24;
+// F2: world positions of the picked samples, op for op as the forward kernel builds them          item = row
+SNRF_HD void feat_positions_one(const FeatBwdParams& P, int64_t row) {
   const int64_t r = row / kBwdK;
   const float tm2 = P.sam_t[row];
-  // positions exactly as the forward kernel builds them (sam.cu): pos = o + d * (ts + te) / 2
-  const float px = sample_coord(P.origins[3 * r + 0], P.dirs[3 * r + 0], tm2);
-  const float py = sample_coord(P.origins[3 * r + 1], P.dirs[3 * r + 1], tm2);
-  const float pz = sample_coord(P.origins[3 * r + 2], P.dirs[3 * r + 2], tm2);
-  float x, y, z, sel;
-  contract_normalize(px, py, pz, false, false, x, y, z, sel);
-  const GridLevel& L = P.enc[e].lv[l];
-  const float qx = mul_add_rn(x, L.scale, 0.5f), qy = mul_add_rn(y, L.scale, 0.5f), qz = mul_add_rn(z, L.scale, 0.5f);
-  const float fx = floorf(qx), fy = floorf(qy), fz = floorf(qz);
-  const float rx = qx - fx, ry = qy - fy, rz = qz - fz;
-  const uint32_t gx = static_cast<uint32_t>(static_cast<int>(fx)), gy = static_cast<uint32_t>(static_cast<int>(fy)),
-                 gz = static_cast<uint32_t>(static_cast<int>(fz));
-  const float* d = P.dx + row * kBwdIn + e * 96 + l * 8;
-  float g[8];
-  bool any = false;
-  for (int f = 0; f < 8; ++f) {
-    g[f] = d[f];
-    any = any || g[f] != 0.f;
-  }
-  if (!any) return;  // dead hidden units / zero-weight samples contribute nothing
-  float* table = P.g_table[e];
-  for (int c = 0; c < 8; ++c) {
-    float w = (c & 1) ? rx : 1.f - rx;
-    w *= (c & 2) ? ry : 1.f - ry;
-    w *= (c & 4) ? rz : 1.f - rz;
-    const uint32_t idx = grid_index(L, gx + (c & 1), gy + ((c >> 1) & 1), gz + (c >> 2));
-    float* t = table + static_cast<size_t>(idx) * 8;
-    for (int f = 0; f < 8; ++f) atomic_add_f32(t + f, w * g[f]);
-  }
+  for (int c = 0; c < 3; ++c) P.xyz[3 * row + c] = sample_coord(P.origins[3 * r + c], P.dirs[3 * r + c], tm2);
 }
 
-// rays per internal block of the backward pass (bounds the fp32 scratch: 28 KB per ray)
+// The chain of items for one block of rays, written once against an executor so that the CUDA launcher (backward.cu)
+// and the host emulation (tests/emu) run the same wiring of buffers, strides and offsets.
+template <class Exec>
+inline void feat_backward_chain(const FeatBwdParams& P, Exec& ex) {
+  const int64_t n = P.n_rays, rows = n * kBwdK;
+  // d_hbar = d_out . W2 ; hidden recompute, hbar, dh ; dx = dh . W1
+  ex.dgrad(P.d_out, P.n_out, P.n_out, P.w2, kBwdHid, nullptr, 0, P.d_hbar, kBwdHid, kBwdHid, n);
+  ex.feat_hidden(P, n * kBwdHid);
+  ex.dgrad(P.dh, kBwdHid, kBwdHid, P.w1, kBwdIn, nullptr, 0, P.dx, kBwdIn, kBwdIn, rows);
+  // weight gradients
+  ex.wgrad_h(P.dh, kBwdHid, kBwdHid, P.x, kBwdIn, kBwdIn, rows, P.g_w1, kBwdIn);
+  ex.wgrad_f(P.d_out, P.n_out, P.n_out, P.hbar, kBwdHid, kBwdHid, n, P.g_w2, kBwdHid);
+  // table scatter (L2 contraction, no selector: sam_field.py:32,116-118)
+  ex.feat_positions(P, rows);
+  for (int e = 0; e < 2; ++e) ex.scatter8(P.enc[e], false, false, P.xyz, P.dx, kBwdIn, e * 96, P.g_table[e], rows);
+}
+constexpr int kFeatBwdLaunches = 8;
+
+// rays per internal block of the feature backward (bounds the fp32 scratch: 30 KB per ray)
 constexpr int64_t kBwdBlockRays = 8192;
 size_t feat_bwd_scratch_floats(int64_t n_rays);
 cudaError_t launch_feat_backward(const FeatBwdParams& P, cudaStream_t stream, int64_t* launches);
+
+// ---------------------------------------------------------------------------------------------
+// density fields (nerfacto base + colour head, proposal)
+// ---------------------------------------------------------------------------------------------
+// d_pre[row, c] = d_rgb[row, c] * s (1 - s), s = sigmoid(pre[row, c])                    item = (row, c), c < 3
+SNRF_HD void sigmoid_bwd_one(const float* d_rgb, const __half* pre, int ldp, float* d_pre, int64_t item) {
+  const int64_t row = item / 3;
+  const int c = static_cast<int>(item % 3);
+  const float s = 1.f / (1.f + expf(-__half2float(pre[row * ldp + c])));
+  d_pre[item] = d_rgb[item] * s * (1.f - s);
+}
+
+// d_o[row, 0] = d_density[row] * exp(clamp(o[row,0], -15, 15)) * sel[row];  d_o[row, 1 + k] = d_geo[row, k]
+//                                                                                      item = (row, c), c < n_o
+SNRF_HD void density_bwd_one(const float* d_density, const __half* o, int ldo, const float* sel, const float* d_geo,
+                             int ldg, int col_geo, float* d_o, int n_o, int64_t item) {
+  const int64_t row = item / n_o;
+  const int c = static_cast<int>(item % n_o);
+  float v;
+  if (c == 0) {
+    const float pre = fminf(fmaxf(__half2float(o[row * ldo]), -15.f), 15.f);
+    v = d_density ? d_density[row] * expf(pre) * sel[row] : 0.f;
+  } else {
+    v = d_geo ? d_geo[row * ldg + col_geo + c - 1] : 0.f;
+  }
+  d_o[item] = v;
+}
+
+struct FieldBwdParams {
+  const float* xyz;        // [n,3] world positions
+  const float* dirs;       // [n,3] (nerfacto colour head) or null
+  const float* d_density;  // [n] or null
+  const float* d_rgb;      // [n,3] or null
+  int64_t n;
+  int which;               // 0 proposal, 1 nerfacto
+  GridDev grid;
+  // forward weights (row-major fp16, tcnn [out,in])
+  const __half *w1, *w2, *wh1, *wh2, *wh3;
+  // saved / recomputed forward activations (fp16) and scratch (fp32): carved out of one buffer by the launcher
+  __half *x, *h1, *o, *hx, *g1, *g2, *pre3;
+  float *sel, *d_pre3, *d_g2, *d_g1, *d_hx, *d_o, *d_h1, *d_x;
+  // outputs, accumulated (+=): flat tcnn layouts
+  float* g_base;           // [W1, W2, table] = field.mlp_base.params / proposal_networks.0.mlp_base.params
+  float* g_head;           // [Wh1, Wh2, Wh3] = field.mlp_head.params (nerfacto only)
+};
+// Backward chain for one block of samples whose forward activations are already in P (see feat_backward_chain).
+template <class Exec>
+inline void field_backward_chain(const FieldBwdParams& P, Exec& ex) {
+  const bool nerfacto = P.which == 1;
+  const int width = nerfacto ? 32 : 10, hidden = nerfacto ? 64 : 16, k_w = nerfacto ? 32 : 16;
+  const int n_net = nerfacto ? 64 * 32 + 16 * 64 : 16 * 16 + 16 * 16;
+  const int64_t n = P.n;
+  const bool colour = nerfacto && P.d_rgb != nullptr;
+  if (colour) {  // rgb = sigmoid(Wh3 relu(Wh2 relu(Wh1 hx))), only outputs 0..2 of the 16 padded ones are used
+    ex.sigmoid_bwd(P.d_rgb, P.pre3, 16, P.d_pre3, n * 3);
+    ex.dgrad(P.d_pre3, 3, 3, P.wh3, 64, P.g2, 64, P.d_g2, 64, 64, n);
+    ex.wgrad_h(P.d_pre3, 3, 3, P.g2, 64, 64, n, P.g_head + 64 * 32 + 64 * 64, 64);
+    ex.dgrad(P.d_g2, 64, 64, P.wh2, 64, P.g1, 64, P.d_g1, 64, 64, n);
+    ex.wgrad_h(P.d_g2, 64, 64, P.g1, 64, 64, n, P.g_head + 64 * 32, 64);
+    ex.dgrad(P.d_g1, 64, 64, P.wh1, 32, nullptr, 0, P.d_hx, 32, 32, n);
+    ex.wgrad_h(P.d_g1, 64, 64, P.hx, 32, 32, n, P.g_head, 32);
+  }
+  // density (output 0) and, for nerfacto, the 15 geo features (outputs 1..15 = head inputs 16..30)
+  const int n_o = nerfacto ? 16 : 1;
+  ex.density_bwd(P.d_density, P.o, 16, P.sel, colour ? P.d_hx : nullptr, 32, 16, P.d_o, n_o, n * n_o);
+  ex.dgrad(P.d_o, n_o, n_o, P.w2, hidden, P.h1, hidden, P.d_h1, hidden, hidden, n);
+  ex.wgrad_h(P.d_o, n_o, n_o, P.h1, hidden, hidden, n, P.g_base + hidden * k_w, hidden);
+  ex.dgrad(P.d_h1, hidden, hidden, P.w1, k_w, nullptr, 0, P.d_x, width, width, n);
+  ex.wgrad_h(P.d_h1, hidden, hidden, P.x, width, width, n, P.g_base, k_w);
+  ex.scatter2(P.grid, true, true, P.xyz, P.d_x, width, 0, P.g_base + n_net, n);
+}
+
+// ---------------------------------------------------------------------------------------------
+// ray-wise renderer ops (what torch autograd does for the reference on [N,S] tensors)
+// ---------------------------------------------------------------------------------------------
+constexpr int kMaxRaySamples = 64;
+
+// RaySamples.get_weights backward (rays.py:141-163; deltas carry no gradient - the sampler detaches its bins,
+// ray_samplers.py:357):  w_i = T_i - T_{i+1},  T_{i+1} = T_i exp(-delta_i sigma_i)
+//   d sigma_k = delta_k * ( g_k * T_{k+1} - sum_{i>k} g_i * w_i )                                  item = ray
+SNRF_HD void weights_bwd_one(const float* deltas, const float* dens, const float* g_w, float* d_dens, int S, int64_t ray) {
+  float w[kMaxRaySamples], t_next[kMaxRaySamples];
+  const float* dl = deltas + ray * S;
+  const float* sg = dens + ray * S;
+  const float* g = g_w + ray * S;
+  float cum = 0.f;
+  for (int i = 0; i < S; ++i) {
+    const float ds = dl[i] * sg[i];
+    const float T = expf(-cum);
+    w[i] = (1.f - expf(-ds)) * T;
+    cum += ds;
+    t_next[i] = expf(-cum);
+  }
+  float suffix = 0.f;  // sum_{i>k} g_i w_i
+  for (int k = S - 1; k >= 0; --k) {
+    const bool finite = w[k] == w[k] && fabsf(w[k]) <= 3.402823466e+38f;  // nan_to_num blocks the gradient of a non-finite weight
+    const float gk = finite ? g[k] : 0.f;
+    d_dens[ray * S + k] = dl[k] * (gk * t_next[k] - suffix);
+    suffix += gk * (finite ? w[k] : 0.f);
+  }
+}
+
+// RGBRenderer.combine_rgb backward (renderers.py:69-112): C = sum_i w_i c_i + bg (1 - sum_i w_i), bg = c_{S-1}
+// ("last_sample") or a fixed colour:  d c_i = w_i G (+ (1 - acc) G for the last sample), d w_i = G . (c_i - bg)
+//                                                                                              item = (ray, i)
+SNRF_HD void rgb_bwd_one(const float* rgb, const float* w, const float* g_out, int bg_fixed, float bg0, float bg1, float bg2,
+                         float* d_rgb, float* d_w, int S, int64_t item) {
+  const int64_t ray = item / S;
+  const int i = static_cast<int>(item % S);
+  const float* c = rgb + (ray * S + i) * 3;
+  const float* G = g_out + ray * 3;
+  const float* last = rgb + (ray * S + S - 1) * 3;
+  const float b0 = bg_fixed ? bg0 : last[0], b1 = bg_fixed ? bg1 : last[1], b2 = bg_fixed ? bg2 : last[2];
+  const float wi = w[ray * S + i];
+  float extra = 0.f;
+  if (!bg_fixed && i == S - 1) {
+    float acc = 0.f;
+    for (int j = 0; j < S; ++j) acc += w[ray * S + j];
+    extra = 1.f - acc;
+  }
+  for (int ch = 0; ch < 3; ++ch) d_rgb[(ray * S + i) * 3 + ch] = (wi + extra) * G[ch];
+  d_w[ray * S + i] = G[0] * (c[0] - b0) + G[1] * (c[1] - b1) + G[2] * (c[2] - b2);
+}
+cudaError_t launch_weights_bwd(const float* deltas, const float* dens, const float* g_w, float* d_dens, int64_t n, int S,
+                               cudaStream_t stream);
+cudaError_t launch_rgb_bwd(const float* rgb, const float* w, const float* g_out, int bg_fixed, const float* bg,
+                           float* d_rgb, float* d_w, int64_t n, int S, cudaStream_t stream);
+
+constexpr int64_t kFieldBwdBlock = 1 << 16;  // samples per internal block (1.8 KB of scratch per sample)
+size_t field_bwd_scratch_bytes(int64_t n);
+// `fwd` runs the forward recomputation (encode + dense layers) into the activation buffers: supplied by api.cu so that
+// the GPU-verified query kernels are the ones that run
+cudaError_t launch_field_backward(const FieldBwdParams& P, void* scratch, cudaStream_t stream, int64_t* launches);
 
 }  // namespace snrf

@@ -8,6 +8,8 @@
 #include "../../segment-anything-in-nerf_b200/csrc/raygen.cuh"
 #include "../../segment-anything-in-nerf_b200/csrc/backward.cuh"
 
+#include <string.h>
+
 #include <vector>
 
 using namespace snrf;
@@ -31,6 +33,49 @@ int emu_generate_rays(const float* intr /*fx fy cx cy*/, int type, int has_dist,
   return 0;
 }
 
+// executor of the backward chains of backward.cuh: every step is a plain loop over the items of one kernel
+struct HostExec {
+  void dgrad(const float* dY, int ldy, int ny, const __half* W, int ldw, const __half* X, int ldx, float* dX, int lddx,
+             int nx, int64_t rows) {
+    for (int64_t i = 0; i < rows * nx; ++i) mlp_dgrad_one(dY, ldy, ny, W, ldw, X, ldx, dX, lddx, nx, i);
+  }
+  void wgrad_h(const float* A, int lda, int na, const __half* B, int ldb, int nb, int64_t rows, float* C, int ldc) {
+    for (int64_t i = 0; i < mlp_wgrad_items(rows, na, nb); ++i) mlp_wgrad_one<__half>(A, lda, na, B, ldb, nb, rows, C, ldc, i);
+  }
+  void wgrad_f(const float* A, int lda, int na, const float* B, int ldb, int nb, int64_t rows, float* C, int ldc) {
+    for (int64_t i = 0; i < mlp_wgrad_items(rows, na, nb); ++i) mlp_wgrad_one<float>(A, lda, na, B, ldb, nb, rows, C, ldc, i);
+  }
+  void scatter2(const GridDev& G, bool linf, bool sel, const float* xyz, const float* dX, int lddx, int col0, float* g,
+                int64_t points) {
+    for (int64_t i = 0; i < points * G.n_levels; ++i) grid_scatter_one<2>(G, linf, sel, xyz, dX, lddx, col0, g, i);
+  }
+  void scatter8(const GridDev& G, bool linf, bool sel, const float* xyz, const float* dX, int lddx, int col0, float* g,
+                int64_t points) {
+    for (int64_t i = 0; i < points * G.n_levels; ++i) grid_scatter_one<8>(G, linf, sel, xyz, dX, lddx, col0, g, i);
+  }
+  void feat_hidden(const FeatBwdParams& P, int64_t items) { for (int64_t i = 0; i < items; ++i) feat_hidden_one(P, i); }
+  void feat_positions(const FeatBwdParams& P, int64_t items) { for (int64_t i = 0; i < items; ++i) feat_positions_one(P, i); }
+  void sigmoid_bwd(const float* d_rgb, const __half* pre, int ldp, float* d_pre, int64_t items) {
+    for (int64_t i = 0; i < items; ++i) sigmoid_bwd_one(d_rgb, pre, ldp, d_pre, i);
+  }
+  void density_bwd(const float* d_density, const __half* o, int ldo, const float* sel, const float* d_geo, int ldg,
+                   int col_geo, float* d_o, int n_o, int64_t items) {
+    for (int64_t i = 0; i < items; ++i) density_bwd_one(d_density, o, ldo, sel, d_geo, ldg, col_geo, d_o, n_o, i);
+  }
+};
+
+static void fill_grid(GridDev& G, const double* levels, int n_levels, int n_features) {
+  G.table = nullptr; G.n_levels = n_levels; G.n_features = n_features;
+  for (int l = 0; l < n_levels; ++l) {
+    const double* v = levels + l * 5;  // {scale, res, size, offset, hashed}
+    G.lv[l].scale = static_cast<float>(v[0]);
+    G.lv[l].res = static_cast<uint32_t>(v[1]);
+    G.lv[l].size = static_cast<uint32_t>(v[2]);
+    G.lv[l].offset = static_cast<uint32_t>(v[3]);
+    G.lv[l].hashed = static_cast<uint32_t>(v[4]);
+  }
+}
+
 // mirrors snrf_feature_backward (HOST pointers): levels[e][l] = {scale, res, size, offset, hashed} as doubles
 int emu_feature_backward(const float* origins, const float* dirs, const float* sam_t, const float* sam_w, long long n_rays,
                          const float* d_out, int n_out, const unsigned short* x_f16, const unsigned short* w1_f16,
@@ -42,31 +87,52 @@ int emu_feature_backward(const float* origins, const float* dirs, const float* s
   P.w1 = reinterpret_cast<const __half*>(w1_f16);
   P.w2 = reinterpret_cast<const __half*>(w2_f16);
   P.n_rays = n_rays; P.n_out = n_out;
-  for (int e = 0; e < 2; ++e) {
-    P.enc[e].table = nullptr; P.enc[e].n_levels = 12; P.enc[e].n_features = 8;
-    for (int l = 0; l < 12; ++l) {
-      const double* v = levels + (e * 12 + l) * 5;
-      P.enc[e].lv[l].scale = static_cast<float>(v[0]);
-      P.enc[e].lv[l].res = static_cast<uint32_t>(v[1]);
-      P.enc[e].lv[l].size = static_cast<uint32_t>(v[2]);
-      P.enc[e].lv[l].offset = static_cast<uint32_t>(v[3]);
-      P.enc[e].lv[l].hashed = static_cast<uint32_t>(v[4]);
-    }
-  }
+  for (int e = 0; e < 2; ++e) fill_grid(P.enc[e], levels + e * 12 * 5, 12, 8);
   const int64_t n = n_rays, rows = n * kBwdK;
-  std::vector<float> d_hbar(n * kBwdHid), hbar(n * kBwdHid), dh(rows * kBwdHid), dx(rows * kBwdIn);
-  P.d_hbar = d_hbar.data(); P.hbar = hbar.data(); P.dh = dh.data(); P.dx = dx.data();
+  std::vector<float> d_hbar(n * kBwdHid), hbar(n * kBwdHid), dh(rows * kBwdHid), dx(rows * kBwdIn), xyz(rows * 3);
+  P.d_hbar = d_hbar.data(); P.hbar = hbar.data(); P.dh = dh.data(); P.dx = dx.data(); P.xyz = xyz.data();
   P.g_w1 = g_w1; P.g_w2 = g_w2; P.g_table[0] = g_table0; P.g_table[1] = g_table1;
-  const int slab = 256;  // kSlabRows of backward.cu
-  for (int64_t i = 0; i < n * kBwdHid; ++i) bwd_dhbar_one(P, i);
-  for (int64_t i = 0; i < n * kBwdHid; ++i) bwd_hidden_one(P, i);
-  for (int64_t i = 0; i < rows * kBwdIn; ++i) bwd_dx_one(P, i);
-  for (int64_t i = 0; i < ((rows + slab - 1) / slab) * kBwdHid * kBwdIn; ++i)
-    bwd_wgrad_one<__half>(P.dh, kBwdHid, P.x, kBwdIn, rows, slab, P.g_w1, i);
-  for (int64_t i = 0; i < ((n + slab - 1) / slab) * n_out * kBwdHid; ++i)
-    bwd_wgrad_one<float>(P.d_out, n_out, P.hbar, kBwdHid, n, slab, P.g_w2, i);
-  for (int64_t i = 0; i < rows * 24; ++i) bwd_scatter_one(P, i);
+  HostExec ex;
+  feat_backward_chain(P, ex);
   if (hbar_out) for (int64_t i = 0; i < n * kBwdHid; ++i) hbar_out[i] = hbar[i];
+  return 0;
+}
+
+// mirror snrf_ray_op_backward modes 0 and 3
+int emu_weights_backward(const float* deltas, const float* dens, const float* g_w, float* d_dens, long long n, int S) {
+  for (int64_t i = 0; i < n; ++i) weights_bwd_one(deltas, dens, g_w, d_dens, S, i);
+  return 0;
+}
+int emu_rgb_backward(const float* rgb, const float* w, const float* g_out, int bg_fixed, const float* bg, float* d_rgb,
+                     float* d_w, long long n, int S) {
+  for (int64_t i = 0; i < n * S; ++i)
+    rgb_bwd_one(rgb, w, g_out, bg_fixed, bg ? bg[0] : 0.f, bg ? bg[1] : 0.f, bg ? bg[2] : 0.f, d_rgb, d_w, S, i);
+  return 0;
+}
+
+// mirrors the backward half of snrf_field_backward: the forward activations (what launch_field_backward recomputes
+// with the query kernels) are supplied by the caller - the test takes them from the oracle.
+// acts: fp16 bit patterns x[n,width] h1[n,hidden] o[n,16] and, for nerfacto colour, hx[n,32] g1[n,64] g2[n,64] pre3[n,16]
+int emu_field_backward(int which, const float* xyz, long long n, const float* d_density, const float* d_rgb,
+                       const double* levels, int n_levels, const unsigned short* w1, const unsigned short* w2,
+                       const unsigned short* wh1, const unsigned short* wh2, const unsigned short* wh3,
+                       const unsigned short* x, const unsigned short* h1, const unsigned short* o,
+                       const unsigned short* hx, const unsigned short* g1, const unsigned short* g2,
+                       const unsigned short* pre3, const float* sel, float* g_base, float* g_head) {
+  FieldBwdParams P;
+  memset(&P, 0, sizeof(P));
+  P.xyz = xyz; P.d_density = d_density; P.d_rgb = d_rgb; P.n = n; P.which = which;
+  fill_grid(P.grid, levels, n_levels, 2);
+  auto H = [](const unsigned short* p) { return reinterpret_cast<__half*>(const_cast<unsigned short*>(p)); };
+  P.w1 = H(w1); P.w2 = H(w2); P.wh1 = H(wh1); P.wh2 = H(wh2); P.wh3 = H(wh3);
+  P.x = H(x); P.h1 = H(h1); P.o = H(o); P.hx = H(hx); P.g1 = H(g1); P.g2 = H(g2); P.pre3 = H(pre3);
+  P.sel = const_cast<float*>(sel);
+  std::vector<float> d_pre3(n * 4), d_g2(n * 64), d_g1(n * 64), d_hx(n * 32), d_o(n * 16), d_h1(n * 64), d_x(n * 32);
+  P.d_pre3 = d_pre3.data(); P.d_g2 = d_g2.data(); P.d_g1 = d_g1.data(); P.d_hx = d_hx.data(); P.d_o = d_o.data();
+  P.d_h1 = d_h1.data(); P.d_x = d_x.data();
+  P.g_base = g_base; P.g_head = g_head;
+  HostExec ex;
+  field_backward_chain(P, ex);
   return 0;
 }
 

@@ -232,3 +232,128 @@ def test_training_shim_logic_on_cpu(monkeypatch):
     assert not torch.equal(sd["sam_field.sam_net.params"], params["sam_field.sam_net.params"])
     assert torch.equal(sd["field.mlp_base.params"], params["field.mlp_base.params"])
     assert sd["conv_head.0.weight"].shape == (256, 256, 3, 3)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# density fields (nerfacto base + colour head, proposal)
+# ---------------------------------------------------------------------------------------------------------
+def _sample_positions(n, seed):
+    """World positions along real rays (inside and outside the unit sphere) and their directions."""
+    o, d = test_rays(n, seed=seed)
+    g = torch.Generator().manual_seed(seed)
+    t = torch.exp(torch.rand(n, generator=g) * 5.0 - 2.5)  # 0.08 .. 12 along the ray
+    return (o + d * t[:, None]).contiguous(), d.contiguous()
+
+
+def _field_activations(cfg, orc, params, which, pos, dirs):
+    """The fp16 forward activations launch_field_backward recomputes on the device, here from the oracle's pieces."""
+    from oracle import tcnn_spec as T
+
+    x_pts, sel = orc._normalized(pos, float("inf"))
+    if which == 1:
+        table, levels, ws = orc.field_table, orc.field_levels, orc.base_w
+    else:
+        table, levels, ws = orc.prop_table, orc.prop_levels, orc.prop_w
+    x = T.hash_grid_encode(x_pts, table, levels, 2)
+    xin = x if which == 1 else torch.cat([x, torch.zeros(x.shape[0], 6)], -1)
+    h1 = T.f16(torch.relu(xin @ T.f16(ws[0]).T))
+    o = T.f16(h1 @ T.f16(ws[1]).T)
+    acts = dict(x=x, h1=h1, o=o, sel=sel.float())
+    if which == 1:
+        hx = torch.cat([T.sh4((dirs + 1.0) / 2.0), o[:, 1:16], torch.ones(o.shape[0], 1)], -1)
+        g1 = T.f16(torch.relu(hx @ T.f16(orc.head_w[0]).T))
+        g2 = T.f16(torch.relu(g1 @ T.f16(orc.head_w[1]).T))
+        acts.update(hx=hx, g1=g1, g2=g2, pre3=T.f16(g2 @ T.f16(orc.head_w[2]).T))
+    return acts
+
+
+def _grid_levels(g):
+    lv = np.zeros((g.n_levels, 5), np.float64)
+    for l, (scale, res, offset, size, hashed) in enumerate(g.levels()):
+        lv[l] = (scale, res, size, offset, float(hashed))
+    return lv
+
+
+@pytest.mark.parametrize("which", [1, 0])
+def test_field_kernel_bodies_match_autograd(which):
+    from emu.build_emu import load
+    from oracle.samnerf_oracle import Oracle
+
+    cfg, params, orc0 = model_pair("tiny", "scene", 23, False, 1)
+    n = 300
+    pos, dirs = _sample_positions(n, seed=5)
+    names = ["field.mlp_base.params", "field.mlp_head.params"] if which == 1 else ["proposal_networks.0.mlp_base.params"]
+    p = {k: v.clone().requires_grad_(k in names) for k, v in params.items()}
+    orc = Oracle(cfg, p)
+    gen = torch.Generator().manual_seed(2)
+    g_d = torch.randn(n, generator=gen)
+    if which == 1:
+        dens, geo = orc.field_density(pos)
+        rgb = orc.field_rgb(dirs, geo)
+        g_rgb = torch.randn(n, 3, generator=gen)
+        ((dens * g_d).sum() + (rgb * g_rgb).sum()).backward()
+    else:
+        dens = orc.proposal_density(pos)
+        g_rgb = None
+        (dens * g_d).sum().backward()
+    with torch.no_grad():
+        acts = _field_activations(cfg, orc0, params, which, pos, dirs)
+    grid = cfg.field_grid if which == 1 else cfg.proposal_grid
+    ws = orc0.base_w if which == 1 else orc0.prop_w
+    g_base = np.zeros(params[names[0]].numel(), np.float32)
+    g_head = np.zeros(params["field.mlp_head.params"].numel(), np.float32)
+    bits = lambda t: None if t is None else _f16_bits(t)
+    arr = lambda t: None if t is None else np.ascontiguousarray(t.detach().numpy(), np.float32)
+    ptr = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+    keep = [arr(pos), arr(g_d), arr(g_rgb), _grid_levels(grid), bits(ws[0]), bits(ws[1])]
+    keep += [bits(w) for w in orc0.head_w]
+    keep += [bits(acts[k]) if k in acts else None for k in ("x", "h1", "o", "hx", "g1", "g2", "pre3")]
+    keep += [arr(acts["sel"])]
+    load().emu_field_backward(which, ptr(keep[0]), C.c_longlong(n), ptr(keep[1]), ptr(keep[2]), ptr(keep[3]), grid.n_levels,
+                              *[ptr(k) for k in keep[4:17]], ptr(g_base), ptr(g_head))
+    want = p[names[0]].grad
+    n_net = cfg.field_mlp_params if which == 1 else cfg.proposal_mlp_params
+    _assert_grad_close(g_base[:n_net], want[:n_net], "d base MLP")
+    _assert_grad_close(g_base[n_net:], want[n_net:], "d table")
+    if which == 1:
+        _assert_grad_close(g_head, p[names[1]].grad, "d head MLP")
+        # rows 3..15 of the padded output layer are unused: exactly zero gradient
+        assert not g_head.reshape(-1)[64 * 32 + 64 * 64 + 3 * 64:].any()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# ray-wise ops: get_weights and the RGB composite
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("S", [32, 64])
+def test_ray_op_bodies_match_autograd(S):
+    from emu.build_emu import load
+    from oracle.samnerf_oracle import composite_rgb, get_weights
+
+    lib = load()
+    n = 200
+    gen = torch.Generator().manual_seed(S)
+    deltas = torch.rand(n, S, generator=gen) * 0.2 + 1e-3
+    dens = torch.exp(torch.randn(n, S, generator=gen) * 2.0).requires_grad_(True)
+    dens.data[::7, 3] = 0.0  # empty samples
+    g_w = torch.randn(n, S, generator=gen)
+    w = get_weights(deltas, dens)
+    (w * g_w).sum().backward()
+    arr = lambda t: np.ascontiguousarray(t.detach().numpy(), np.float32)
+    ptr = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+    d_dens = np.zeros((n, S), np.float32)
+    a = [arr(deltas), arr(dens), arr(g_w)]
+    lib.emu_weights_backward(ptr(a[0]), ptr(a[1]), ptr(a[2]), ptr(d_dens), C.c_longlong(n), S)
+    _assert_grad_close(d_dens, dens.grad, "d densities")
+
+    for bg in (None, (0.2, 0.7, 1.0)):
+        rgb = torch.rand(n, S, 3, generator=gen).requires_grad_(True)
+        wt = w.detach().clone().requires_grad_(True)
+        g_out = torch.randn(n, 3, generator=gen)
+        out = composite_rgb(rgb, wt, None if bg is None else torch.tensor(bg), training=True)
+        (out * g_out).sum().backward()
+        d_rgb, d_w = np.zeros((n, S, 3), np.float32), np.zeros((n, S), np.float32)
+        b = [arr(rgb), arr(wt), arr(g_out), None if bg is None else np.asarray(bg, np.float32)]
+        lib.emu_rgb_backward(ptr(b[0]), ptr(b[1]), ptr(b[2]), int(bg is not None), ptr(b[3]), ptr(d_rgb), ptr(d_w),
+                             C.c_longlong(n), S)
+        _assert_grad_close(d_rgb, rgb.grad, f"d rgb samples (bg {bg})")
+        _assert_grad_close(d_w, wt.grad, f"d weights (bg {bg})")
