@@ -116,6 +116,8 @@ class RaySamples(_Carrier):
     def get_weights(self, densities: torch.Tensor) -> torch.Tensor:
         """rays.py:141-163 -> ``snrf_ray_op`` mode 0."""
         n, s = densities.shape[0], densities.shape[1]
+        if densities.requires_grad and torch.is_grad_enabled():
+            return _GetWeightsFn.apply(densities.reshape(n, s), self.deltas.reshape(n, s), self.renderer)[..., None]
         w = self.renderer.ray_op(0, self.deltas.reshape(n, s), densities.reshape(n, s))
         return w[..., None]
 
@@ -160,6 +162,14 @@ class _Field:
     def __init__(self, renderer: Renderer):
         self.renderer = renderer
 
+    #: set by SAMModel: callable returning the dict of trainable flat parameters while the model is in training
+    #: mode (else None) - the hook through which the component shims become differentiable
+    trainable: Optional[Callable] = None
+
+    def _params(self):
+        p = self.trainable() if self.trainable is not None else None
+        return p if p and torch.is_grad_enabled() else None
+
     def density_fn(self, positions: torch.Tensor) -> torch.Tensor:
         """base_field.py:38-56."""
         return self._density(positions)[0]
@@ -172,6 +182,9 @@ class HashMLPDensityField(_Field):
     """density_fields.py:39-125 (the proposal network)."""
 
     def _density(self, positions):
+        p = self._params()
+        if p and "proposal_networks.0.mlp_base.params" in p:
+            return _ProposalDensityFn.apply(p["proposal_networks.0.mlp_base.params"], self.renderer, positions.detach()), None
         return self.renderer.query_density("proposal", positions)
 
     def get_density(self, ray_samples: RaySamples):
@@ -202,6 +215,15 @@ class TCNNNerfactoField(_Field):
         return {FieldHeadNames.RGB: rgb}
 
     def forward(self, ray_samples: RaySamples, compute_normals: bool = False):
+        p = self._params()
+        if p and "field.mlp_base.params" in p:
+            # training: density and colour in one differentiable call (tinycudann's autograd in the reference)
+            if ray_samples.camera_indices is None:
+                raise AttributeError("Camera indices are not provided.")  # nerfacto_field.py:273-275
+            density, rgb = _NerfactoFieldFn.apply(p["field.mlp_base.params"], p["field.mlp_head.params"], self.renderer,
+                                                  ray_samples.frustums.get_positions().detach(),
+                                                  ray_samples.frustums.directions.detach())
+            return {FieldHeadNames.RGB: rgb, FieldHeadNames.DENSITY: density}
         density, emb = self.get_density(ray_samples)
         out = self.get_outputs(ray_samples, density_embedding=emb)
         out[FieldHeadNames.DENSITY] = density
@@ -255,6 +277,12 @@ class ProposalNetworkSampler:
         edges0 = sp_inv(bins * s_far + (1 - bins) * s_near)
         rs0 = self._samples(ray_bundle, edges0, bins.expand(n, -1))
         rs1 = self._samples(ray_bundle, edges1, None)
+        if density_fns and torch.is_grad_enabled():
+            # training (ray_samplers.py:586-593): the proposal weights handed to the interlevel loss carry the
+            # gradient of the proposal network; the sample positions themselves are detached (ray_samplers.py:357)
+            dens0 = density_fns[0](rs0.frustums.get_positions())
+            if dens0.requires_grad:
+                return rs1, [rs0.get_weights(dens0)], [rs0]
         return rs1, [w0[..., None]], [rs0]
 
     __call__ = generate_ray_samples
@@ -303,8 +331,11 @@ class RGBRenderer:
         if ray_indices is not None:
             raise NotImplementedError("packed samples are not on this path (renderers.py:90-95)")
         n, s = weights.shape[0], weights.shape[1]
-        return self.renderer.ray_op(3, rgb.reshape(n, s, 3), weights.reshape(n, s),
-                                    background=_resolve_background(self.background_color))
+        bg = _resolve_background(self.background_color)
+        if (rgb.requires_grad or weights.requires_grad) and torch.is_grad_enabled():
+            # training: no nan_to_num / clamp (renderers.py:132-139); sum_i w_i <= 1 keeps the value in [0, 1] anyway
+            return _RGBCompositeFn.apply(rgb.reshape(n, s, 3), weights.reshape(n, s), self.renderer, bg)
+        return self.renderer.ray_op(3, rgb.reshape(n, s, 3), weights.reshape(n, s), background=bg)
 
     __call__ = forward
 
@@ -351,12 +382,80 @@ class MeanRenderer:
 
 
 # ------------------------------------------------------------------------------------------------
-# training side of the feature branch
+# training side: autograd Functions over libsnrf's forward / backward kernels.  The flat parameters
+# are inputs only so that autograd routes their gradients; the values used are the ones uploaded to the library
+# (``SAMModel._sync_params``).
 # ------------------------------------------------------------------------------------------------
+class _ProposalDensityFn(torch.autograd.Function):
+    """``HashMLPDensityField.density_fn`` (density_fields.py:102-125)."""
+
+    @staticmethod
+    def forward(ctx, params, renderer, positions):
+        density, _ = renderer.query_density("proposal", positions)
+        ctx.renderer = renderer
+        ctx.save_for_backward(positions)
+        return density
+
+    @staticmethod
+    def backward(ctx, d_density):
+        (positions,) = ctx.saved_tensors
+        g = ctx.renderer.field_backward("proposal", positions, d_density=d_density.contiguous())
+        return g["base"], None, None
+
+
+class _NerfactoFieldFn(torch.autograd.Function):
+    """``TCNNNerfactoField.forward`` (nerfacto_field.py:242-351): density and rgb of every sample."""
+
+    @staticmethod
+    def forward(ctx, base, head, renderer, positions, directions):
+        density, geo = renderer.query_density("field", positions)
+        rgb = renderer.query_rgb(directions, geo)
+        ctx.renderer = renderer
+        ctx.save_for_backward(positions, directions)
+        return density, rgb
+
+    @staticmethod
+    def backward(ctx, d_density, d_rgb):
+        positions, directions = ctx.saved_tensors
+        g = ctx.renderer.field_backward("field", positions, directions,
+                                        d_density=None if d_density is None else d_density.contiguous(),
+                                        d_rgb=None if d_rgb is None else d_rgb.contiguous())
+        return g["base"], g.get("head"), None, None, None
+
+
+class _GetWeightsFn(torch.autograd.Function):
+    """``RaySamples.get_weights`` (rays.py:141-163); deltas are detached (ray_samplers.py:357)."""
+
+    @staticmethod
+    def forward(ctx, densities, deltas, renderer):
+        ctx.renderer = renderer
+        ctx.save_for_backward(densities, deltas)
+        return renderer.ray_op(0, deltas, densities)
+
+    @staticmethod
+    def backward(ctx, g_w):
+        densities, deltas = ctx.saved_tensors
+        return ctx.renderer.ray_op_backward(0, deltas, densities, g_w.contiguous()), None, None
+
+
+class _RGBCompositeFn(torch.autograd.Function):
+    """``RGBRenderer.combine_rgb`` (renderers.py:69-112)."""
+
+    @staticmethod
+    def forward(ctx, rgb, weights, renderer, background):
+        ctx.renderer, ctx.background = renderer, background
+        ctx.save_for_backward(rgb, weights)
+        return renderer.ray_op(3, rgb, weights, background=background)
+
+    @staticmethod
+    def backward(ctx, g_out):
+        rgb, weights = ctx.saved_tensors
+        d_rgb, d_w = ctx.renderer.ray_op_backward(3, rgb, weights, g_out.contiguous(), background=ctx.background)
+        return d_rgb, d_w, None, None
+
+
 class _FeatureBranchFn(torch.autograd.Function):
-    """``MeanRenderer(SAMField.get_outputs(sam_samples))`` (sam_model.py:256-277, sam_field.py:112-140) with
-    libsnrf's forward and backward kernels.  The flat parameters are inputs only so that autograd routes their
-    gradients; the values used are the ones uploaded to the library (``SAMModel._sync_params``)."""
+    """``MeanRenderer(SAMField.get_outputs(sam_samples))`` (sam_model.py:256-277, sam_field.py:112-140)."""
 
     @staticmethod
     def forward(ctx, net, grid0, grid1, renderer, which, origins, directions, sam_t, sam_w):
@@ -400,6 +499,10 @@ class SAMModel:
         self.renderer_accumulation = AccumulationRenderer(r)
         self.renderer_depth = DepthRenderer(r)
         self.renderer_mean = MeanRenderer(r)
+        self.params: Dict[str, torch.nn.Parameter] = {}
+        hook = lambda: self.params if self.training else None  # noqa: E731
+        for f in (self.proposal_networks[0], self.field):
+            f.trainable = hook
 
     def load_state_dict(self, state_dict: Dict[str, torch.Tensor], strict: bool = False):
         """Accepts the reference's pipeline keys (with or without the ``module.`` / ``_model.`` prefixes,
@@ -410,30 +513,31 @@ class SAMModel:
         self.renderer.load_params(self._loaded)
         self.params = {}  # trainable copies are (re)built by train()
 
-    # ---- training (first slice of SURVEY 8 f-1: the sam_field / conv parameter groups) -------------
+    # ---- training -------------------------------------------------------------------
     def train(self, mode: bool = True):
-        """Training mode: the ``sam_field`` tensors become fp32 ``nn.Parameter``s on the device whose gradients
-        come from libsnrf's backward kernels; the conv head (patch_size > 1) runs as a torch module so that autograd
-        covers it.  The collider switches to its training near plane (scene_colliders.py:185).  Geometry is
-        frozen and sampled deterministically - its backward / jitter are not built yet."""
+        """Training mode: every flat hot-path tensor becomes an fp32 ``nn.Parameter`` on the device whose gradient
+        comes from libsnrf's backward kernels (``snrf_field_backward``, ``snrf_feature_backward``,
+        ``snrf_ray_op_backward``); the conv head (patch_size > 1) runs as a torch module so that autograd covers it.
+        The collider switches to its training near plane (scene_colliders.py:185).  Sampling stays deterministic:
+        the stratified jitter of training mode (ray_samplers.py:104-112,314-322) is not built yet."""
         self.training = bool(mode)
         self.collider.training = self.training
         if not self.training:
             self._sync_params(eval_conv=True)
             return self
-        if not self.config.distill_sam:
-            raise RuntimeError("training needs distill_sam (the only trainable group built so far is sam_field)")
         loaded = getattr(self, "_loaded", None)
         if loaded is None:
             raise RuntimeError("load_state_dict() before train(): the fp32 master copies come from there")
         dev = self.renderer.device
         if not getattr(self, "params", None):
             self.params, self._uploaded = {}, {}
-            for which in ("sam", "clipseg"):
-                for name in Renderer.FEATURE_PARAMS[which]:
-                    if name in loaded:
-                        self.params[name] = torch.nn.Parameter(loaded[name].to(dev, torch.float32).reshape(-1).clone())
-                        self._uploaded[name] = self.params[name]._version
+            names = list(Renderer.DENSITY_PARAMS)
+            if self.config.distill_sam:
+                names += [n for which in ("sam", "clipseg") for n in Renderer.FEATURE_PARAMS[which]]
+            for name in names:
+                if name in loaded:
+                    self.params[name] = torch.nn.Parameter(loaded[name].to(dev, torch.float32).reshape(-1).clone())
+                    self._uploaded[name] = self.params[name]._version
             if "conv_head.0.weight" in loaded:
                 k = self.config.kernel_size
                 self.conv_head = torch.nn.Sequential(
@@ -447,8 +551,14 @@ class SAMModel:
         return self.train(False)
 
     def get_param_groups(self) -> Dict[str, List[torch.nn.Parameter]]:
-        """sam_model.py:330-335 - the groups built so far (``proposal_networks`` / ``fields`` are frozen)."""
-        groups = {"sam_field": list(getattr(self, "params", {}).values())}
+        """nerfacto.py:236-240 + sam_model.py:330-335."""
+        p = getattr(self, "params", {})
+        groups = {
+            "proposal_networks": [v for k, v in p.items() if k.startswith("proposal_networks.")],
+            "fields": [v for k, v in p.items() if k.startswith("field.")],
+        }
+        if self.config.distill_sam:
+            groups["sam_field"] = [v for k, v in p.items() if k.startswith("sam_field.")]
         if getattr(self, "conv_head", None) is not None:
             groups["conv"] = list(self.conv_head.parameters())
         return groups
@@ -467,6 +577,11 @@ class SAMModel:
         """Push parameters an optimiser step has changed (tensor version counters) back into the library's packed
         fp16 copies - the re-upload SURVEY 8 b asks for."""
         r = self.renderer
+        for name in Renderer.DENSITY_PARAMS:
+            p = getattr(self, "params", {}).get(name)
+            if p is not None and p._version != self._uploaded[name]:
+                r.upload_density_params(name, p)
+                self._uploaded[name] = p._version
         for which in ("sam", "clipseg"):
             names = Renderer.FEATURE_PARAMS[which]
             changed = {}
@@ -486,38 +601,42 @@ class SAMModel:
                 self._conv_uploaded = versions
 
     def _get_outputs_training(self, ray_bundle: RayBundle, get_feature, fast: bool):
+        """sam_model.py:226-301 in training mode, component by component like the reference: the samplers' positions
+        are detached (ray_samplers.py:357), the two density fields / get_weights / the RGB composite are autograd
+        Functions over libsnrf kernels, and the feature branch takes the top-k picks of the fused render."""
         cfg, r = self.config, self.renderer
         self._sync_params()
-        bg = _resolve_background(self.renderer_rgb.background_color)
+        if ray_bundle.camera_indices is None:  # the field insists on them (nerfacto_field.py:273-275)
+            ray_bundle.camera_indices = torch.zeros_like(ray_bundle.origins[..., :1], dtype=torch.long)
+        ray_samples, weights_list, ray_samples_list = self.proposal_sampler(ray_bundle, density_fns=self.density_fns)
+        ray_samples_list.append(ray_samples)
+        field_outputs = self.field(ray_samples)
+        weights = ray_samples.get_weights(field_outputs[FieldHeadNames.DENSITY])
+        weights_list.append(weights)
+        out = {"rgb": self.renderer_rgb(rgb=field_outputs[FieldHeadNames.RGB], weights=weights)}
         with torch.no_grad():
-            out = r.render(ray_bundle.origins, ray_bundle.directions, ray_bundle.nears, ray_bundle.fars, get_feature=(),
-                           fast=fast, background=bg, picks=True)
-        sam_t, sam_w = out.pop("_sam_t"), out.pop("_sam_w")
-        o = r._prep(ray_bundle.origins, 3)
-        d = r._prep(ray_bundle.directions, 3)
-        for which in ("sam", "clipseg"):
-            names = Renderer.FEATURE_PARAMS[which]
-            if which not in get_feature or names[0] not in self.params:
-                continue
-            feat = _FeatureBranchFn.apply(*[self.params[n] for n in names], r, which, o, d, sam_t, sam_w)
-            if which == "sam" and cfg.patch_size > 1:  # sam_model.py:260-265
-                p = cfg.patch_size
-                feat = feat.reshape(-1, p, p, feat.shape[-1]).permute(0, 3, 1, 2)
-                feat = self.conv_head(feat).mean(dim=[2, 3])
-            out[which] = feat
+            out["depth"] = self.renderer_depth(weights=weights, ray_samples=ray_samples)
+            if not fast:
+                out["accumulation"] = self.renderer_accumulation(weights=weights)
+                out["prop_depth_0"] = self.renderer_depth(weights=weights_list[0], ray_samples=ray_samples_list[0])
+        out["weights_list"], out["ray_samples_list"] = weights_list, ray_samples_list
+        feats = [f for f in get_feature if Renderer.FEATURE_PARAMS[f][0] in self.params]
+        if feats:
+            with torch.no_grad():  # top-k + sharpen of the fused kernel (sam_model.py:244-255)
+                picks = r.render(ray_bundle.origins, ray_bundle.directions, ray_bundle.nears, ray_bundle.fars,
+                                 get_feature=(), fast=True, picks=True)
+            sam_t, sam_w = picks["_sam_t"], picks["_sam_w"]
+            o = r._prep(ray_bundle.origins, 3)
+            d = r._prep(ray_bundle.directions, 3)
+            for which in feats:
+                names = Renderer.FEATURE_PARAMS[which]
+                feat = _FeatureBranchFn.apply(*[self.params[n] for n in names], r, which, o, d, sam_t, sam_w)
+                if which == "sam" and cfg.patch_size > 1:  # sam_model.py:260-265
+                    p = cfg.patch_size
+                    feat = feat.reshape(-1, p, p, feat.shape[-1]).permute(0, 3, 1, 2)
+                    feat = self.conv_head(feat).mean(dim=[2, 3])
+                out[which] = feat
         return out
-
-    @classmethod
-    def from_checkpoint(cls, path: str, device: int = 0, engine: str = "tcgen05", base: Optional[SAMNeRFConfig] = None):
-        """Build the model from a reference training checkpoint (``step-*.ckpt`` file or its directory; layout
-        nerfstudio/engine/trainer.py:389-400): the configuration is inferred from the tensors it carries."""
-        from .checkpoint import load_checkpoint
-
-        cfg, params, step = load_checkpoint(path, base)
-        model = cls(cfg, device=device, engine=engine)
-        model.renderer.load_params(params)
-        model.step = step
-        return model
 
     # sam_model.py:303-314
     def forward(self, ray_bundle: RayBundle, **kwargs):

@@ -161,14 +161,8 @@ class Renderer:
             t = params[name].detach().to(torch.float32).contiguous().view(-1)
             return t, t.data_ptr(), t.numel()
 
-        d = grid_desc(cfg.proposal_grid)
-        t, p, n = flat("proposal_networks.0.mlp_base.params")
-        self._check(lib.snrf_upload_proposal(self.h, p, n, C.byref(d), s))
-        d = grid_desc(cfg.field_grid)
-        t, p, n = flat("field.mlp_base.params")
-        self._check(lib.snrf_upload_field_base(self.h, p, n, C.byref(d), s))
-        t, p, n = flat("field.mlp_head.params")
-        self._check(lib.snrf_upload_field_head(self.h, p, n, s))
+        for name in self.DENSITY_PARAMS:
+            self.upload_density_params(name, params[name])
         for which, (enc, net, n_out) in enumerate(
             (("sam_field.clip_encs", "sam_field.sam_net", cfg.sam_out),
              ("sam_field.clipseg_encs", "sam_field.clipseg_net", cfg.clipseg_out))
@@ -188,6 +182,23 @@ class Renderer:
         if "conv_head.0.weight" in params:
             self.upload_conv_head(*[params[k] for k in ("conv_head.0.weight", "conv_head.0.bias", "conv_head.2.weight",
                                                         "conv_head.2.bias")])
+
+    DENSITY_PARAMS = ("proposal_networks.0.mlp_base.params", "field.mlp_base.params", "field.mlp_head.params")
+
+    def upload_density_params(self, name: str, t: torch.Tensor) -> None:
+        """(Re-)upload one of the proposal / nerfacto flat parameter tensors (host or device, fp32 -> packed fp16)."""
+        cfg, lib, s = self.cfg, self.lib, self.stream
+        t = t.detach().to(torch.float32).contiguous().view(-1)
+        if name == "proposal_networks.0.mlp_base.params":
+            d = grid_desc(cfg.proposal_grid)
+            self._check(lib.snrf_upload_proposal(self.h, t.data_ptr(), t.numel(), C.byref(d), s))
+        elif name == "field.mlp_base.params":
+            d = grid_desc(cfg.field_grid)
+            self._check(lib.snrf_upload_field_base(self.h, t.data_ptr(), t.numel(), C.byref(d), s))
+        elif name == "field.mlp_head.params":
+            self._check(lib.snrf_upload_field_head(self.h, t.data_ptr(), t.numel(), s))
+        else:
+            raise KeyError(name)
 
     def upload_conv_head(self, w0: torch.Tensor, b0: torch.Tensor, w2: torch.Tensor, b2: torch.Tensor) -> None:
         """``conv_head.{0,2}.{weight,bias}`` (sam_model.py:202-208), host or device tensors."""
@@ -437,6 +448,48 @@ class Renderer:
             self.h, {"sam": 0, "clipseg": 1}[which], o.data_ptr(), d.data_ptr(), t.data_ptr(), w.data_ptr(), n,
             g.data_ptr(), enc.data_ptr(), _ptr(res.get("net")), _ptr(res.get("grid0")), _ptr(res.get("grid1")), self.stream))
         return res
+
+    def field_backward(self, which: str, positions: torch.Tensor, directions: Optional[torch.Tensor] = None,
+                       d_density: Optional[torch.Tensor] = None, d_rgb: Optional[torch.Tensor] = None,
+                       grads: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
+        """Backward of ``query_density`` / ``query_rgb``: flat fp32 gradients ``base`` (and ``head`` with ``d_rgb``)
+        of the ``proposal`` or nerfacto ``field`` parameters, accumulated (+=) into ``grads``."""
+        cfg = self.cfg
+        x = self._prep(positions, 3)
+        n = x.shape[0]
+        prep = lambda t, c: None if t is None else t.to(device=self.device, dtype=torch.float32).reshape(n, c).contiguous()
+        d = None if directions is None else self._prep(directions.expand(*positions.shape[:-1], 3), 3)
+        gd, gr = prep(d_density, 1), prep(d_rgb, 3)
+        if which == "proposal":
+            sizes = {"base": cfg.proposal_mlp_params + cfg.proposal_grid.n_params}
+        else:
+            sizes = {"base": cfg.field_mlp_params + cfg.field_grid.n_params, "head": cfg.head_mlp_params}
+        grads = {} if grads is None else grads
+        for k, sz in sizes.items():
+            if k == "head" and gr is None:
+                continue
+            if k not in grads:
+                grads[k] = torch.zeros(sz, device=self.device)
+            assert grads[k].is_cuda and grads[k].dtype == torch.float32 and grads[k].is_contiguous() and grads[k].numel() == sz, k
+        self._check(self.lib.snrf_field_backward(
+            self.h, 0 if which == "proposal" else 1, x.data_ptr(), _ptr(d), n, _ptr(gd), _ptr(gr),
+            grads["base"].data_ptr(), _ptr(grads.get("head")), self.stream))
+        return grads
+
+    def ray_op_backward(self, mode: int, a, b, g, background=None):
+        """Backward of ``ray_op`` mode 0 (get_weights: returns ``d_densities``) or mode 3 (RGB composite: returns
+        ``(d_rgb_samples, d_weights)``)."""
+        a = a.to(device=self.device, dtype=torch.float32).contiguous()
+        b = b.to(device=self.device, dtype=torch.float32).contiguous()
+        g = g.to(device=self.device, dtype=torch.float32).contiguous()
+        n, s = b.shape[0], b.shape[1]
+        out_a = torch.empty_like(a)
+        out_b = torch.empty(n, s, device=self.device) if mode == 3 else None
+        bg = (C.c_float * 3)(*[float(v) for v in background]) if background is not None else None
+        self._check(self.lib.snrf_ray_op_backward(self.h, mode, a.data_ptr(), b.data_ptr(), g.data_ptr(), out_a.data_ptr(),
+                                                  _ptr(out_b), n, s, L.BG_FIXED if bg is not None else L.BG_LAST_SAMPLE,
+                                                  C.cast(bg, C.c_void_p) if bg is not None else None, self.stream))
+        return out_a if mode == 0 else (out_a, out_b)
 
     def sample(self, origins, directions, nears=None, fars=None):
         """Proposal weights ``[N,64]``, nerf bin edges ``[N,33]`` and proposal median depth ``[N,1]``."""

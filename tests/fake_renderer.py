@@ -14,6 +14,7 @@ from samnerf_b200.renderer import Renderer
 
 class FakeRenderer:
     FEATURE_PARAMS = Renderer.FEATURE_PARAMS
+    DENSITY_PARAMS = Renderer.DENSITY_PARAMS
 
     def __init__(self, cfg, device: int = 0, engine: str = "tcgen05"):
         self.cfg, self.device, self.engine = cfg, torch.device("cpu"), engine
@@ -37,6 +38,105 @@ class FakeRenderer:
                 self.p[name] = t.detach().clone()
                 self.uploads.append(name)
         self.orc = Oracle(self.cfg, self.p)
+
+    def upload_density_params(self, name, t):
+        from oracle.samnerf_oracle import Oracle
+
+        self.p[name] = t.detach().clone().view(-1)
+        self.uploads.append(name)
+        self.orc = Oracle(self.cfg, self.p)
+
+    # ---- component queries / ray ops: oracle forward, emulated kernel bodies backward ----------------
+    def query_density(self, which, positions):
+        with torch.no_grad():
+            if which == "proposal":
+                return self.orc.proposal_density(positions)[..., None], None
+            dens, geo = self.orc.field_density(positions)
+            return dens[..., None], geo.to(torch.float16)
+
+    def query_rgb(self, directions, geo):
+        with torch.no_grad():
+            return self.orc.field_rgb(directions.expand(*geo.shape[:-1], 3), geo.float())
+
+    def sample(self, origins, directions, nears=None, fars=None):
+        with torch.no_grad():
+            res = self.orc.render_rays(self._prep(origins, 3), self._prep(directions, 3), self._prep(nears, 1),
+                                       self._prep(fars, 1), get_feature=(), return_intermediates=True)
+        return res["_w0"], res["_eu1"], res["prop_depth_0"]
+
+    def ray_op(self, mode, a, b=None, c=None, n_channels=0, background=None):
+        from oracle.samnerf_oracle import composite_rgb, get_weights, median_depth
+
+        with torch.no_grad():
+            if mode == 0:
+                return get_weights(a, b)
+            if mode == 1:
+                return a.sum(-1, keepdim=True)
+            if mode == 2:
+                return median_depth(a, b, c)
+            if mode == 3:
+                return composite_rgb(a, b, background)
+            return (a * b[..., None]).sum(-2)
+
+    def ray_op_backward(self, mode, a, b, g, background=None):
+        from emu.build_emu import load
+
+        arr = lambda t: np.ascontiguousarray(t.detach().numpy(), np.float32)
+        ptr = lambda x: None if x is None else x.ctypes.data_as(C.c_void_p)
+        n, s = b.shape[0], b.shape[1]
+        keep = [arr(a), arr(b), arr(g)]
+        if mode == 0:
+            out = np.zeros((n, s), np.float32)
+            load().emu_weights_backward(ptr(keep[0]), ptr(keep[1]), ptr(keep[2]), ptr(out), C.c_longlong(n), s)
+            return torch.from_numpy(out)
+        bg = None if background is None else np.asarray([float(v) for v in background], np.float32)
+        d_rgb, d_w = np.zeros((n, s, 3), np.float32), np.zeros((n, s), np.float32)
+        load().emu_rgb_backward(ptr(keep[0]), ptr(keep[1]), ptr(keep[2]), int(bg is not None), ptr(bg), ptr(d_rgb), ptr(d_w),
+                                C.c_longlong(n), s)
+        return torch.from_numpy(d_rgb), torch.from_numpy(d_w)
+
+    def field_backward(self, which, positions, directions=None, d_density=None, d_rgb=None, grads=None):
+        from emu.build_emu import load
+        from oracle import tcnn_spec as T
+
+        cfg, orc = self.cfg, self.orc
+        w = 0 if which == "proposal" else 1
+        pos = positions.reshape(-1, 3).float()
+        n = pos.shape[0]
+        dirs = None if directions is None else directions.expand(*positions.shape[:-1], 3).reshape(-1, 3).float()
+        with torch.no_grad():  # the activations launch_field_backward recomputes on the device
+            x_pts, sel = orc._normalized(pos, float("inf"))
+            table, levels, ws = (orc.field_table, orc.field_levels, orc.base_w) if w else (orc.prop_table, orc.prop_levels, orc.prop_w)
+            x = T.hash_grid_encode(x_pts, table, levels, 2)
+            xin = x if w else torch.cat([x, torch.zeros(n, 6)], -1)
+            h1 = T.f16(torch.relu(xin @ T.f16(ws[0]).T))
+            o = T.f16(h1 @ T.f16(ws[1]).T)
+            acts = dict(x=x, h1=h1, o=o)
+            if w and d_rgb is not None:
+                hx = torch.cat([T.sh4((dirs + 1.0) / 2.0), o[:, 1:16], torch.ones(n, 1)], -1)
+                g1 = T.f16(torch.relu(hx @ T.f16(orc.head_w[0]).T))
+                g2 = T.f16(torch.relu(g1 @ T.f16(orc.head_w[1]).T))
+                acts.update(hx=hx, g1=g1, g2=g2, pre3=T.f16(g2 @ T.f16(orc.head_w[2]).T))
+        grid = cfg.field_grid if w else cfg.proposal_grid
+        lv = np.zeros((grid.n_levels, 5), np.float64)
+        for l, (scale, res, offset, size, hashed) in enumerate(grid.levels()):
+            lv[l] = (scale, res, size, offset, float(hashed))
+        n_base = (cfg.field_mlp_params + grid.n_params) if w else (cfg.proposal_mlp_params + grid.n_params)
+        g_base, g_head = np.zeros(n_base, np.float32), np.zeros(cfg.head_mlp_params, np.float32)
+        arr = lambda t: None if t is None else np.ascontiguousarray(t.detach().reshape(n, -1).numpy(), np.float32)
+        bits = lambda t: None if t is None else np.ascontiguousarray(t.detach().to(torch.float16).numpy().view(np.uint16))
+        ptr = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+        keep = [arr(pos), arr(d_density), arr(d_rgb), lv, bits(ws[0]), bits(ws[1])] + [bits(m) for m in orc.head_w]
+        keep += [bits(acts.get(k)) for k in ("x", "h1", "o", "hx", "g1", "g2", "pre3")] + [arr(sel.float())]
+        load().emu_field_backward(w, ptr(keep[0]), C.c_longlong(n), ptr(keep[1]), ptr(keep[2]), ptr(keep[3]), grid.n_levels,
+                                  *[ptr(k) for k in keep[4:17]], ptr(g_base), ptr(g_head))
+        grads = {} if grads is None else grads
+        full = {"base": torch.from_numpy(g_base)}
+        if d_rgb is not None:
+            full["head"] = torch.from_numpy(g_head)
+        for k, v in full.items():
+            grads[k] = grads[k] + v if k in grads else v
+        return grads
 
     def upload_conv_head(self, w0, b0, w2, b2):
         from oracle.samnerf_oracle import Oracle

@@ -204,6 +204,7 @@ def test_training_shim_logic_on_cpu(monkeypatch):
     m.train()
     groups = m.get_param_groups()
     assert len(groups["sam_field"]) == 3 and len(groups["conv"]) == 4
+    assert len(groups["proposal_networks"]) == 1 and len(groups["fields"]) == 2
     assert m.collider.training
     o, d = test_rays(64, seed=4)  # 4 patches of 16 rays
     bundle = api.RayBundle(origins=o, directions=d)
@@ -213,7 +214,7 @@ def test_training_shim_logic_on_cpu(monkeypatch):
     for step in range(3):
         opt.zero_grad()
         out = m(bundle, get_feature=["sam"])
-        assert out["sam"].shape == (4, 256) and out["rgb"].shape == (64, 3) and not out["rgb"].requires_grad
+        assert out["sam"].shape == (4, 256) and out["rgb"].shape == (64, 3) and out["rgb"].requires_grad
         loss = torch.nn.functional.mse_loss(out["sam"], target, reduction="none").mean(dim=-1).nanmean()
         loss.backward()
         for p in groups["sam_field"]:
@@ -357,3 +358,148 @@ def test_ray_op_bodies_match_autograd(S):
                              C.c_longlong(n), S)
         _assert_grad_close(d_rgb, rgb.grad, f"d rgb samples (bg {bg})")
         _assert_grad_close(d_w, wt.grad, f"d weights (bg {bg})")
+
+
+def test_training_step_gradients_match_autograd_end_to_end(monkeypatch):
+    """One full training step through the shim (proposal sampler -> fields -> get_weights -> RGB composite, every
+    backward an emulated kernel body) against torch autograd through the oracle's own functions on the same detached
+    sample positions: rgb loss + a loss on both weight lists, gradients of all three density-field tensors."""
+    import samnerf_b200.nerfstudio_api as api
+    from fake_renderer import FakeRenderer
+    from oracle.samnerf_oracle import Oracle, composite_rgb, get_weights
+
+    monkeypatch.setattr(api, "Renderer", FakeRenderer)
+    cfg, params, orc0 = model_pair("tiny", "scene", 25, False, 1)
+    m = api.SAMModel(cfg)
+    m.load_state_dict(params)
+    m.train()
+    o, d = test_rays(48, seed=6)
+    gen = torch.Generator().manual_seed(3)
+    target = torch.rand(48, 3, generator=gen)
+    c0, c1 = torch.randn(48, 64, 1, generator=gen), torch.randn(48, 32, 1, generator=gen)
+
+    out = m(api.RayBundle(origins=o, directions=d), get_feature=[])
+    assert set(out) >= {"rgb", "depth", "accumulation", "prop_depth_0", "weights_list", "ray_samples_list"}
+    loss = ((out["rgb"] - target) ** 2).mean() + (out["weights_list"][0] * c0).mean() + (out["weights_list"][1] * c1).mean()
+    loss.backward()
+
+    # reference: same positions (training near plane 0.05, detached bins), oracle functions under autograd
+    names = list(FakeRenderer.DENSITY_PARAMS)
+    p = {k: v.clone().requires_grad_(k in names) for k, v in params.items()}
+    orc = Oracle(cfg, p)
+    nears, fars = torch.full((48, 1), 0.05), torch.full((48, 1), float(cfg.far_plane))
+    with torch.no_grad():
+        res = orc0.render_rays(o, d, nears, fars, get_feature=(), return_intermediates=True)
+    eu0, eu1 = res["_eu0"], res["_eu1"]
+    pos0 = o[:, None, :] + d[:, None, :] * ((eu0[:, :-1] + eu0[:, 1:]) / 2)[..., None]
+    pos1 = o[:, None, :] + d[:, None, :] * ((eu1[:, :-1] + eu1[:, 1:]) / 2)[..., None]
+    w0 = get_weights(eu0[:, 1:] - eu0[:, :-1], orc.proposal_density(pos0))
+    dens, geo = orc.field_density(pos1)
+    rgb_s = orc.field_rgb(d[:, None, :].expand(-1, 32, -1), geo)
+    w1 = get_weights(eu1[:, 1:] - eu1[:, :-1], dens)
+    rgb = composite_rgb(rgb_s, w1, None, training=True)
+    ref_loss = ((rgb - target) ** 2).mean() + (w0[..., None] * c0).mean() + (w1[..., None] * c1).mean()
+    ref_loss.backward()
+    assert abs(float(loss.detach()) - float(ref_loss.detach())) < 1e-5
+    for name in names:
+        _assert_grad_close(m.params[name].grad, p[name].grad, name)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# the same comparisons through the C ABI on a GPU
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.hw_unverified
+@pytest.mark.parametrize("which", ["field", "proposal"])
+def test_gpu_field_backward_matches_autograd(which):
+    from helpers import make_renderer
+    from oracle.samnerf_oracle import Oracle
+
+    cfg, params, orc0 = model_pair("tiny", "scene", 23, False, 1)
+    r = make_renderer(cfg, params)
+    n = 70000  # more than one internal block of 65 536 samples
+    pos, dirs = _sample_positions(n, seed=5)
+    names = ["field.mlp_base.params", "field.mlp_head.params"] if which == "field" else ["proposal_networks.0.mlp_base.params"]
+    p = {k: v.clone().requires_grad_(k in names) for k, v in params.items()}
+    orc = Oracle(cfg, p)
+    gen = torch.Generator().manual_seed(2)
+    g_d = torch.randn(n, generator=gen)
+    if which == "field":
+        dens, geo = orc.field_density(pos)
+        g_rgb = torch.randn(n, 3, generator=gen)
+        ((dens * g_d).sum() + (orc.field_rgb(dirs, geo) * g_rgb).sum()).backward()
+    else:
+        g_rgb = None
+        (orc.proposal_density(pos) * g_d).sum().backward()
+    g = r.field_backward(which, pos, dirs if which == "field" else None, d_density=g_d, d_rgb=g_rgb)
+    torch.cuda.synchronize()
+    n_net = cfg.field_mlp_params if which == "field" else cfg.proposal_mlp_params
+    want = p[names[0]].grad
+    _assert_grad_close(g["base"][:n_net].cpu(), want[:n_net], "d base MLP")
+    _assert_grad_close(g["base"][n_net:].cpu(), want[n_net:], "d table")
+    if which == "field":
+        _assert_grad_close(g["head"].cpu(), p[names[1]].grad, "d head MLP")
+    # accumulation (+=) and density-only calls
+    g2 = r.field_backward(which, pos, dirs if which == "field" else None, d_density=g_d, d_rgb=g_rgb,
+                          grads={k: v.clone() for k, v in g.items()})
+    assert torch.allclose(g2["base"], 2.0 * g["base"], rtol=1e-3, atol=1e-6 * float(g["base"].abs().max()))
+    only_d = r.field_backward(which, pos, d_density=g_d)
+    assert set(only_d) == {"base"} and torch.isfinite(only_d["base"]).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.hw_unverified
+def test_gpu_ray_op_backward_matches_autograd():
+    from helpers import make_renderer
+    from oracle.samnerf_oracle import composite_rgb, get_weights
+
+    cfg, params, _ = model_pair("tiny", "scene", 23, False, 1)
+    r = make_renderer(cfg, params)
+    for S in (32, 64):
+        n = 3000
+        gen = torch.Generator().manual_seed(S)
+        deltas = torch.rand(n, S, generator=gen) * 0.2 + 1e-3
+        dens = torch.exp(torch.randn(n, S, generator=gen) * 2.0).requires_grad_(True)
+        g_w = torch.randn(n, S, generator=gen)
+        w = get_weights(deltas, dens)
+        (w * g_w).sum().backward()
+        _assert_grad_close(r.ray_op_backward(0, deltas, dens.detach(), g_w).cpu(), dens.grad, "d densities")
+        for bg in (None, (0.2, 0.7, 1.0)):
+            rgb = torch.rand(n, S, 3, generator=gen).requires_grad_(True)
+            wt = w.detach().clone().requires_grad_(True)
+            g_out = torch.randn(n, 3, generator=gen)
+            (composite_rgb(rgb, wt, None if bg is None else torch.tensor(bg), training=True) * g_out).sum().backward()
+            d_rgb, d_w = r.ray_op_backward(3, rgb.detach(), wt.detach(), g_out, background=bg)
+            _assert_grad_close(d_rgb.cpu(), rgb.grad, "d rgb samples")
+            _assert_grad_close(d_w.cpu(), wt.grad, "d weights")
+    with pytest.raises(RuntimeError, match="64 samples"):
+        r.ray_op_backward(0, torch.rand(4, 65), torch.rand(4, 65), torch.rand(4, 65))
+
+
+@pytest.mark.gpu
+@pytest.mark.hw_unverified
+def test_gpu_full_training_step_lowers_rgb_and_feature_losses():
+    from samnerf_b200.nerfstudio_api import RayBundle, SAMModel
+
+    cfg, params, _ = model_pair("tiny", "scene", 25, False, 1)
+    m = SAMModel(cfg)
+    m.load_state_dict(params)
+    m.train()
+    o, d = test_rays(1024, seed=6)
+    bundle = RayBundle(origins=o.cuda(), directions=d.cuda())
+    gen = torch.Generator().manual_seed(3)
+    image = torch.rand(1024, 3, generator=gen).cuda()
+    feat = (torch.randn(1024, 256, generator=gen) * 0.1).cuda()
+    groups = m.get_param_groups()
+    opt = torch.optim.Adam([q for g in groups.values() for q in g], lr=1e-3, eps=1e-15)
+    hist = []
+    for _ in range(5):
+        opt.zero_grad()
+        out = m(bundle, get_feature=["sam"])
+        rgb_loss = torch.nn.functional.mse_loss(out["rgb"], image)
+        sam_loss = torch.nn.functional.mse_loss(out["sam"], feat, reduction="none").mean(dim=-1).nanmean()
+        (rgb_loss + sam_loss).backward()
+        assert all(q.grad is not None and torch.isfinite(q.grad).all() for g in groups.values() for q in g)
+        opt.step()
+        hist.append((float(rgb_loss.detach()), float(sam_loss.detach())))
+    assert hist[-1][0] < hist[0][0] and hist[-1][1] < hist[0][1], hist
