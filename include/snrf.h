@@ -64,8 +64,15 @@ int snrf_set_engine(snrf_ctx* ctx, int engine);
  * terminates early, hence opt-in. */
 int snrf_set_early_termination(snrf_ctx* ctx, float eps);
 /* eval-mode PDF sample positions u[33] = linspace(0, 1-1/33, 33) + 1/66 (ray_samplers.py:325-327).  The
- * library computes the same table itself; a host may override it so that both sides share the bits. */
+ * library computes the same table itself; a host may override it so that both sides share the bits.  n = 66:
+ * followed by the 33 linspace values without the offset (the base of the training-mode positions, :314-322). */
 int snrf_set_pdf_u(snrf_ctx* ctx, const float* u_host, int n);
+/* Training-mode stratified sampling (ray_samplers.py:104-112,314-322 with single_jitter, the nerfacto default):
+ * jitter[n_rays,2] (DEVICE) = per ray {t_rand of the initial sampler, rand of the PDF sampler}, uniform in [0,1) -
+ * the caller draws them (torch.rand in the reference).  One-shot: applies to the NEXT snrf_render / snrf_sample
+ * call on ctx, which must carry exactly n_rays rays, and is cleared by it.  NULL clears.  Not for
+ * snrf_render_frame / snrf_render_camera (whole frames are eval-mode renders). */
+int snrf_set_jitter(snrf_ctx* ctx, const float* jitter, int64_t n_rays);
 
 /* ---- parameters: flat fp32 tensors in tcnn order, host OR device pointers --------------------------
  * Each call converts to fp16 and packs into the kernels' layouts once (replaces tcnn's `params` tensors:

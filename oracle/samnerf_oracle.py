@@ -212,19 +212,27 @@ class Oracle:
         return out
 
     # ---- samplers -------------------------------------------------------------------------
-    def initial_samples(self, nears: torch.Tensor, fars: torch.Tensor):
-        """``SpacedSampler.generate_ray_samples`` (eval: no jitter) with the piecewise spacing -
-        ray_samplers.py:79-126,223-246.  Returns spacing bins ``[1,S+1]``, euclidean bins ``[N,S+1]``
-        and ``(s_near, s_far)``."""
+    def initial_samples(self, nears: torch.Tensor, fars: torch.Tensor, t_rand: Optional[torch.Tensor] = None):
+        """``SpacedSampler.generate_ray_samples`` with the piecewise spacing - ray_samplers.py:79-126,223-246.
+        ``t_rand[N,1]``: the single-jitter random numbers of training mode (:104-112; ``single_jitter=True`` is the
+        nerfacto default, nerfacto.py:113,211); ``None`` = eval (no jitter).  Returns spacing bins ``[1|N,S+1]``,
+        euclidean bins ``[N,S+1]`` and ``(s_near, s_far)``."""
         s = self.cfg.num_proposal_samples
         bins = torch.linspace(0.0, 1.0, s + 1)[None, ...]
+        if t_rand is not None:
+            bin_centers = (bins[..., 1:] + bins[..., :-1]) / 2.0
+            bin_upper = torch.cat([bin_centers, bins[..., -1:]], -1)
+            bin_lower = torch.cat([bins[..., :1], bin_centers], -1)
+            bins = bin_lower + (bin_upper - bin_lower) * t_rand
         s_near, s_far = spacing_fn(nears), spacing_fn(fars)
         eu = spacing_fn_inv(bins * s_far + (1 - bins) * s_near)
         return bins, eu, (s_near, s_far)
 
-    def pdf_sample(self, weights: torch.Tensor, existing_bins: torch.Tensor, s_near, s_far):
-        """``PDFSampler.generate_ray_samples`` (eval, ``include_original=False``, padding 0.01) -
-        ray_samplers.py:274-369.  ``weights[N,S]`` -> spacing bins and euclidean bins ``[N, S'+1]``."""
+    def pdf_sample(self, weights: torch.Tensor, existing_bins: torch.Tensor, s_near, s_far,
+                   rand: Optional[torch.Tensor] = None):
+        """``PDFSampler.generate_ray_samples`` (``include_original=False``, padding 0.01) -
+        ray_samplers.py:274-369.  ``weights[N,S]`` -> spacing bins and euclidean bins ``[N, S'+1]``.
+        ``rand[N,1]``: the single-jitter random numbers of training mode (:314-322); ``None`` = eval."""
         num_samples = self.cfg.num_nerf_samples
         num_bins = num_samples + 1
         eps = 1e-5
@@ -237,7 +245,10 @@ class Oracle:
         cdf = torch.min(torch.ones_like(pdf), torch.cumsum(pdf, dim=-1))
         cdf = torch.cat([torch.zeros_like(cdf[..., :1]), cdf], dim=-1)
         u = torch.linspace(0.0, 1.0 - (1.0 / num_bins), steps=num_bins)
-        u = u + 1.0 / (2 * num_bins)
+        if rand is not None:
+            u = u.expand(size=(*cdf.shape[:-1], num_bins)) + rand / num_bins
+        else:
+            u = u + 1.0 / (2 * num_bins)
         u = u.expand(size=(*cdf.shape[:-1], num_bins)).contiguous()
         existing_bins = existing_bins.expand(cdf.shape[0], -1)
         inds = torch.searchsorted(cdf, u, side="right")
@@ -263,6 +274,7 @@ class Oracle:
         fast: bool = False,
         background=None,
         return_intermediates: bool = False,
+        jitter: Optional[torch.Tensor] = None,
     ) -> Dict[str, torch.Tensor]:
         """``SAMModel.forward`` -> ``get_outputs`` in eval mode - samnerf/sam_model.py:226-314
         (collider scene_colliders.py:183-188; sampler driver ray_samplers.py:558-599)."""
@@ -275,13 +287,14 @@ class Oracle:
         o, d = origins[:, None, :], directions[:, None, :]
 
         # proposal level (ray_samplers.py:575-593; rays.py:48-57,226-270)
-        bins0, eu0, (s_near, s_far) = self.initial_samples(nears, fars)
+        # jitter[N,2]: training-mode single-jitter random numbers of the two sampling levels (None = eval)
+        bins0, eu0, (s_near, s_far) = self.initial_samples(nears, fars, None if jitter is None else jitter[:, 0:1])
         starts0, ends0 = eu0[:, :-1], eu0[:, 1:]
         pos0 = o + d * ((starts0 + ends0) / 2)[..., None]
         dens0 = self.proposal_density(pos0)
         w0 = get_weights(ends0 - starts0, dens0)
         # anneal == 1.0 in eval (ray_samplers.py:545,583)
-        bins1, eu1 = self.pdf_sample(w0, bins0, s_near, s_far)
+        bins1, eu1 = self.pdf_sample(w0, bins0, s_near, s_far, None if jitter is None else jitter[:, 1:2])
         starts, ends = eu1[:, :-1], eu1[:, 1:]
         pos = o + d * ((starts + ends) / 2)[..., None]
 

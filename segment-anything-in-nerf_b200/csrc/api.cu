@@ -66,6 +66,8 @@ struct snrf_ctx {
   int sm_count = 148;
   int engine = 1;
   float et_eps = 0.f;  // snrf_set_early_termination
+  const float* jitter = nullptr;  // snrf_set_jitter: training-mode draws for the next render / sample call
+  int64_t jitter_rays = 0;
   std::string err;
   int64_t launches = 0;
   // proposal field
@@ -191,7 +193,8 @@ int stage(snrf_ctx* ctx, const float* src, int64_t n, DevBuf& tmp, cudaStream_t 
 }
 
 void default_pdf_u(float* u, int n_bins) {
-  // torch.linspace(0, 1 - 1/n_bins, n_bins) (float32, symmetric fill) + 1/(2 n_bins)   ray_samplers.py:325-327
+  // u[0..n):   torch.linspace(0, 1 - 1/n_bins, n_bins) (float32, symmetric fill) + 1/(2 n_bins)   ray_samplers.py:325-327
+  // u[n..2n):  the same linspace without the offset (training mode adds rand / n_bins instead, :314-322)
   const float end = static_cast<float>(1.0 - (1.0 / n_bins));
   const float step = (end - 0.f) / static_cast<float>(n_bins - 1);
   const int half = n_bins / 2;
@@ -199,6 +202,7 @@ void default_pdf_u(float* u, int n_bins) {
   for (int i = 0; i < n_bins; ++i) {
     const float v = i < half ? 0.f + step * static_cast<float>(i) : end - step * static_cast<float>(n_bins - i - 1);
     u[i] = v + off;
+    u[n_bins + i] = v;
   }
 }
 
@@ -248,7 +252,7 @@ int snrf_ctx_create(int device, snrf_ctx** out) {
     delete ctx;
     return SNRF_E_INVALID;
   }
-  float u[33];
+  float u[66];
   default_pdf_u(u, 33);
   if (ctx->pdf_u.ensure(sizeof(u)) != cudaSuccess ||
       cudaMemcpy(ctx->pdf_u.p, u, sizeof(u), cudaMemcpyHostToDevice) != cudaSuccess) {
@@ -312,9 +316,16 @@ int snrf_set_early_termination(snrf_ctx* ctx, float eps) {
 }
 
 int snrf_set_pdf_u(snrf_ctx* ctx, const float* u_host, int n) {
-  if (!ctx || !u_host || n != 33) return fail(ctx, SNRF_E_INVALID, "pdf_u must have 33 entries");
+  if (!ctx || !u_host || (n != 33 && n != 66)) return fail(ctx, SNRF_E_INVALID, "pdf_u must have 33 (or 33 + 33) entries");
   CK(cudaSetDevice(ctx->device));
-  CK(cudaMemcpy(ctx->pdf_u.p, u_host, 33 * sizeof(float), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(ctx->pdf_u.p, u_host, n * sizeof(float), cudaMemcpyHostToDevice));
+  return SNRF_OK;
+}
+
+int snrf_set_jitter(snrf_ctx* ctx, const float* jitter, int64_t n_rays) {
+  if (!ctx || n_rays < 0) return fail(ctx, SNRF_E_INVALID, "bad argument");
+  ctx->jitter = jitter;
+  ctx->jitter_rays = jitter ? n_rays : 0;
   return SNRF_OK;
 }
 
@@ -578,6 +589,15 @@ static int fill_march(snrf_ctx* ctx, MarchParams& M, const float* origins, const
   M.k_sam = o->k_sam;
   M.sharpen = o->sharpen;
   M.et_eps = ctx->et_eps;
+  M.pdf_u_base = ctx->pdf_u.as<float>() + 33;
+  if (ctx->jitter) {  // one-shot: consumed by this call
+    const float* j = ctx->jitter;
+    const int64_t nj = ctx->jitter_rays;
+    ctx->jitter = nullptr;
+    ctx->jitter_rays = 0;
+    if (nj != n) return fail(ctx, SNRF_E_INVALID, "snrf_set_jitter was given %lld rays, the call has %lld", (long long)nj, (long long)n);
+    M.jitter = j;
+  }
   return SNRF_OK;
 }
 

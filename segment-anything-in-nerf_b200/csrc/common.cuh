@@ -74,6 +74,16 @@ SNRF_HD float round_f16(float x) { return __half2float(__float2half_rn(x)); }
 SNRF_HD float spacing_fn(float x) { return x < 1.f ? x / 2.f : 1.f - 1.f / (2.f * x); }
 SNRF_HD float spacing_fn_inv(float x) { return x < 0.5f ? 2.f * x : 1.f / (2.f - 2.f * x); }
 
+// Spacing-space bin edge j of n_bins + 1 under training-mode single jitter (ray_samplers.py:104-112):
+// bins = linspace(0, 1, n_bins + 1); bin_lower + (bin_upper - bin_lower) * t_rand with lower / upper = the neighbouring
+// bin centres (2j-1)/(2 n_bins), (2j+1)/(2 n_bins) and the ends 0, 1 at j = 0, n_bins.  n_bins is a power of two here,
+// so every term but the final multiply-add is exact in fp32 and this is the torch expression bit for bit.
+SNRF_HD float jittered_bin(int j, int n_bins, float t_rand) {
+  const float lower = j == 0 ? 0.f : static_cast<float>(2 * j - 1) * (1.f / static_cast<float>(2 * n_bins));
+  const float upper = j == n_bins ? 1.f : static_cast<float>(2 * j + 1) * (1.f / static_cast<float>(2 * n_bins));
+  return mul_add_rn(upper - lower, t_rand, lower);
+}
+
 // torch.nan_to_num defaults: nan -> 0, +inf -> FLT_MAX, -inf -> -FLT_MAX
 SNRF_HD float nan_to_num(float x) {
   if (x != x) return 0.f;

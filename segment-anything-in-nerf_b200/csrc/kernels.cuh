@@ -66,6 +66,8 @@ struct MarchParams {
   float* dbg_density; // [N,32]
   float* dbg_rgb;     // [N,32,3]
   float et_eps;       // early-termination transmittance threshold, 0 = exact (see march_kernel<.., ET>)
+  const float* jitter;      // [N,2] training-mode single-jitter draws, or null = eval (see march_kernel<.., JIT>)
+  const float* pdf_u_base;  // [33] linspace(0, 1 - 1/33, 33) without the eval-mode half-bin offset
 };
 cudaError_t launch_march(const MarchParams& P, int sm_count, cudaStream_t stream);
 

@@ -249,8 +249,11 @@ class SAMField(_Field):
 class ProposalNetworkSampler:
     """ray_samplers.py:509-599, eval mode, one proposal iteration (samconfigs.py:84,138)."""
 
-    def __init__(self, renderer: Renderer):
+    def __init__(self, renderer: Renderer, train_stratified: bool = True):
         self.renderer = renderer
+        self.training = False             # set by SAMModel.train()
+        self.train_stratified = train_stratified  # ray_samplers.py:67
+        self.last_jitter: Optional[torch.Tensor] = None
 
     def _samples(self, bundle: RayBundle, edges: torch.Tensor, spacing: Optional[torch.Tensor]) -> RaySamples:
         o, d = bundle.origins[:, None, :], bundle.directions[:, None, :]
@@ -265,17 +268,28 @@ class ProposalNetworkSampler:
 
     def generate_ray_samples(self, ray_bundle: RayBundle, density_fns=None) -> Tuple[RaySamples, List, List]:
         r = self.renderer
-        w0, edges1, _ = r.sample(ray_bundle.origins, ray_bundle.directions, ray_bundle.nears, ray_bundle.fars)
+        # training: stratified sampling with one draw per ray and level (single_jitter, nerfacto.py:113,211) -
+        # drawn here with torch.rand like the reference (ray_samplers.py:104-112,314-322), consumed by the kernel
+        jitter = None
+        if self.training and self.train_stratified:
+            n_rays = ray_bundle.origins.reshape(-1, 3).shape[0]
+            jitter = torch.rand((n_rays, 2), device=r.device)
+        self.last_jitter = jitter
+        w0, edges1, _ = r.sample(ray_bundle.origins, ray_bundle.directions, ray_bundle.nears, ray_bundle.fars, jitter=jitter)
         n = w0.shape[0]
         # level-0 samples for ray_samples_list: the piecewise bins are a closed form of (near, far)
         nears = ray_bundle.nears if ray_bundle.nears is not None else torch.zeros(n, 1, device=w0.device)
         fars = ray_bundle.fars if ray_bundle.fars is not None else torch.full((n, 1), r.cfg.far_plane, device=w0.device)
         bins = torch.linspace(0.0, 1.0, r.cfg.num_proposal_samples + 1, device=w0.device)[None]
+        if jitter is not None:  # ray_samplers.py:108-111
+            centers = (bins[..., 1:] + bins[..., :-1]) / 2.0
+            upper, lower = torch.cat([centers, bins[..., -1:]], -1), torch.cat([bins[..., :1], centers], -1)
+            bins = lower + (upper - lower) * jitter[:, 0:1].to(w0.device)
         sp = lambda x: torch.where(x < 1, x / 2, 1 - 1 / (2 * x))  # noqa: E731  ray_samplers.py:242
         sp_inv = lambda x: torch.where(x < 0.5, 2 * x, 1 / (2 - 2 * x))  # noqa: E731  ray_samplers.py:243
         s_near, s_far = sp(nears.to(w0.device)), sp(fars.to(w0.device))
         edges0 = sp_inv(bins * s_far + (1 - bins) * s_near)
-        rs0 = self._samples(ray_bundle, edges0, bins.expand(n, -1))
+        rs0 = self._samples(ray_bundle, edges0, bins.expand(n, -1) if bins.shape[0] == 1 else bins)
         rs1 = self._samples(ray_bundle, edges1, None)
         if density_fns and torch.is_grad_enabled():
             # training (ray_samplers.py:586-593): the proposal weights handed to the interlevel loss carry the
@@ -518,10 +532,11 @@ class SAMModel:
         """Training mode: every flat hot-path tensor becomes an fp32 ``nn.Parameter`` on the device whose gradient
         comes from libsnrf's backward kernels (``snrf_field_backward``, ``snrf_feature_backward``,
         ``snrf_ray_op_backward``); the conv head (patch_size > 1) runs as a torch module so that autograd covers it.
-        The collider switches to its training near plane (scene_colliders.py:185).  Sampling stays deterministic:
-        the stratified jitter of training mode (ray_samplers.py:104-112,314-322) is not built yet."""
+        The collider switches to its training near plane (scene_colliders.py:185) and the sampler to stratified
+        single-jitter sampling (ray_samplers.py:104-112,314-322)."""
         self.training = bool(mode)
         self.collider.training = self.training
+        self.proposal_sampler.training = self.training
         if not self.training:
             self._sync_params(eval_conv=True)
             return self
@@ -624,7 +639,7 @@ class SAMModel:
         if feats:
             with torch.no_grad():  # top-k + sharpen of the fused kernel (sam_model.py:244-255)
                 picks = r.render(ray_bundle.origins, ray_bundle.directions, ray_bundle.nears, ray_bundle.fars,
-                                 get_feature=(), fast=True, picks=True)
+                                 get_feature=(), fast=True, picks=True, jitter=self.proposal_sampler.last_jitter)
             sam_t, sam_w = picks["_sam_t"], picks["_sam_w"]
             o = r._prep(ray_bundle.origins, 3)
             d = r._prep(ray_bundle.directions, 3)

@@ -77,9 +77,9 @@ class Renderer:
         self.set_engine(engine)
         # share the bits of the eval-mode PDF sample positions with torch (ray_samplers.py:325-327)
         nb = cfg.num_nerf_samples + 1
-        u = torch.linspace(0.0, 1.0 - (1.0 / nb), steps=nb) + 1.0 / (2 * nb)
-        u = u.contiguous()
-        self._check(self.lib.snrf_set_pdf_u(self.h, u.data_ptr(), nb))
+        base = torch.linspace(0.0, 1.0 - (1.0 / nb), steps=nb)
+        u = torch.cat([base + 1.0 / (2 * nb), base]).contiguous()  # eval positions, then the training-mode base (:314-322)
+        self._check(self.lib.snrf_set_pdf_u(self.h, u.data_ptr(), 2 * nb))
         self.have_sam = self.have_clipseg = self.have_conv = False
 
     # ------------------------------------------------------------------------------------------
@@ -239,6 +239,7 @@ class Renderer:
         debug: bool = False,
         out: Optional[Dict[str, torch.Tensor]] = None,
         picks: bool = False,
+        jitter: Optional[torch.Tensor] = None,
     ) -> Dict[str, torch.Tensor]:
         """One chunk of rays: ``SAMModel.forward`` in eval mode (samnerf/sam_model.py:226-314).
         ``out``: optional preallocated CUDA output tensors (e.g. row slices of frame buffers) to write into."""
@@ -298,6 +299,7 @@ class Renderer:
             dbg = L.DebugOut()
             dbg.sam_t, dbg.sam_w = out["_sam_t"].data_ptr(), out["_sam_w"].data_ptr()
         opts = self._opts(background)
+        jit = self._set_jitter(jitter, n)
         rc = self.lib.snrf_render(
             self.h, o.data_ptr(), d.data_ptr(), _ptr(nr), _ptr(fr), n, flags, C.byref(opts),
             out["rgb"].data_ptr(), out["depth"].data_ptr(), _ptr(out.get("accumulation")),
@@ -491,11 +493,22 @@ class Renderer:
                                                   C.cast(bg, C.c_void_p) if bg is not None else None, self.stream))
         return out_a if mode == 0 else (out_a, out_b)
 
-    def sample(self, origins, directions, nears=None, fars=None):
-        """Proposal weights ``[N,64]``, nerf bin edges ``[N,33]`` and proposal median depth ``[N,1]``."""
+    def _set_jitter(self, jitter: Optional[torch.Tensor], n: int):
+        """Training-mode single-jitter draws ``[n,2]`` for the next render / sample call (``snrf_set_jitter``).
+        Returns the device tensor so that the caller keeps it alive across the launch."""
+        if jitter is None:
+            return None
+        j = jitter.to(device=self.device, dtype=torch.float32).reshape(n, 2).contiguous()
+        self._check(self.lib.snrf_set_jitter(self.h, j.data_ptr(), n))
+        return j
+
+    def sample(self, origins, directions, nears=None, fars=None, jitter: Optional[torch.Tensor] = None):
+        """Proposal weights ``[N,64]``, nerf bin edges ``[N,33]`` and proposal median depth ``[N,1]``;
+        ``jitter[N,2]`` switches to training-mode stratified sampling (ray_samplers.py:104-112,314-322)."""
         o, d = self._prep(origins, 3), self._prep(directions, 3)
         nr, fr = self._prep(nears, 1), self._prep(fars, 1)
         n = o.shape[0]
+        jit = self._set_jitter(jitter, n)  # noqa: F841  (kept alive until the launch is enqueued)
         w0 = torch.empty(n, 64, device=self.device)
         edges = torch.empty(n, 33, device=self.device)
         pd = torch.empty(n, 1, device=self.device)

@@ -98,6 +98,13 @@ int emu_feature_backward(const float* origins, const float* dirs, const float* s
   return 0;
 }
 
+// training-mode spacing bins of the initial sampler (march.cu, JIT instantiation): out[n, n_bins + 1]
+int emu_jittered_bins(const float* t_rand, long long n, int n_bins, float* out) {
+  for (int64_t r = 0; r < n; ++r)
+    for (int j = 0; j <= n_bins; ++j) out[r * (n_bins + 1) + j] = jittered_bin(j, n_bins, t_rand[r]);
+  return 0;
+}
+
 // mirror snrf_ray_op_backward modes 0 and 3
 int emu_weights_backward(const float* deltas, const float* dens, const float* g_w, float* d_dens, long long n, int S) {
   for (int64_t i = 0; i < n; ++i) weights_bwd_one(deltas, dens, g_w, d_dens, S, i);

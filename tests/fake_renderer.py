@@ -58,10 +58,10 @@ class FakeRenderer:
         with torch.no_grad():
             return self.orc.field_rgb(directions.expand(*geo.shape[:-1], 3), geo.float())
 
-    def sample(self, origins, directions, nears=None, fars=None):
+    def sample(self, origins, directions, nears=None, fars=None, jitter=None):
         with torch.no_grad():
             res = self.orc.render_rays(self._prep(origins, 3), self._prep(directions, 3), self._prep(nears, 1),
-                                       self._prep(fars, 1), get_feature=(), return_intermediates=True)
+                                       self._prep(fars, 1), get_feature=(), return_intermediates=True, jitter=jitter)
         return res["_w0"], res["_eu1"], res["prop_depth_0"]
 
     def ray_op(self, mode, a, b=None, c=None, n_channels=0, background=None):
@@ -147,11 +147,11 @@ class FakeRenderer:
         self.orc = Oracle(self.cfg, self.p)
 
     def render(self, origins, directions, nears=None, fars=None, get_feature=(), patch=False, fast=False, background=None,
-               debug=False, out=None, picks=False):
+               debug=False, out=None, picks=False, jitter=None):
         with torch.no_grad():
             res = self.orc.render_rays(self._prep(origins, 3), self._prep(directions, 3), self._prep(nears, 1),
                                        self._prep(fars, 1), get_feature=tuple(get_feature) or ("sam",), fast=fast,
-                                       background=background, return_intermediates=True)
+                                       background=background, return_intermediates=True, jitter=jitter)
         eu = res["_eu1"]
         tm2 = eu[:, :-1] + eu[:, 1:]
         keep = {k: v for k, v in res.items() if not k.startswith("_") and (k in get_feature or k in ("rgb", "depth", "accumulation", "prop_depth_0"))}

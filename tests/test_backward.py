@@ -60,7 +60,8 @@ def _assert_grad_close(got, want, what):
     print(f"{what}: max|err| {err:.3e}  max|grad| {scale:.3e}  ratio {err / scale:.2e}")
     assert err <= GRAD_RTOL_OF_MAX * scale, f"{what}: max|err| {err:.3e} vs max|grad| {scale:.3e}"
     # and the gradient must be where the reference has it (same sparsity pattern of the table scatter)
-    nz_w, nz_g = want != 0, got != 0
+    # (entries below 1e-6 of the largest one may legitimately underflow to zero on one side only)
+    nz_w, nz_g = want.abs() > 1e-6 * scale, got != 0
     assert float((nz_w & ~nz_g).float().mean()) < 1e-4, what
 
 
@@ -378,6 +379,7 @@ def test_training_step_gradients_match_autograd_end_to_end(monkeypatch):
     target = torch.rand(48, 3, generator=gen)
     c0, c1 = torch.randn(48, 64, 1, generator=gen), torch.randn(48, 32, 1, generator=gen)
 
+    torch.manual_seed(11)  # the sampler draws its stratified jitter from the global generator, like the reference
     out = m(api.RayBundle(origins=o, directions=d), get_feature=[])
     assert set(out) >= {"rgb", "depth", "accumulation", "prop_depth_0", "weights_list", "ray_samples_list"}
     loss = ((out["rgb"] - target) ** 2).mean() + (out["weights_list"][0] * c0).mean() + (out["weights_list"][1] * c1).mean()
@@ -388,8 +390,10 @@ def test_training_step_gradients_match_autograd_end_to_end(monkeypatch):
     p = {k: v.clone().requires_grad_(k in names) for k, v in params.items()}
     orc = Oracle(cfg, p)
     nears, fars = torch.full((48, 1), 0.05), torch.full((48, 1), float(cfg.far_plane))
+    jit = m.proposal_sampler.last_jitter  # the stratified draws of this training step
+    assert jit is not None and jit.shape == (48, 2)
     with torch.no_grad():
-        res = orc0.render_rays(o, d, nears, fars, get_feature=(), return_intermediates=True)
+        res = orc0.render_rays(o, d, nears, fars, get_feature=(), return_intermediates=True, jitter=jit)
     eu0, eu1 = res["_eu0"], res["_eu1"]
     pos0 = o[:, None, :] + d[:, None, :] * ((eu0[:, :-1] + eu0[:, 1:]) / 2)[..., None]
     pos1 = o[:, None, :] + d[:, None, :] * ((eu1[:, :-1] + eu1[:, 1:]) / 2)[..., None]
@@ -503,3 +507,20 @@ def test_gpu_full_training_step_lowers_rgb_and_feature_losses():
         opt.step()
         hist.append((float(rgb_loss.detach()), float(sam_loss.detach())))
     assert hist[-1][0] < hist[0][0] and hist[-1][1] < hist[0][1], hist
+
+
+def test_jittered_bins_are_the_torch_expression_bit_for_bit():
+    """The closed form the march kernel uses for the training-mode spacing bins (common.cuh jittered_bin) against
+    the reference's tensor expression (ray_samplers.py:100-111)."""
+    from emu.build_emu import load
+
+    n, nb = 4096, 64
+    t_rand = torch.rand(n, 1, generator=torch.Generator().manual_seed(0))
+    bins = torch.linspace(0.0, 1.0, nb + 1)[None, ...]
+    centers = (bins[..., 1:] + bins[..., :-1]) / 2.0
+    upper, lower = torch.cat([centers, bins[..., -1:]], -1), torch.cat([bins[..., :1], centers], -1)
+    want = lower + (upper - lower) * t_rand
+    got = np.zeros((n, nb + 1), np.float32)
+    tr = np.ascontiguousarray(t_rand.numpy().ravel(), np.float32)
+    load().emu_jittered_bins(tr.ctypes.data_as(C.c_void_p), C.c_longlong(n), nb, got.ctypes.data_as(C.c_void_p))
+    assert np.array_equal(got, want.numpy())

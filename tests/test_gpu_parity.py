@@ -205,3 +205,29 @@ def test_component_shims(tiny):
     sw = torch.rand(300, 16, generator=torch.Generator().manual_seed(2))
     assert_mostly_close(MeanRenderer(r)(emb.cuda(), sw[..., None].cuda()), (sw[..., None] * emb).sum(-2),
                         dict(rtol=1e-5, atol=1e-5), 1.0, "mean renderer")
+
+
+@pytest.mark.hw_unverified
+def test_training_mode_sampler_matches_reference():
+    """snrf_sample with snrf_set_jitter (march_kernel<.., JIT>) against the reference's own ProposalNetworkSampler
+    run in training mode with recorded torch.rand draws (tests/golden/sampler_training.npz)."""
+    import os
+
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sampler_training.npz"))
+    from samnerf_b200 import SAMNeRFConfig, make_synthetic_params
+
+    cfg = SAMNeRFConfig.tiny(clipseg=False, patch_size=1)
+    r = make_renderer(cfg, make_synthetic_params(cfg, "scene", 8))
+    o, d, jit = (torch.from_numpy(z[k]) for k in ("_origins", "_directions", "jitter"))
+    w0, edges1, _ = r.sample(o, d, jitter=jit)
+    torch.cuda.synchronize()
+    assert_mostly_close(w0, z["w0"], TOL["weights"], FRAC_SMOOTH, "training-mode proposal weights")
+    assert_mostly_close(edges1, z["edges1"], TOL["edges"], 0.99, "training-mode nerf bin edges")
+    # one-shot: the next call is an eval-mode call again, and a mismatched ray count is refused
+    w0_eval, edges_eval, _ = r.sample(o, d)
+    ref_eval = r.sample(o, d)
+    assert torch.equal(edges_eval, ref_eval[1]) and float((edges_eval - edges1).abs().max()) > 1e-3
+    with pytest.raises(RuntimeError, match="snrf_set_jitter"):
+        r.sample(o[:10], d[:10], jitter=jit)
+    out = r.render(o, d, get_feature=(), debug=True, jitter=jit)
+    assert_mostly_close(out["_edges"], z["edges1"], TOL["edges"], 0.99, "render() with jitter uses the same samples")

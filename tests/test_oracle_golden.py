@@ -52,3 +52,26 @@ def test_image_matches_reference():
     for key in ("rgb", "accumulation", "depth", "prop_depth_0", "clipseg"):
         np.testing.assert_allclose(out[key].numpy(), g[key], rtol=1e-5, atol=1e-6, err_msg=key)
     np.testing.assert_allclose(out["sam"].numpy()[::st, ::st], g["sam"], rtol=1e-5, atol=2e-6)
+
+
+def test_training_mode_sampler_matches_reference():
+    """Stratified single-jitter sampling (ray_samplers.py:104-112,314-322): the reference's own sampler in training
+    mode with its torch.rand draws recorded (oracle/make_jitter_golden.py) vs the oracle fed the same draws."""
+    import numpy as np
+    import torch
+
+    from oracle.samnerf_oracle import Oracle
+    from samnerf_b200 import SAMNeRFConfig, make_synthetic_params
+
+    z = np.load(os.path.join(GOLDEN, "sampler_training.npz"))
+    cfg = SAMNeRFConfig.tiny(clipseg=False, patch_size=1)
+    orc = Oracle(cfg, make_synthetic_params(cfg, "scene", 8))
+    o, d, jit = (torch.from_numpy(z[k]) for k in ("_origins", "_directions", "jitter"))
+    res = orc.render_rays(o, d, get_feature=(), return_intermediates=True, jitter=jit)
+    np.testing.assert_allclose(res["_eu0"].numpy(), z["edges0"], rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(res["_w0"].numpy(), z["w0"], rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(res["_bins1"].numpy(), z["spacing1"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(res["_eu1"].numpy(), z["edges1"], rtol=2e-5, atol=1e-6)
+    # and the jitter really moved the samples away from the eval-mode positions
+    ev = orc.render_rays(o, d, get_feature=(), return_intermediates=True)
+    assert float((ev["_eu1"] - res["_eu1"]).abs().max()) > 1e-3
