@@ -1,0 +1,11 @@
+#!/bin/bash
+# First gpurun call of the next round: everything that was written after the round-1 GPU budget was spent.
+#   gpurun --timeout 1500 -- 'bash tools/round2_first_call.sh'
+# Writes gpurun_out/r2_*.log / *.json.  Each step has its own timeout so that one hang cannot eat the call.
+mkdir -p gpurun_out
+echo "== verified GPU tests"; timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/r2_tests_verified.log 2>&1; tail -3 gpurun_out/r2_tests_verified.log
+echo "== hardware-unverified GPU tests (no -x: see every failure)"
+SNRF_RUN_UNVERIFIED=1 timeout 900 python -m pytest tests -m "gpu and hw_unverified" -q > gpurun_out/r2_tests_unverified.log 2>&1; tail -25 gpurun_out/r2_tests_unverified.log
+echo "== bench (exact)"; timeout 400 python bench.py > gpurun_out/r2_bench.json 2> gpurun_out/r2_bench.err; tail -c 600 gpurun_out/r2_bench.json
+echo "== bench (early termination 1e-4)"; timeout 300 python bench.py --early-termination 1e-4 --no-cpu-baseline > gpurun_out/r2_bench_et.json 2>> gpurun_out/r2_bench.err; tail -c 400 gpurun_out/r2_bench_et.json
+echo "== training step"; timeout 300 python tools/bench_train.py > gpurun_out/r2_train.json 2> gpurun_out/r2_train.err; cat gpurun_out/r2_train.json; tail -3 gpurun_out/r2_train.err
