@@ -228,8 +228,8 @@ int snrf_feature_forward(snrf_ctx* ctx, int which, const float* origins, const f
                          const float* sam_w, int64_t n_rays, float* out, void* enc_f16, void* stream);
 /* Given d_out[N,n_out], ACCUMULATE (+=, like torch's .grad) fp32 gradients in the reference's flat layouts:
  * grad_net [256*192 + n_out*256] for sam_field.{sam,clipseg}_net.params (layer-1 matrix, then layer-2),
- * grad_grid0 / grad_grid1 [entries*8] for sam_field.{clip,clipseg}_encs.{0,1}.params.  Any of the three may be
- * NULL (that parameter is frozen).  Replaces tinycudann's autograd for these modules (sam_field.py:51,63,84,99). */
+ * grad_grid0 / grad_grid1 [entries*8] for sam_field.{clip,clipseg}_encs.{0,1}.params (16-byte aligned: the table
+ * scatter uses vector reductions).  Any of the three may be NULL (that parameter is frozen).  Replaces tinycudann's autograd for these modules (sam_field.py:51,63,84,99). */
 int snrf_feature_backward(snrf_ctx* ctx, int which, const float* origins, const float* dirs, const float* sam_t,
                           const float* sam_w, int64_t n_rays, const float* d_out, const void* enc_f16,
                           float* grad_net, float* grad_grid0, float* grad_grid1, void* stream);
@@ -240,7 +240,7 @@ int snrf_feature_backward(snrf_ctx* ctx, int which, const float* origins, const 
  * losses on [N,S] tensors.  which: 0 = proposal field, 1 = nerfacto field.  xyz[n,3] world positions; dirs[n,3]
  * (nerfacto with d_rgb, else NULL); d_density[n] / d_rgb[n,3]: upstream gradients, either may be NULL.
  * grad_base: flat fp32 gradient of proposal_networks.0.mlp_base.params / field.mlp_base.params (MLP matrices, then the
- * grid), grad_head: of field.mlp_head.params (needed with d_rgb).  Gradients are ACCUMULATED (+=).
+ * grid; 16-byte aligned), grad_head: of field.mlp_head.params (needed with d_rgb).  Gradients are ACCUMULATED (+=).
  * trunc_exp backward is g * exp(clamp(x, -15, 15)) (activations.py:33-37). */
 int snrf_field_backward(snrf_ctx* ctx, int which, const float* xyz, const float* dirs, int64_t n,
                         const float* d_density, const float* d_rgb, float* grad_base, float* grad_head, void* stream);

@@ -1026,6 +1026,8 @@ int snrf_feature_backward(snrf_ctx* ctx, int which, const float* origins, const 
   if (which < 0 || which > 1 || n_rays < 0) return fail(ctx, SNRF_E_INVALID, "bad argument");
   if (n_rays == 0) return SNRF_OK;
   if (!origins || !dirs || !sam_t || !sam_w || !d_out || !enc_f16) return fail(ctx, SNRF_E_INVALID, "null argument");
+  if ((reinterpret_cast<uintptr_t>(grad_grid0) | reinterpret_cast<uintptr_t>(grad_grid1)) & 15u)
+    return fail(ctx, SNRF_E_INVALID, "grid gradients must be 16-byte aligned");
   FeatureNet& f = ctx->feat[which];
   if (!f.have_grid[0] || !f.have_grid[1] || !f.have_net)
     return fail(ctx, SNRF_E_STATE, "%s parameters not uploaded", which == 0 ? "sam_field" : "clipseg");
@@ -1076,6 +1078,7 @@ int snrf_field_backward(snrf_ctx* ctx, int which, const float* xyz, const float*
   if (!xyz || !grad_base || (!d_density && !d_rgb)) return fail(ctx, SNRF_E_INVALID, "null argument");
   if (d_rgb && (which != 1 || !dirs || !grad_head))
     return fail(ctx, SNRF_E_INVALID, "d_rgb needs the nerfacto field (which = 1), dirs and grad_head");
+  if (reinterpret_cast<uintptr_t>(grad_base) & 15u) return fail(ctx, SNRF_E_INVALID, "grad_base must be 16-byte aligned");
   if (which == 0 ? !ctx->have_prop : !(ctx->have_base && (ctx->have_head || !d_rgb)))
     return fail(ctx, SNRF_E_STATE, "field parameters not uploaded");
   cudaStream_t s = static_cast<cudaStream_t>(stream);

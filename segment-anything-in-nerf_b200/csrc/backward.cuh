@@ -36,6 +36,24 @@ SNRF_HD void atomic_add_f32(float* p, float v) {
 #endif
 }
 
+// F consecutive floats at a 4F-byte aligned address: one vector reduction (REDG.E.ADD.F32x4 / F32x2, sm_90+)
+// instead of F scalar ones
+template <int F>
+SNRF_HD void atomic_add_vec(float* p, const float (&v)[F]) {
+#ifdef __CUDA_ARCH__
+  if (F == 8) {
+    atomicAdd(reinterpret_cast<float4*>(p), make_float4(v[0], v[1], v[2], v[3]));
+    atomicAdd(reinterpret_cast<float4*>(p) + 1, make_float4(v[4 % F], v[5 % F], v[6 % F], v[7 % F]));
+  } else if (F == 2) {
+    atomicAdd(reinterpret_cast<float2*>(p), make_float2(v[0], v[1]));
+  } else {
+    for (int f = 0; f < F; ++f) atomicAdd(p + f, v[f]);
+  }
+#else
+  for (int f = 0; f < F; ++f) p[f] += v[f];
+#endif
+}
+
 template <typename T>
 SNRF_HD float ld_f32(const T* p);
 template <>
@@ -108,8 +126,9 @@ SNRF_HD void grid_scatter_one(const GridDev& G, bool linf, bool selector, const 
     w *= (c & 2) ? ry : 1.f - ry;
     w *= (c & 4) ? rz : 1.f - rz;
     const uint32_t idx = grid_index(L, gx + (c & 1), gy + ((c >> 1) & 1), gz + (c >> 2));
-    float* t = g_table + static_cast<size_t>(idx) * F;
-    for (int f = 0; f < F; ++f) atomic_add_f32(t + f, w * g[f]);
+    float wg[F];
+    for (int f = 0; f < F; ++f) wg[f] = w * g[f];
+    atomic_add_vec<F>(g_table + static_cast<size_t>(idx) * F, wg);
   }
 }
 
