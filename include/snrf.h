@@ -234,6 +234,13 @@ int snrf_feature_backward(snrf_ctx* ctx, int which, const float* origins, const 
                           const float* sam_w, int64_t n_rays, const float* d_out, const void* enc_f16,
                           float* grad_net, float* grad_grid0, float* grad_grid1, void* stream);
 
+/* Backward of snrf_patch_aggregate (conv head, sam_model.py:202-208,260-265; torch autograd + cuDNN in the reference):
+ * feat_in[P*16,256] as given to the forward call, d_out[P,256].  grad_w0 / grad_w2 [256*256*9] and grad_b0 / grad_b2
+ * [256] in torch's Conv2d layouts, ACCUMULATED (+=); d_feat[P*16,256] WRITTEN (NULL = not needed). */
+int snrf_patch_aggregate_backward(snrf_ctx* ctx, const float* feat_in, int64_t n_patches, int p, const float* d_out,
+                                  float* grad_w0, float* grad_b0, float* grad_w2, float* grad_b2, float* d_feat,
+                                  void* stream);
+
 /* Backward of the density fields at arbitrary sample positions - the counterpart of snrf_query_density /
  * snrf_query_rgb, i.e. what tinycudann's autograd does for HashMLPDensityField (density_fields.py:92-125) and
  * TCNNNerfactoField (nerfacto_field.py:157-175,228-351) while torch autograd handles weights, compositing and the

@@ -85,6 +85,7 @@ SYMBOLS = {
                                 _P, _P, _P]),
     "snrf_feature_forward": (_I, [_P, _I, _P, _P, _P, _P, _L, _P, _P, _P]),
     "snrf_feature_backward": (_I, [_P, _I, _P, _P, _P, _P, _L, _P, _P, _P, _P, _P, _P]),
+    "snrf_patch_aggregate_backward": (_I, [_P, _P, _L, _I, _P, _P, _P, _P, _P, _P, _P]),
     "snrf_field_backward": (_I, [_P, _I, _P, _P, _L, _P, _P, _P, _P, _P]),
     "snrf_ray_op_backward": (_I, [_P, _I, _P, _P, _P, _P, _P, _L, _I, _I, _P, _P]),
     "snrf_launch_count": (_L, [_P]),

@@ -82,6 +82,7 @@ struct snrf_ctx {
   FeatureNet feat[2];
   // conv head
   DevBuf conv_w[2], conv_b[2];
+  DevBuf conv_w_rm[2];  // [256 x 2304] row-major fp16 = torch's Conv2d layout (backward pass)
   bool have_conv = false;
   // per-kernel CUDA-event timing (bench.py's roofline): 0 march, 1 feature gather+MLP1, 2 tap GEMM
   bool timing = false;
@@ -284,6 +285,7 @@ void snrf_ctx_destroy(snrf_ctx* ctx) {
   for (DevBuf* b : bufs) b->release();
   ctx->sam_t[1].release(); ctx->sam_w[1].release();
   ctx->cam_rows.release(); ctx->cam_cols.release(); ctx->cam_o.release(); ctx->cam_d.release();
+  ctx->conv_w_rm[0].release(); ctx->conv_w_rm[1].release();
   ctx->bwd_scratch.release(); ctx->bwd_sink.release();
   ctx->hbar[0][1].release(); ctx->hbar[1][0].release(); ctx->hbar[1][1].release();
   if (ctx->aux_feat) cudaStreamDestroy(ctx->aux_feat);
@@ -548,7 +550,12 @@ int snrf_upload_conv_head(snrf_ctx* ctx, const float* w0, const float* b0, const
       for (int i = 0; i < 256; ++i)
         for (int t = 0; t < 9; ++t) taps[(static_cast<size_t>(t) * 256 + o) * 256 + i] = host[(static_cast<size_t>(o) * 256 + i) * 9 + t];
     DevBuf tmp;
-    int rc = stage(ctx, taps.data(), n_w, tmp, s);
+    int rc = stage(ctx, host.data(), n_w, tmp, s);
+    if (rc) return rc;
+    CK(ctx->conv_w_rm[c].ensure(n_w * 2));
+    LAUNCH(launch_f32_to_f16(tmp.as<float>(), ctx->conv_w_rm[c].as<__half>(), n_w, s));
+    CK(cudaStreamSynchronize(s));
+    rc = stage(ctx, taps.data(), n_w, tmp, s);
     if (rc) return rc;
     CK(ctx->conv_w[c].ensure(n_w * 2));
     for (int t = 0; t < 9; ++t)
@@ -1067,6 +1074,36 @@ int snrf_feature_backward(snrf_ctx* ctx, int which, const float* origins, const 
   const cudaError_t e = launch_feat_backward(B, s, &launched);
   ctx->launches += launched;
   if (e != cudaSuccess) return fail(ctx, SNRF_E_CUDA, "feature backward failed: %s", cudaGetErrorString(e));
+  return SNRF_OK;
+}
+
+int snrf_patch_aggregate_backward(snrf_ctx* ctx, const float* feat_in, int64_t n_patches, int p, const float* d_out,
+                                  float* grad_w0, float* grad_b0, float* grad_w2, float* grad_b2, float* d_feat,
+                                  void* stream) {
+  if (!ctx) return SNRF_E_INVALID;
+  if (!feat_in || !d_out || !grad_w0 || !grad_b0 || !grad_w2 || !grad_b2 || n_patches < 0)
+    return fail(ctx, SNRF_E_INVALID, "null argument");
+  if (p != 4) return fail(ctx, SNRF_E_INVALID, "patch_size %d unsupported (the conv head kernels are built for p = 4)", p);
+  if (!ctx->have_conv) return fail(ctx, SNRF_E_STATE, "conv head parameters not uploaded");
+  if (n_patches == 0) return SNRF_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CK(cudaSetDevice(ctx->device));
+  CK(ctx->bwd_scratch.ensure(conv_bwd_scratch_bytes(n_patches)));
+  ConvBwdParams B;
+  memset(&B, 0, sizeof(B));
+  B.feat_in = feat_in;
+  B.d_out = d_out;
+  B.rows = n_patches * 16;
+  B.w1 = ctx->conv_w_rm[0].as<__half>();
+  B.w2 = ctx->conv_w_rm[1].as<__half>();
+  B.b1 = ctx->conv_b[0].as<float>();
+  B.b2 = ctx->conv_b[1].as<float>();
+  B.g_w1 = grad_w0; B.g_b1 = grad_b0; B.g_w2 = grad_w2; B.g_b2 = grad_b2;
+  B.d_feat = d_feat;
+  int64_t launched = 0;
+  const cudaError_t e = launch_conv_backward(B, ctx->bwd_scratch.p, s, &launched);
+  ctx->launches += launched;
+  if (e != cudaSuccess) return fail(ctx, SNRF_E_CUDA, "conv head backward failed: %s", cudaGetErrorString(e));
   return SNRF_OK;
 }
 

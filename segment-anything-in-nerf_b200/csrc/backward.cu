@@ -60,9 +60,44 @@ __global__ void rgb_bwd_kernel(const float* rgb, const float* w, const float* g_
   if (i < items) rgb_bwd_one(rgb, w, g_out, bg_fixed, bg0, bg1, bg2, d_rgb, d_w, S, i);
 }
 
+template <typename TX>
+__global__ void conv_im2col_kernel(const TX* X, __half* Xcol, int64_t items) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < items) conv_im2col_one<TX>(X, Xcol, i);
+}
+__global__ void conv_fwd_kernel(const __half* Xcol, const __half* W, const float* b, __half* Y, int relu, int64_t items) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < items) conv_fwd_one(Xcol, W, b, Y, relu, i);
+}
+__global__ void conv_mean_bwd_kernel(const float* d_out, float* d_y, int64_t items) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < items) conv_mean_bwd_one(d_out, d_y, i);
+}
+__global__ void conv_col2im_kernel(const float* dXcol, const __half* mask, float* dX, int64_t items) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < items) conv_col2im_one(dXcol, mask, dX, i);
+}
+__global__ void conv_bias_grad_kernel(const float* dY, int64_t rows, float* g_b, int64_t items) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < items) conv_bias_grad_one(dY, rows, g_b, i);
+}
+
 // executor of the backward chains of backward.cuh: every step is one kernel launch on `s`
 struct DeviceExec {
   cudaStream_t s;
+  void im2col_f32(const float* X, __half* Xcol, int64_t items) { conv_im2col_kernel<float><<<blocks_for(items), kThreads, 0, s>>>(X, Xcol, items); }
+  void im2col_f16(const __half* X, __half* Xcol, int64_t items) { conv_im2col_kernel<__half><<<blocks_for(items), kThreads, 0, s>>>(X, Xcol, items); }
+  void conv_fwd(const __half* Xcol, const __half* W, const float* b, __half* Y, int relu, int64_t items) {
+    conv_fwd_kernel<<<blocks_for(items), kThreads, 0, s>>>(Xcol, W, b, Y, relu, items);
+  }
+  void conv_mean_bwd(const float* d_out, float* d_y, int64_t items) { conv_mean_bwd_kernel<<<blocks_for(items), kThreads, 0, s>>>(d_out, d_y, items); }
+  void col2im(const float* dXcol, const __half* mask, float* dX, int64_t items) {
+    conv_col2im_kernel<<<blocks_for(items), kThreads, 0, s>>>(dXcol, mask, dX, items);
+  }
+  void bias_grad(const float* dY, int64_t rows, float* g_b) {
+    const int64_t items = ((rows + kSlabRows - 1) / kSlabRows) * kConvC;
+    conv_bias_grad_kernel<<<blocks_for(items), kThreads, 0, s>>>(dY, rows, g_b, items);
+  }
   void dgrad(const float* dY, int ldy, int ny, const __half* W, int ldw, const __half* X, int ldx, float* dX, int lddx,
              int nx, int64_t rows) {
     const int64_t items = rows * nx;
@@ -232,6 +267,40 @@ cudaError_t launch_field_backward(const FieldBwdParams& P0, void* scratch, cudaS
     field_backward_chain(P, ex);
     if (launches) *launches += colour ? 13 : 6;
     e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}
+
+// ---------------------------------------------------------------------------------------------
+// conv head
+// ---------------------------------------------------------------------------------------------
+size_t conv_bwd_scratch_bytes(int64_t n_patches) {
+  const int64_t rows = (n_patches < kConvBwdBlockPatches ? n_patches : kConvBwdBlockPatches) * kConvPos;
+  return static_cast<size_t>(rows) * (2 * kConvK * 2 + kConvC * 2 + kConvC * 4 + kConvK * 4 + kConvC * 4) + 256;
+}
+
+cudaError_t launch_conv_backward(const ConvBwdParams& P0, void* scratch, cudaStream_t s, int64_t* launches) {
+  const int64_t block_rows = kConvBwdBlockPatches * kConvPos;
+  for (int64_t r0 = 0; r0 < P0.rows; r0 += block_rows) {
+    const int64_t n = P0.rows - r0 < block_rows ? P0.rows - r0 : block_rows;
+    ConvBwdParams P = P0;
+    P.feat_in += r0 * kConvC;
+    P.d_out += (r0 / kConvPos) * kConvC;
+    if (P.d_feat) P.d_feat += r0 * kConvC;
+    P.rows = n;
+    float* f = reinterpret_cast<float*>(scratch);
+    P.d_y = f;      f += n * kConvC;
+    P.d_xcol = f;   f += n * kConvK;
+    P.d_hid = f;    f += n * kConvC;
+    __half* h = reinterpret_cast<__half*>(f);
+    P.xcol1 = h;    h += n * kConvK;
+    P.xcol2 = h;    h += n * kConvK;
+    P.hid = h;
+    DeviceExec ex{s};
+    conv_backward_chain(P, ex);
+    if (launches) *launches += P.d_feat ? 12 : 10;
+    const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
   }
   return cudaSuccess;

@@ -336,6 +336,109 @@ cudaError_t launch_weights_bwd(const float* deltas, const float* dens, const flo
 cudaError_t launch_rgb_bwd(const float* rgb, const float* w, const float* g_out, int bg_fixed, const float* bg,
                            float* d_rgb, float* d_w, int64_t n, int S, cudaStream_t stream);
 
+// ---------------------------------------------------------------------------------------------
+// conv head (patch aggregation, sam_model.py:202-208,260-265): Conv3x3(pad 1) -> ReLU -> Conv3x3(pad 1) -> mean over
+// the 4 x 4 patch.  Rows are patch-major with row-major positions inside a patch; torch's Conv2d weight
+// [out][in][ky][kx] read as a row-major [256 x 2304] matrix with k = in*9 + ky*3 + kx is the GEMM operand of the
+// im2col form, so weight gradients come out directly in the layout of `conv_head.{0,2}.weight.grad`.
+// Operands are fp16 with fp32 accumulation like the forward kernel (deviation 3).
+// ---------------------------------------------------------------------------------------------
+constexpr int kConvC = 256, kConvP = 4, kConvPos = kConvP * kConvP, kConvK = kConvC * 9;
+
+// row of the position shifted by tap (ky, kx) inside the same patch, or -1 outside the patch
+SNRF_HD int64_t conv_shifted_row(int64_t row, int dy, int dx) {
+  const int pos = static_cast<int>(row % kConvPos);
+  const int y = pos / kConvP + dy, x = pos % kConvP + dx;
+  if (y < 0 || y >= kConvP || x < 0 || x >= kConvP) return -1;
+  return row - pos + y * kConvP + x;
+}
+// Xcol[row, i*9 + ky*3 + kx] = X[shifted(row, ky-1, kx-1), i] (0 outside)                 item = (row, k)
+template <typename TX>
+SNRF_HD void conv_im2col_one(const TX* X, __half* Xcol, int64_t item) {
+  const int64_t row = item / kConvK;
+  const int k = static_cast<int>(item % kConvK);
+  const int i = k / 9, t = k % 9;
+  const int64_t src = conv_shifted_row(row, t / 3 - 1, t % 3 - 1);
+  Xcol[item] = __float2half_rn(src < 0 ? 0.f : ld_f32<TX>(X + src * kConvC + i));
+}
+// Y[row,o] = fp16(act(sum_k Xcol[row,k] W[o,k] + b[o]))                                   item = (row, o)
+SNRF_HD void conv_fwd_one(const __half* Xcol, const __half* W, const float* b, __half* Y, int relu, int64_t item) {
+  const int64_t row = item / kConvC;
+  const int o = static_cast<int>(item % kConvC);
+  const __half* x = Xcol + row * kConvK;
+  const __half* w = W + static_cast<size_t>(o) * kConvK;
+  float a = 0.f;
+  for (int k = 0; k < kConvK; ++k) a += __half2float(x[k]) * __half2float(w[k]);
+  a += b[o];
+  if (relu) a = fmaxf(a, 0.f);
+  Y[item] = __float2half_rn(a);
+}
+// d_y[row,o] = d_out[patch(row), o] / 16 (backward of the mean over the patch)            item = (row, o)
+SNRF_HD void conv_mean_bwd_one(const float* d_out, float* d_y, int64_t item) {
+  const int64_t row = item / kConvC;
+  d_y[item] = d_out[(row / kConvPos) * kConvC + item % kConvC] / static_cast<float>(kConvPos);
+}
+// adjoint of im2col: dX[row,i] = sum_t dXcol[shifted(row, 1-ky, 1-kx), i*9 + t], times [mask > 0] if given
+//                                                                                         item = (row, i)
+SNRF_HD void conv_col2im_one(const float* dXcol, const __half* mask, float* dX, int64_t item) {
+  const int64_t row = item / kConvC;
+  const int i = static_cast<int>(item % kConvC);
+  float a = 0.f;
+  for (int t = 0; t < 9; ++t) {
+    const int64_t src = conv_shifted_row(row, 1 - t / 3, 1 - t % 3);
+    if (src >= 0) a += dXcol[src * kConvK + i * 9 + t];
+  }
+  if (mask && !(__half2float(mask[item]) > 0.f)) a = 0.f;
+  dX[item] = a;
+}
+// g_b[o] += sum_{row in slab} dY[row,o]                                                   item = (slab, o)
+SNRF_HD void conv_bias_grad_one(const float* dY, int64_t rows, float* g_b, int64_t item) {
+  const int o = static_cast<int>(item % kConvC);
+  const int64_t r0 = (item / kConvC) * kSlabRows;
+  const int64_t r1 = r0 + kSlabRows < rows ? r0 + kSlabRows : rows;
+  float a = 0.f;
+  for (int64_t r = r0; r < r1; ++r) a += dY[r * kConvC + o];
+  atomic_add_f32(g_b + o, a);
+}
+
+struct ConvBwdParams {
+  const float* feat_in;   // [rows,256] fp32 rows as handed to snrf_patch_aggregate
+  const float* d_out;     // [rows/16,256]
+  int64_t rows;
+  const __half *w1, *w2;  // [256 x 2304] row-major fp16 (torch layout)
+  const float *b1, *b2;   // [256]
+  // scratch
+  __half *xcol1, *xcol2, *hid;  // [rows,2304] x2, [rows,256]
+  float *d_y, *d_xcol, *d_hid;  // [rows,256], [rows,2304], [rows,256]
+  // outputs: parameter gradients accumulated (+=), d_feat written
+  float *g_w1, *g_b1, *g_w2, *g_b2;
+  float* d_feat;          // [rows,256] or null
+};
+template <class Exec>
+inline void conv_backward_chain(const ConvBwdParams& P, Exec& ex) {
+  const int64_t n = P.rows;
+  // forward recomputation
+  ex.im2col_f32(P.feat_in, P.xcol1, n * kConvK);
+  ex.conv_fwd(P.xcol1, P.w1, P.b1, P.hid, 1, n * kConvC);
+  ex.im2col_f16(P.hid, P.xcol2, n * kConvK);
+  // second conv
+  ex.conv_mean_bwd(P.d_out, P.d_y, n * kConvC);
+  ex.bias_grad(P.d_y, n, P.g_b2);
+  ex.wgrad_h(P.d_y, kConvC, kConvC, P.xcol2, kConvK, kConvK, n, P.g_w2, kConvK);
+  ex.dgrad(P.d_y, kConvC, kConvC, P.w2, kConvK, nullptr, 0, P.d_xcol, kConvK, kConvK, n);
+  ex.col2im(P.d_xcol, P.hid, P.d_hid, n * kConvC);
+  // first conv
+  ex.bias_grad(P.d_hid, n, P.g_b1);
+  ex.wgrad_h(P.d_hid, kConvC, kConvC, P.xcol1, kConvK, kConvK, n, P.g_w1, kConvK);
+  if (P.d_feat) {
+    ex.dgrad(P.d_hid, kConvC, kConvC, P.w1, kConvK, nullptr, 0, P.d_xcol, kConvK, kConvK, n);
+    ex.col2im(P.d_xcol, nullptr, P.d_feat, n * kConvC);
+  }
+}
+constexpr int64_t kConvBwdBlockPatches = 256;  // 4096 rows, 21 KB of scratch per row
+size_t conv_bwd_scratch_bytes(int64_t n_patches);
+cudaError_t launch_conv_backward(const ConvBwdParams& P, void* scratch, cudaStream_t stream, int64_t* launches);
+
 constexpr int64_t kFieldBwdBlock = 1 << 16;  // samples per internal block (1.8 KB of scratch per sample)
 size_t field_bwd_scratch_bytes(int64_t n);
 // `fwd` runs the forward recomputation (encode + dense layers) into the activation buffers: supplied by api.cu so that

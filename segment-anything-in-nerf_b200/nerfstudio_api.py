@@ -468,6 +468,22 @@ class _RGBCompositeFn(torch.autograd.Function):
         return d_rgb, d_w, None, None
 
 
+class _PatchAggregateFn(torch.autograd.Function):
+    """``conv_head(feat).mean(dim=[2, 3])`` over 4 x 4 ray patches (sam_model.py:202-208,260-265)."""
+
+    @staticmethod
+    def forward(ctx, feat, w0, b0, w2, b2, renderer):
+        ctx.renderer = renderer
+        ctx.save_for_backward(feat)
+        return renderer.patch_aggregate(feat)
+
+    @staticmethod
+    def backward(ctx, d_out):
+        (feat,) = ctx.saved_tensors
+        g, d_feat = ctx.renderer.patch_aggregate_backward(feat, d_out.contiguous(), want_d_feat=ctx.needs_input_grad[0])
+        return (d_feat,) + tuple(g[n] for n in Renderer.CONV_PARAMS) + (None,)
+
+
 class _FeatureBranchFn(torch.autograd.Function):
     """``MeanRenderer(SAMField.get_outputs(sam_samples))`` (sam_model.py:256-277, sam_field.py:112-140)."""
 
@@ -531,14 +547,14 @@ class SAMModel:
     def train(self, mode: bool = True):
         """Training mode: every flat hot-path tensor becomes an fp32 ``nn.Parameter`` on the device whose gradient
         comes from libsnrf's backward kernels (``snrf_field_backward``, ``snrf_feature_backward``,
-        ``snrf_ray_op_backward``); the conv head (patch_size > 1) runs as a torch module so that autograd covers it.
+        ``snrf_patch_aggregate_backward``, ``snrf_ray_op_backward``).
         The collider switches to its training near plane (scene_colliders.py:185) and the sampler to stratified
         single-jitter sampling (ray_samplers.py:104-112,314-322)."""
         self.training = bool(mode)
         self.collider.training = self.training
         self.proposal_sampler.training = self.training
         if not self.training:
-            self._sync_params(eval_conv=True)
+            self._sync_params()
             return self
         loaded = getattr(self, "_loaded", None)
         if loaded is None:
@@ -553,13 +569,10 @@ class SAMModel:
                 if name in loaded:
                     self.params[name] = torch.nn.Parameter(loaded[name].to(dev, torch.float32).reshape(-1).clone())
                     self._uploaded[name] = self.params[name]._version
-            if "conv_head.0.weight" in loaded:
-                k = self.config.kernel_size
-                self.conv_head = torch.nn.Sequential(
-                    torch.nn.Conv2d(256, 256, k, stride=1, padding=(k - 1) // 2), torch.nn.ReLU(inplace=True),
-                    torch.nn.Conv2d(256, 256, k, stride=1, padding=(k - 1) // 2)).to(dev)
-                self.conv_head.load_state_dict({n[len("conv_head."):]: v for n, v in loaded.items() if n.startswith("conv_head.")})
-                self._conv_uploaded = [p._version for p in self.conv_head.parameters()]
+            if self.config.distill_sam and self.config.patch_size > 1 and "conv_head.0.weight" in loaded:
+                for name in Renderer.CONV_PARAMS:
+                    self.params[name] = torch.nn.Parameter(loaded[name].to(dev, torch.float32).clone())
+                    self._uploaded[name] = self.params[name]._version
         return self
 
     def eval(self):
@@ -574,8 +587,9 @@ class SAMModel:
         }
         if self.config.distill_sam:
             groups["sam_field"] = [v for k, v in p.items() if k.startswith("sam_field.")]
-        if getattr(self, "conv_head", None) is not None:
-            groups["conv"] = list(self.conv_head.parameters())
+            conv = [v for k, v in p.items() if k.startswith("conv_head.")]
+            if conv:
+                groups["conv"] = conv
         return groups
 
     def state_dict(self) -> Dict[str, torch.Tensor]:
@@ -583,12 +597,9 @@ class SAMModel:
         sd = dict(getattr(self, "_loaded", {}))
         for name, p in getattr(self, "params", {}).items():
             sd[name] = p.detach().cpu().clone()
-        if getattr(self, "conv_head", None) is not None:
-            for n, v in self.conv_head.state_dict().items():
-                sd["conv_head." + n] = v.detach().cpu().clone()
         return sd
 
-    def _sync_params(self, eval_conv: bool = False) -> None:
+    def _sync_params(self) -> None:
         """Push parameters an optimiser step has changed (tensor version counters) back into the library's packed
         fp16 copies - the re-upload SURVEY 8 b asks for."""
         r = self.renderer
@@ -607,13 +618,11 @@ class SAMModel:
                     self._uploaded[name] = p._version
             if changed:
                 r.upload_feature_params(which, **changed)
-        conv = getattr(self, "conv_head", None)
-        if eval_conv and conv is not None:
-            versions = [p._version for p in conv.parameters()]
-            if versions != self._conv_uploaded:
-                sd = conv.state_dict()
-                r.upload_conv_head(*[sd[k] for k in ("0.weight", "0.bias", "2.weight", "2.bias")])
-                self._conv_uploaded = versions
+        conv = [getattr(self, "params", {}).get(n) for n in Renderer.CONV_PARAMS]
+        if conv[0] is not None and any(p._version != self._uploaded[n] for p, n in zip(conv, Renderer.CONV_PARAMS)):
+            r.upload_conv_head(*conv)
+            for p, n in zip(conv, Renderer.CONV_PARAMS):
+                self._uploaded[n] = p._version
 
     def _get_outputs_training(self, ray_bundle: RayBundle, get_feature, fast: bool):
         """sam_model.py:226-301 in training mode, component by component like the reference: the samplers' positions
@@ -647,9 +656,7 @@ class SAMModel:
                 names = Renderer.FEATURE_PARAMS[which]
                 feat = _FeatureBranchFn.apply(*[self.params[n] for n in names], r, which, o, d, sam_t, sam_w)
                 if which == "sam" and cfg.patch_size > 1:  # sam_model.py:260-265
-                    p = cfg.patch_size
-                    feat = feat.reshape(-1, p, p, feat.shape[-1]).permute(0, 3, 1, 2)
-                    feat = self.conv_head(feat).mean(dim=[2, 3])
+                    feat = _PatchAggregateFn.apply(feat, *[self.params[n] for n in Renderer.CONV_PARAMS], r)
                 out[which] = feat
         return out
 

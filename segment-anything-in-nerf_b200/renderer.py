@@ -451,6 +451,31 @@ class Renderer:
             g.data_ptr(), enc.data_ptr(), _ptr(res.get("net")), _ptr(res.get("grid0")), _ptr(res.get("grid1")), self.stream))
         return res
 
+    CONV_PARAMS = ("conv_head.0.weight", "conv_head.0.bias", "conv_head.2.weight", "conv_head.2.bias")
+
+    def patch_aggregate_backward(self, feat: torch.Tensor, d_out: torch.Tensor,
+                                 grads: Optional[Dict[str, torch.Tensor]] = None, want_d_feat: bool = True):
+        """Backward of ``patch_aggregate``: returns ``(grads, d_feat)`` with ``grads`` keyed like ``CONV_PARAMS``
+        (torch Conv2d layouts, accumulated into the tensors passed in) and ``d_feat[P*16,256]``."""
+        p = self.cfg.patch_size
+        f = feat.to(device=self.device, dtype=torch.float32).contiguous()
+        n_patches = f.shape[0] // (p * p)
+        g = d_out.to(device=self.device, dtype=torch.float32).reshape(n_patches, f.shape[1]).contiguous()
+        k = self.cfg.kernel_size
+        shapes = {"conv_head.0.weight": (256, 256, k, k), "conv_head.0.bias": (256,),
+                  "conv_head.2.weight": (256, 256, k, k), "conv_head.2.bias": (256,)}
+        grads = {} if grads is None else grads
+        for name, shp in shapes.items():
+            if name not in grads:
+                grads[name] = torch.zeros(*shp, device=self.device)
+            t = grads[name]
+            assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and tuple(t.shape) == shp, name
+        d_feat = torch.empty_like(f) if want_d_feat else None
+        self._check(self.lib.snrf_patch_aggregate_backward(
+            self.h, f.data_ptr(), n_patches, p, g.data_ptr(), *[grads[n].data_ptr() for n in self.CONV_PARAMS],
+            _ptr(d_feat), self.stream))
+        return grads, d_feat
+
     def field_backward(self, which: str, positions: torch.Tensor, directions: Optional[torch.Tensor] = None,
                        d_density: Optional[torch.Tensor] = None, d_rgb: Optional[torch.Tensor] = None,
                        grads: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:

@@ -53,6 +53,18 @@ struct HostExec {
                 int64_t points) {
     for (int64_t i = 0; i < points * G.n_levels; ++i) grid_scatter_one<8>(G, linf, sel, xyz, dX, lddx, col0, g, i);
   }
+  void im2col_f32(const float* X, __half* Xcol, int64_t items) { for (int64_t i = 0; i < items; ++i) conv_im2col_one<float>(X, Xcol, i); }
+  void im2col_f16(const __half* X, __half* Xcol, int64_t items) { for (int64_t i = 0; i < items; ++i) conv_im2col_one<__half>(X, Xcol, i); }
+  void conv_fwd(const __half* Xcol, const __half* W, const float* b, __half* Y, int relu, int64_t items) {
+    for (int64_t i = 0; i < items; ++i) conv_fwd_one(Xcol, W, b, Y, relu, i);
+  }
+  void conv_mean_bwd(const float* d_out, float* d_y, int64_t items) { for (int64_t i = 0; i < items; ++i) conv_mean_bwd_one(d_out, d_y, i); }
+  void col2im(const float* dXcol, const __half* mask, float* dX, int64_t items) {
+    for (int64_t i = 0; i < items; ++i) conv_col2im_one(dXcol, mask, dX, i);
+  }
+  void bias_grad(const float* dY, int64_t rows, float* g_b) {
+    for (int64_t i = 0; i < ((rows + kSlabRows - 1) / kSlabRows) * kConvC; ++i) conv_bias_grad_one(dY, rows, g_b, i);
+  }
   void feat_hidden(const FeatBwdParams& P, int64_t items) { for (int64_t i = 0; i < items; ++i) feat_hidden_one(P, i); }
   void feat_positions(const FeatBwdParams& P, int64_t items) { for (int64_t i = 0; i < items; ++i) feat_positions_one(P, i); }
   void sigmoid_bwd(const float* d_rgb, const __half* pre, int ldp, float* d_pre, int64_t items) {
@@ -114,6 +126,34 @@ int emu_rgb_backward(const float* rgb, const float* w, const float* g_out, int b
                      float* d_w, long long n, int S) {
   for (int64_t i = 0; i < n * S; ++i)
     rgb_bwd_one(rgb, w, g_out, bg_fixed, bg ? bg[0] : 0.f, bg ? bg[1] : 0.f, bg ? bg[2] : 0.f, d_rgb, d_w, S, i);
+  return 0;
+}
+
+// mirrors snrf_patch_aggregate_backward (HOST pointers; w1 / w2 are fp16 bit patterns of torch's [256,256,3,3] weights)
+int emu_conv_backward(const float* feat_in, long long n_patches, const float* d_out, const unsigned short* w1,
+                      const float* b1, const unsigned short* w2, const float* b2, float* g_w1, float* g_b1, float* g_w2,
+                      float* g_b2, float* d_feat, float* out_fwd /*[P,256] forward value of the recomputation, or null*/) {
+  ConvBwdParams P;
+  memset(&P, 0, sizeof(P));
+  const int64_t n = n_patches * kConvPos;
+  P.feat_in = feat_in; P.d_out = d_out; P.rows = n;
+  P.w1 = reinterpret_cast<const __half*>(w1); P.w2 = reinterpret_cast<const __half*>(w2); P.b1 = b1; P.b2 = b2;
+  std::vector<__half> xcol1(n * kConvK), xcol2(n * kConvK), hid(n * kConvC);
+  std::vector<float> d_y(n * kConvC), d_xcol(n * kConvK), d_hid(n * kConvC);
+  P.xcol1 = xcol1.data(); P.xcol2 = xcol2.data(); P.hid = hid.data();
+  P.d_y = d_y.data(); P.d_xcol = d_xcol.data(); P.d_hid = d_hid.data();
+  P.g_w1 = g_w1; P.g_b1 = g_b1; P.g_w2 = g_w2; P.g_b2 = g_b2; P.d_feat = d_feat;
+  HostExec ex;
+  conv_backward_chain(P, ex);
+  if (out_fwd) {  // second conv + patch mean from the recomputed activations, to check the recomputation itself
+    std::vector<__half> y2(n * kConvC);
+    for (int64_t i = 0; i < n * kConvC; ++i) {
+      const int64_t row = i / kConvC; const int o = static_cast<int>(i % kConvC);
+      float a = 0.f;
+      for (int k = 0; k < kConvK; ++k) a += __half2float(xcol2[row * kConvK + k]) * __half2float(P.w2[static_cast<size_t>(o) * kConvK + k]);
+      out_fwd[(row / kConvPos) * kConvC + o] += (a + b2[o]) / static_cast<float>(kConvPos);
+    }
+  }
   return 0;
 }
 

@@ -15,6 +15,7 @@ from samnerf_b200.renderer import Renderer
 class FakeRenderer:
     FEATURE_PARAMS = Renderer.FEATURE_PARAMS
     DENSITY_PARAMS = Renderer.DENSITY_PARAMS
+    CONV_PARAMS = Renderer.CONV_PARAMS
 
     def __init__(self, cfg, device: int = 0, engine: str = "tcgen05"):
         self.cfg, self.device, self.engine = cfg, torch.device("cpu"), engine
@@ -137,6 +138,29 @@ class FakeRenderer:
         for k, v in full.items():
             grads[k] = grads[k] + v if k in grads else v
         return grads
+
+    def patch_aggregate(self, feat):
+        with torch.no_grad():
+            return self.orc.patch_aggregate(feat)
+
+    def patch_aggregate_backward(self, feat, d_out, grads=None, want_d_feat=True):
+        from emu.build_emu import load
+
+        n_patches = feat.shape[0] // 16
+        arr = lambda t: np.ascontiguousarray(t.detach().numpy(), np.float32)
+        bits = lambda t: np.ascontiguousarray(t.detach().reshape(256, -1).to(torch.float16).numpy().view(np.uint16))
+        ptr = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+        w0, b0, w2, b2 = [self.p[n] for n in self.CONV_PARAMS]
+        g = [np.zeros(t.numel(), np.float32) for t in (w0, b0, w2, b2)]
+        d_feat = np.zeros((feat.shape[0], 256), np.float32) if want_d_feat else None
+        keep = [arr(feat), arr(d_out), bits(w0), arr(b0), bits(w2), arr(b2)]
+        load().emu_conv_backward(ptr(keep[0]), C.c_longlong(n_patches), ptr(keep[1]), ptr(keep[2]), ptr(keep[3]), ptr(keep[4]),
+                                 ptr(keep[5]), ptr(g[0]), ptr(g[1]), ptr(g[2]), ptr(g[3]), ptr(d_feat), None)
+        out = {n: torch.from_numpy(x).view(self.p[n].shape) for n, x in zip(self.CONV_PARAMS, g)}
+        grads = {} if grads is None else grads
+        for n, v in out.items():
+            grads[n] = grads[n] + v if n in grads else v
+        return grads, (None if d_feat is None else torch.from_numpy(d_feat))
 
     def upload_conv_head(self, w0, b0, w2, b2):
         from oracle.samnerf_oracle import Oracle
