@@ -420,7 +420,9 @@ def main():
                     help="opt-in transmittance threshold below which a ray's last 16 nerf samples are skipped "
                          "(0 = exact, the default and the headline configuration)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-rays", type=int, default=16384)
+    ap.add_argument("--cpu-rays", type=int, default=32768,
+                    help="rays of the bounded CPU-baseline sample (one reference chunk, timed twice: ~4 s of host work at "
+                         "the ~0.017 Mrays/s measured on the GPU box, ~45 s on a slow 8-core host)")
     ap.add_argument("--ref-rays", type=int, default=4096)
     args = ap.parse_args()
     if args.impl == "reference":
