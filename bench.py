@@ -199,6 +199,8 @@ def run_native(args):
     r.load_params(params)
     if args.early_termination > 0:
         r.set_early_termination(args.early_termination)  # opt-in, not the reference's exact arithmetic: see config
+    if args.feature_cutoff >= 0:
+        r.set_feature_cutoff(args.feature_cutoff)  # opt-in bucketed feature kernel: see config
     o_all, d_all = frame_rays()
     n_all = o_all.shape[0]
     assert H % world == 0
@@ -376,6 +378,7 @@ def run_native(args):
                        "tiles": (f"{world} row blocks of {H // world} rows; 256-d features exchanged by {gather_mode}, "
                                  "frame ends with a symmetric-memory barrier") if world > 1 else "single GPU",
                        "early_termination": args.early_termination or None,
+                       "feature_cutoff": args.feature_cutoff if args.feature_cutoff >= 0 else None,
                        "chunk": chunk, "pipeline": "chunks pipelined over 3 streams" if (args.pipeline == 2 or (args.pipeline == 1 and world > 1 and symm is not None and args.gather in ("mc", "peer"))) else "sequential"},
             "roofline": {"bound": "hbm", "kernel": "sam_kernel (feature-field gather + MLP layer 1 + weighted sum)",
                          "achieved": ach, "peak": peak, "unit": "GB/s", "frac": (ach / peak) if ach else None,
@@ -419,6 +422,10 @@ def main():
     ap.add_argument("--early-termination", type=float, default=0.0,
                     help="opt-in transmittance threshold below which a ray's last 16 nerf samples are skipped "
                          "(0 = exact, the default and the headline configuration)")
+    ap.add_argument("--feature-cutoff", type=float, default=-1.0,
+                    help="opt-in bucketed feature kernel: evaluate only the leading picked samples of a ray whose "
+                         "sharpened weight is >= this (0 = drop exact zeros, 5.96e-8 = below one fp32 ulp of the sum); "
+                         "< 0 = every sample (default and headline configuration)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-rays", type=int, default=32768,
                     help="rays of the bounded CPU-baseline sample (one reference chunk, timed twice: ~4 s of host work at "

@@ -63,6 +63,13 @@ int snrf_set_engine(snrf_ctx* ctx, int engine);
  * eps < 0.5 up to the eps-weighted tail; per-sample debug outputs of skipped samples read 0.  The reference never
  * terminates early, hence opt-in. */
 int snrf_set_early_termination(snrf_ctx* ctx, float eps);
+/* Feature samples below the precision of their own sum (opt-in; default < 0 = off, every one of the 16 picked
+ * samples of every ray is evaluated).  cutoff >= 0: rays are bucketed by the number of leading slots whose sharpened,
+ * renormalised weight (sam_model.py:244-248) is >= cutoff (> 0 when cutoff == 0) and only 2 / 4 / 8 / 16 slots of a ray
+ * are gathered and pushed through the MLP accordingly; the weights dropped per ray sum to < 16 * cutoff.  cutoff = 0 is
+ * exact up to fp32 summation order; 2^-24 drops less than one fp32 ulp of the accumulated feature.  tcgen05 engine
+ * only.  See csrc/sam_bucket.cu. */
+int snrf_set_feature_cutoff(snrf_ctx* ctx, float cutoff);
 /* eval-mode PDF sample positions u[33] = linspace(0, 1-1/33, 33) + 1/66 (ray_samplers.py:325-327).  The
  * library computes the same table itself; a host may override it so that both sides share the bits.  n = 66:
  * followed by the 33 linspace values without the offset (the base of the training-mode positions, :314-322). */

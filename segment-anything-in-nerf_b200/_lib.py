@@ -13,7 +13,7 @@ import sys
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SNRF_LIB_PATH") or os.path.join(_HERE, "libsnrf.so")
 CSRC = os.path.join(_HERE, "csrc")
-SOURCES = ["api.cu", "march.cu", "sam.cu", "gemm.cu", "query.cu", "raygen.cu", "backward.cu"]
+SOURCES = ["api.cu", "march.cu", "sam.cu", "gemm.cu", "query.cu", "raygen.cu", "backward.cu", "sam_bucket.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared",
@@ -62,6 +62,7 @@ SYMBOLS = {
     "snrf_set_pdf_u": (_I, [_P, _P, _I]),
     "snrf_set_early_termination": (_I, [_P, _F]),
     "snrf_set_jitter": (_I, [_P, _P, _L]),
+    "snrf_set_feature_cutoff": (_I, [_P, _F]),
     "snrf_upload_proposal": (_I, [_P, _P, _L, C.POINTER(GridDesc), _P]),
     "snrf_upload_field_base": (_I, [_P, _P, _L, C.POINTER(GridDesc), _P]),
     "snrf_upload_field_head": (_I, [_P, _P, _L, _P]),

@@ -66,6 +66,7 @@ struct snrf_ctx {
   int sm_count = 148;
   int engine = 1;
   float et_eps = 0.f;  // snrf_set_early_termination
+  float feat_cutoff = -1.f;  // snrf_set_feature_cutoff: < 0 = kernel B on every slot (default), >= 0 = bucketed kernel B'
   const float* jitter = nullptr;  // snrf_set_jitter: training-mode draws for the next render / sample call
   int64_t jitter_rays = 0;
   std::string err;
@@ -106,6 +107,7 @@ struct snrf_ctx {
   DevBuf sam_t[2], sam_w[2], hbar[2][2], feat_f16, hid_f16, q_feat, q_h1, q_h2, q_sel, q_x;
   DevBuf cam_rows, cam_cols, cam_o, cam_d;  // snrf_generate_rays / snrf_render_camera
   DevBuf bwd_scratch, bwd_sink;             // snrf_feature_backward
+  DevBuf bucket_lists[2], bucket_counts[2]; // bucketed feature kernel, per pipeline slot
 };
 
 namespace {
@@ -287,6 +289,7 @@ void snrf_ctx_destroy(snrf_ctx* ctx) {
   ctx->cam_rows.release(); ctx->cam_cols.release(); ctx->cam_o.release(); ctx->cam_d.release();
   ctx->conv_w_rm[0].release(); ctx->conv_w_rm[1].release();
   ctx->bwd_scratch.release(); ctx->bwd_sink.release();
+  for (int i = 0; i < 2; ++i) { ctx->bucket_lists[i].release(); ctx->bucket_counts[i].release(); }
   ctx->hbar[0][1].release(); ctx->hbar[1][0].release(); ctx->hbar[1][1].release();
   if (ctx->aux_feat) cudaStreamDestroy(ctx->aux_feat);
   if (ctx->aux_out) cudaStreamDestroy(ctx->aux_out);
@@ -314,6 +317,12 @@ int snrf_set_engine(snrf_ctx* ctx, int engine) {
 int snrf_set_early_termination(snrf_ctx* ctx, float eps) {
   if (!ctx || !(eps >= 0.f) || eps >= 0.5f) return fail(ctx, SNRF_E_INVALID, "early-termination threshold must be in [0, 0.5)");
   ctx->et_eps = eps;
+  return SNRF_OK;
+}
+
+int snrf_set_feature_cutoff(snrf_ctx* ctx, float cutoff) {
+  if (!ctx || cutoff != cutoff || cutoff > 1e-2f) return fail(ctx, SNRF_E_INVALID, "feature cut-off must be < 0 (off) or in [0, 1e-2]");
+  ctx->feat_cutoff = cutoff;
   return SNRF_OK;
 }
 
@@ -735,7 +744,34 @@ static int render_chunk(snrf_ctx* ctx, const float* origins, const float* dirs, 
     S.w1 = f.w1_core.as<__half>();
     S.hbar = hbar.as<__half>();
     S.dbg_feat = (which == 0 && dbg) ? reinterpret_cast<__half*>(dbg->sam_feat) : nullptr;
-    TIMED_LAUNCH(1, cs.feat, launch_sam(S, ctx->engine == 1, cs.small_cta, ctx->sm_count, cs.feat));
+    if (ctx->feat_cutoff >= 0.f && ctx->engine == 1 && !S.dbg_feat) {
+      // bucketed variant (sam_bucket.cu): pre-pass + one launch per bucket, all on the feature stream
+      CK(ctx->bucket_lists[slot].ensure(static_cast<size_t>(kFeatBuckets) * n_rays * sizeof(int)));
+      CK(ctx->bucket_counts[slot].ensure(kFeatBuckets * sizeof(int)));
+      SamBucketParams Bk;
+      memset(&Bk, 0, sizeof(Bk));
+      Bk.origins = origins; Bk.dirs = dirs; Bk.sam_t = M.sam_t; Bk.sam_w = M.sam_w;
+      Bk.enc[0] = f.grid[0]; Bk.enc[1] = f.grid[1];
+      Bk.w1 = f.w1_core.as<__half>();
+      Bk.hbar = hbar.as<__half>();
+      cudaEvent_t e0 = nullptr, e1 = nullptr;
+      if (ctx->timing) {
+        e0 = get_event(ctx); e1 = get_event(ctx);
+        cudaEventRecord(e0, cs.feat);
+      }
+      LAUNCH(launch_bucket_assign(M.sam_w, ctx->feat_cutoff, ctx->bucket_counts[slot].as<int>(),
+                                  ctx->bucket_lists[slot].as<int>(), n_rays, cs.feat));
+      int64_t launched = 0;
+      CK(launch_sam_bucketed(Bk, ctx->bucket_counts[slot].as<int>(), ctx->bucket_lists[slot].as<int>(), n_rays,
+                             ctx->sm_count, cs.feat, &launched));
+      ctx->launches += launched;
+      if (ctx->timing) {
+        cudaEventRecord(e1, cs.feat);
+        ctx->ev_used.push_back({1, {e0, e1}});
+      }
+    } else {
+      TIMED_LAUNCH(1, cs.feat, launch_sam(S, ctx->engine == 1, cs.small_cta, ctx->sm_count, cs.feat));
+    }
     if (cs.out != cs.feat) {
       CK(cudaEventRecord(ctx->ev_feat[slot][which], cs.feat));
       CK(cudaStreamWaitEvent(cs.out, ctx->ev_feat[slot][which], 0));

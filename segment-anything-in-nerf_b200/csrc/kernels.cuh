@@ -85,6 +85,40 @@ struct SamParams {
 };
 cudaError_t launch_sam(const SamParams& P, bool tcgen05, bool small_cta, int sm_count, cudaStream_t stream);
 
+// ---- kernel B': kernel B over rays bucketed by their number of significant slots (sam_bucket.cu) ---------
+constexpr int kFeatBuckets = 4;  // rays with <= 2, <= 4, <= 8, <= 16 significant slots
+struct SamBucketParams {
+  const float* origins;
+  const float* dirs;
+  const float* sam_t;  // [N,16]
+  const float* sam_w;  // [N,16] descending per ray (march.cu stores slot = rank)
+  GridDev enc[2];
+  const __half* w1;    // core-matrix layout, as SamParams
+  __half* hbar;        // [N,256]
+  const int* list;     // ray indices of this bucket
+  const int* count;    // number of entries in `list` (device memory, written by the pre-pass)
+};
+// Pre-pass, one thread per ray: significant slots = 1 + index of the last slot whose weight is not below the
+// cut-off (NaN weights - 0/0 rays, sam_model.py:248 - count as significant, so such a ray keeps all 16 slots and
+// yields the same NaN row as kernel B); cut-off 0 keeps every non-zero weight.  lists: [kFeatBuckets][n].
+SNRF_HD void bucket_assign_one(const float* sam_w, float eps, int* counts, int* lists, int64_t n, int64_t ray) {
+  int k = 0;
+  for (int s = 0; s < 16; ++s) {
+    const float w = sam_w[ray * 16 + s];
+    if (!(w < eps) && w != 0.f) k = s + 1;
+  }
+  const int b = k <= 2 ? 0 : k <= 4 ? 1 : k <= 8 ? 2 : 3;
+#ifdef __CUDA_ARCH__
+  const int pos = atomicAdd(counts + b, 1);
+#else
+  const int pos = counts[b]++;
+#endif
+  lists[static_cast<int64_t>(b) * n + pos] = static_cast<int>(ray);
+}
+cudaError_t launch_bucket_assign(const float* sam_w, float eps, int* counts, int* lists, int64_t n, cudaStream_t stream);
+cudaError_t launch_sam_bucketed(const SamBucketParams& P, const int* counts, const int* lists, int64_t n_rays, int sm_count,
+                                cudaStream_t stream, int64_t* launches);
+
 // ---- kernel C/D: tap GEMM  out = act(sum_t A_t[M,256] x W_t[N,256]^T + bias) ----------------------
 struct GemmParams {
   const __half* a;     // [M,256] fp16 rows

@@ -1,0 +1,273 @@
+// Kernel B' - kernel B (sam.cu) over rays bucketed by how many of their k = 16 picked samples still carry weight.
+//
+// The MeanRenderer weights are sharpened with w^10 and renormalised (samnerf/sam_model.py:244-248), so most of a ray's
+// 16 slots end up far below the unit roundoff of the fp32 sum they are accumulated into: on the 800x800 scene-like
+// frame 60 % of the rays have at most 2 slots with w >= 2^-24, 28 % at most 4, 12 % at most 8, 0.4 % more (oracle
+// count; the slots are stored in descending weight order, so the significant ones are a prefix).  Kernel B spends the
+// same 24 levels x 8 corners x 16 B of gathers and the same 128-row tensor-core tile on every slot.  Here a pre-pass
+// sorts the rays into four buckets by their significant-slot count (<= 2, <= 4, <= 8, 16) and one launch per bucket
+// runs tiles of 128 / SLOTS rays x SLOTS slots: same gather code, same tcgen05 tile, a log2(SLOTS)-step row
+// reduction in the epilogue.  Every slot below SLOTS is evaluated with its real weight; only slots >= SLOTS - all
+// of them below the cut-off - are dropped.  cut-off 0 drops exact zeros only (bit-for-bit the same sum up to fp32
+// summation order); the default 2^-24 drops at most 1.2e-7 of total weight per ray (measured), i.e. less than one
+// fp32 ulp of the accumulated sum, which is then rounded to fp16 anyway.  Rays whose weights are NaN (0/0,
+// sam_model.py:248) count as fully significant and produce the same NaN row as kernel B.
+//
+// NOT YET RUN ON HARDWARE (written after the round-1 GPU budget was spent): opt-in through snrf_set_feature_cutoff;
+// kernel B stays the default path.  The gather, MMA issue, TMEM epilogue and barrier protocol are copied from the
+// GPU-verified kernel B; what is new is the row -> (ray, slot) mapping through the bucket list, the per-lane ray
+// loads, and the generalised reduction width.
+#include "kernels.cuh"
+
+namespace snrf {
+namespace {
+
+constexpr int kK = 16;      // slots per ray in sam_t / sam_w
+constexpr int kIn = 192;    // encoder width
+constexpr int kHid = 256;   // hidden width
+constexpr uint32_t kSBO = kIn * 16;
+constexpr uint32_t kW1Bytes = kHid * kIn * 2;    // 98304
+constexpr uint32_t kATileBytes = 128 * kIn * 2;  // 49152
+constexpr uint32_t kSmemBytes = kW1Bytes + 2 * kATileBytes + 2 * 128 * 4 + 64;
+constexpr int kThreads = 512;
+
+// 12 levels x 4 (y,z) corners x 16 B for the sample this lane pair owns (identical to sam.cu's gather_f8)
+template <uint32_t MASK>
+__device__ __forceinline__ void gather_f8(const GridDev& G, int k0, float x, float y, float z, int xb, int row,
+                                          unsigned char* a_tile) {
+  const unsigned FULL = 0xffffffffu;
+#pragma unroll
+  for (int l = 0; l < 12; ++l) {
+    const GridLevel& L = G.lv[l];
+    const float qx = __fadd_rn(__fmul_rn(x, L.scale), 0.5f);
+    const float qy = __fadd_rn(__fmul_rn(y, L.scale), 0.5f);
+    const float qz = __fadd_rn(__fmul_rn(z, L.scale), 0.5f);
+    const float fx = floorf(qx), fy = floorf(qy), fz = floorf(qz);
+    const float rx = qx - fx, ry = qy - fy, rz = qz - fz;
+    const uint32_t gx = static_cast<uint32_t>(static_cast<int>(fx)) + xb;
+    const uint32_t gy = static_cast<uint32_t>(static_cast<int>(fy));
+    const uint32_t gz = static_cast<uint32_t>(static_cast<int>(fz));
+    const float wx = xb ? rx : 1.f - rx;
+    uint32_t idx[4];
+    uint4 v[4];
+    corner_indices(L, level_hashed<MASK>(L, l), gx, gy, gz, idx);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) v[c] = ldg_u128(G.table + 8 * static_cast<size_t>(idx[c]));
+    float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      float w = wx * ((c & 1) ? ry : 1.f - ry);
+      w *= ((c >> 1) ? rz : 1.f - rz);
+      const float2 f0 = h2_to_f2(v[c].x), f1 = h2_to_f2(v[c].y), f2 = h2_to_f2(v[c].z), f3 = h2_to_f2(v[c].w);
+      a[0] += w * f0.x; a[1] += w * f0.y; a[2] += w * f1.x; a[3] += w * f1.y;
+      a[4] += w * f2.x; a[5] += w * f2.y; a[6] += w * f3.x; a[7] += w * f3.y;
+    }
+    float o[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float send = xb ? a[i] : a[i + 4];
+      const float mine = xb ? a[i + 4] : a[i];
+      o[i] = mine + __shfl_xor_sync(FULL, send, 1);
+    }
+    const uint2 pk = make_uint2(f2_to_h2(o[0], o[1]), f2_to_h2(o[2], o[3]));
+    *reinterpret_cast<uint2*>(a_tile + core_offset(row, k0 + l * 8 + xb * 4, kIn)) = pk;
+  }
+}
+
+// Sum v[0..31] over groups of 2^LOG consecutive lanes; on return v[0 .. (32 >> LOG)) hold the sums of columns
+// base .. base + (32 >> LOG), base = sum over steps of (lane bit `step` ? 16 >> step : 0).  LOG = 4 is sam.cu's
+// halving_reduce16.
+template <int LOG>
+__device__ __forceinline__ int halving_reduce(float (&v)[32], int lane) {
+  const unsigned FULL = 0xffffffffu;
+  int base = 0;
+#pragma unroll
+  for (int step = 0; step < LOG; ++step) {
+    const int half = 16 >> step;
+    const bool up = (lane >> step) & 1;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      const float send = up ? v[i] : v[i + half];
+      const float keep = up ? v[i + half] : v[i];
+      v[i] = keep + __shfl_xor_sync(FULL, send, 1 << step);
+    }
+    base += up ? half : 0;
+  }
+  return base;
+}
+
+template <int SLOTS>
+struct Log2;
+template <> struct Log2<2> { static constexpr int v = 1; };
+template <> struct Log2<4> { static constexpr int v = 2; };
+template <> struct Log2<8> { static constexpr int v = 3; };
+template <> struct Log2<16> { static constexpr int v = 4; };
+
+template <uint32_t M0, uint32_t M1, int SLOTS>
+__global__ void __launch_bounds__(kThreads, 1) sam_bucket_kernel(const SamBucketParams P) {
+  constexpr int kRPT = 128 / SLOTS;  // rays per 128-row tile
+  constexpr int LOG = Log2<SLOTS>::v;
+  constexpr int kKeep = 32 >> LOG;   // columns a lane holds after the row reduction
+  extern __shared__ __align__(128) unsigned char smem[];
+  unsigned char* s_w1 = smem;
+  unsigned char* s_a = smem + kW1Bytes;
+  float* s_sw = reinterpret_cast<float*>(smem + kW1Bytes + 2 * kATileBytes);  // [2][128]
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_sw + 256);                // [2]
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 2);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  for (uint32_t i = tid; i < kW1Bytes / 16; i += kThreads)
+    reinterpret_cast<uint4*>(s_w1)[i] = ldg_u128(reinterpret_cast<const uint4*>(P.w1) + i);
+  if (tid == 0) {
+    mbar_init(smem_u32(&s_bar[0]), 1);
+    mbar_init(smem_u32(&s_bar[1]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc(smem_u32(s_tmem), 512);
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+
+  const int n_list = *P.count;  // rays in this bucket (written by the pre-pass on the same stream)
+  const int64_t n_tiles = (static_cast<int64_t>(n_list) + kRPT - 1) / kRPT;
+  const int g = warp & 7, e = warp >> 3;
+  const int s16 = lane >> 1, xb = lane & 1;
+  const int row = g * 16 + s16;           // tile row this lane pair gathers
+  const int r_loc = row / SLOTS, slot = row % SLOTS;
+
+  // ---- epilogue of one tile out of TMEM --------------------------------------------------------
+  auto epilogue = [&](int64_t tile, int buf, uint32_t parity) {
+    mbar_wait(smem_u32(&s_bar[buf]), parity);
+    tc_fence_after();
+    const int quarter = warp & 3, cq = warp >> 2;
+    const int erow = quarter * 32 + lane;
+    const float wgt = s_sw[buf * 128 + erow];
+    const int64_t li = tile * kRPT + erow / SLOTS;
+    const bool valid = li < n_list;
+    const int64_t ray = valid ? P.list[li] : 0;
+#pragma unroll 1
+    for (int chunk = 0; chunk < 2; ++chunk) {
+      float v[32];
+      const int col0 = cq * 64 + chunk * 32;
+      tmem_ld32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * 256 + col0, v);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = round_f16(fmaxf(v[i], 0.f)) * wgt;
+      const int base = halving_reduce<LOG>(v, lane);
+      if (valid) {
+        __half* dst = P.hbar + ray * kHid + col0 + base;
+#pragma unroll
+        for (int i = 0; i < kKeep; i += 2) *reinterpret_cast<uint32_t*>(dst + i) = f2_to_h2(v[i], v[i + 1]);
+      }
+    }
+    tc_fence_before();
+  };
+
+  int64_t prev_tile = -1;
+  int it = 0;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+    const int buf = it & 1;
+    unsigned char* a_tile = s_a + buf * kATileBytes;
+    const int64_t li = tile * kRPT + r_loc;
+    const bool valid = li < n_list;
+    // rows past the end of the list recompute the last ray with weight 0 (their results are never stored), so that
+    // every lane of the warp runs the same gather and its full-mask shuffles
+    const int64_t ray = P.list[valid ? li : n_list - 1];
+    const float tm2 = P.sam_t[ray * kK + slot];
+    if (e == 0 && xb == 0) s_sw[buf * 128 + row] = valid ? P.sam_w[ray * kK + slot] : 0.f;
+    const float px = __fadd_rn(P.origins[3 * ray + 0], __fmul_rn(P.dirs[3 * ray + 0], tm2) / 2.f);
+    const float py = __fadd_rn(P.origins[3 * ray + 1], __fmul_rn(P.dirs[3 * ray + 1], tm2) / 2.f);
+    const float pz = __fadd_rn(P.origins[3 * ray + 2], __fmul_rn(P.dirs[3 * ray + 2], tm2) / 2.f);
+    float x, y, z, sel;
+    contract_normalize(px, py, pz, false, false, x, y, z, sel);
+    if (e == 0)
+      gather_f8<M0>(P.enc[0], 0, x, y, z, xb, row, a_tile);
+    else
+      gather_f8<M1>(P.enc[1], 96, x, y, z, xb, row, a_tile);
+    fence_async_smem();
+    __syncthreads();
+
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t a_addr = smem_u32(a_tile), b_addr = smem_u32(s_w1);
+      const uint32_t idesc = umma_idesc_f16(128, 256);
+#pragma unroll
+      for (int ks = 0; ks < kIn / 16; ++ks) {
+        umma_f16(tmem_base + buf * 256, umma_desc(a_addr + ks * 256, 128, kSBO), umma_desc(b_addr + ks * 256, 128, kSBO),
+                 idesc, ks > 0 ? 1u : 0u);
+      }
+      umma_commit(smem_u32(&s_bar[buf]));
+    }
+    __syncwarp();
+    if (it > 0) epilogue(prev_tile, buf ^ 1, static_cast<uint32_t>(((it - 1) >> 1) & 1));
+    prev_tile = tile;
+  }
+  if (it > 0) epilogue(prev_tile, (it - 1) & 1, static_cast<uint32_t>(((it - 1) >> 1) & 1));
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
+__global__ void bucket_assign_kernel(const float* sam_w, float eps, int* counts, int* lists, int64_t n) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) bucket_assign_one(sam_w, eps, counts, lists, n, i);
+}
+
+constexpr uint32_t kEnc0MaskStd = 0xE00u, kEnc1MaskStd = 0xFFFu;  // as in sam.cu
+
+template <uint32_t M0, uint32_t M1, int SLOTS>
+cudaError_t launch_one(const SamBucketParams& P, int grid, cudaStream_t stream) {
+  static bool configured_dev[64] = {false};
+  int dev_id = 0;
+  if (cudaGetDevice(&dev_id) != cudaSuccess || dev_id < 0 || dev_id >= 64) return cudaErrorInvalidDevice;
+  auto* k = sam_bucket_kernel<M0, M1, SLOTS>;
+  if (!configured_dev[dev_id]) {
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    if (e != cudaSuccess) return e;
+    configured_dev[dev_id] = true;
+  }
+  k<<<grid, kThreads, kSmemBytes, stream>>>(P);
+  return cudaGetLastError();
+}
+
+template <int SLOTS>
+cudaError_t launch_slots(const SamBucketParams& P, bool std_cfg, int grid, cudaStream_t stream) {
+  return std_cfg ? launch_one<kEnc0MaskStd, kEnc1MaskStd, SLOTS>(P, grid, stream)
+                 : launch_one<kRuntimeMask, kRuntimeMask, SLOTS>(P, grid, stream);
+}
+
+}  // namespace
+
+cudaError_t launch_bucket_assign(const float* sam_w, float eps, int* counts, int* lists, int64_t n, cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  cudaError_t e = cudaMemsetAsync(counts, 0, kFeatBuckets * sizeof(int), stream);
+  if (e != cudaSuccess) return e;
+  bucket_assign_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(sam_w, eps, counts, lists, n);
+  return cudaGetLastError();
+}
+
+// One launch per bucket; the bucket sizes stay on the device (each kernel reads its own count), so the grid is sized
+// for the worst case (every ray in this bucket) and surplus CTAs exit after the prologue.
+cudaError_t launch_sam_bucketed(const SamBucketParams& P0, const int* counts, const int* lists, int64_t n_rays, int sm_count,
+                                cudaStream_t stream, int64_t* launches) {
+  if (n_rays <= 0) return cudaSuccess;
+  const bool std_cfg = hashed_mask(P0.enc[0]) == kEnc0MaskStd && hashed_mask(P0.enc[1]) == kEnc1MaskStd;
+  for (int b = 0; b < kFeatBuckets; ++b) {
+    SamBucketParams P = P0;
+    P.list = lists + static_cast<int64_t>(b) * n_rays;
+    P.count = counts + b;
+    const int slots = 2 << b;  // 2, 4, 8, 16
+    const int64_t tiles = (n_rays + (128 / slots) - 1) / (128 / slots);
+    const int grid = static_cast<int>(tiles < sm_count ? tiles : sm_count);
+    cudaError_t e = b == 0 ? launch_slots<2>(P, std_cfg, grid, stream)
+                  : b == 1 ? launch_slots<4>(P, std_cfg, grid, stream)
+                  : b == 2 ? launch_slots<8>(P, std_cfg, grid, stream)
+                           : launch_slots<16>(P, std_cfg, grid, stream);
+    if (e != cudaSuccess) return e;
+    if (launches) *launches += 1;
+  }
+  return cudaSuccess;
+}
+
+}  // namespace snrf

@@ -7,6 +7,7 @@
 // Built by tests/emu/build_emu.py with nvcc (host code only; no CUDA call is ever made).
 #include "../../segment-anything-in-nerf_b200/csrc/raygen.cuh"
 #include "../../segment-anything-in-nerf_b200/csrc/backward.cuh"
+#include "../../segment-anything-in-nerf_b200/csrc/kernels.cuh"
 
 #include <string.h>
 
@@ -107,6 +108,13 @@ int emu_feature_backward(const float* origins, const float* dirs, const float* s
   HostExec ex;
   feat_backward_chain(P, ex);
   if (hbar_out) for (int64_t i = 0; i < n * kBwdHid; ++i) hbar_out[i] = hbar[i];
+  return 0;
+}
+
+// pre-pass of the bucketed feature kernel (sam_bucket.cu): counts[4], lists[4][n]
+int emu_bucket_assign(const float* sam_w, float eps, long long n, int* counts, int* lists) {
+  for (int b = 0; b < kFeatBuckets; ++b) counts[b] = 0;
+  for (int64_t r = 0; r < n; ++r) bucket_assign_one(sam_w, eps, counts, lists, n, r);
   return 0;
 }
 

@@ -164,3 +164,32 @@ def test_early_termination_stays_within_its_bounds(full):
     assert torch.equal(again["rgb"], exact["rgb"]) and torch.equal(again["sam"], exact["sam"])
     with pytest.raises(RuntimeError, match="threshold"):
         r.set_early_termination(0.7)
+
+
+@pytest.mark.hw_unverified
+@pytest.mark.parametrize("cutoff,rel", [(0.0, 1e-5), (2.0 ** -24, 1e-4)])
+def test_bucketed_feature_kernel_matches_kernel_b(full, cutoff, rel):
+    """snrf_set_feature_cutoff: rays bucketed by their significant-slot count give the same feature rows as the
+    kernel that evaluates all 16 slots - up to fp32 summation order (cut-off 0) / one fp32 ulp of the sum (2^-24)."""
+    cfg, r = full
+    o, d = test_rays(9000, seed=14)
+    o, d = o.cuda(), d.cuda()
+    exact = r.render(o, d, get_feature=("sam",))
+    r.set_feature_cutoff(cutoff)
+    try:
+        got = r.render(o, d, get_feature=("sam",))
+        part = r.render(o[:1003], d[:1003], get_feature=("sam",))  # ragged: partial tiles in every bucket
+        torch.cuda.synchronize()
+    finally:
+        r.set_feature_cutoff(-1.0)
+    for k in ("rgb", "depth", "accumulation"):
+        assert torch.equal(got[k], exact[k]), k
+    a, b = got["sam"], exact["sam"]
+    assert torch.equal(torch.isnan(a), torch.isnan(b))
+    ok = torch.isfinite(b).all(-1)
+    err = (a[ok] - b[ok]).abs().max(-1).values / b[ok].abs().max(-1).values.clamp_min(1e-6)
+    assert float(err.max()) <= max(rel, 2.0 ** -10), float(err.max())  # hbar is stored in fp16: one flip is 2^-11
+    assert float((err <= rel).float().mean()) > 0.99
+    assert torch.equal(part["sam"], got["sam"][:1003])
+    again = r.render(o, d, get_feature=("sam",))
+    assert torch.equal(again["sam"], exact["sam"])

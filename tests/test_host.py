@@ -88,3 +88,40 @@ def test_scene_regime_is_scene_like():
     assert float(out["accumulation"].median()) > 0.99
     assert float((out["_sam_weights"] > 1e-3).float().sum(-1).mean()) < 4.0       # sharpened weights concentrate
     assert not torch.isnan(out["sam"]).any()
+
+
+def test_bucket_prepass_body():
+    """Pre-pass of the bucketed feature kernel (csrc/sam_bucket.cu): every ray lands in exactly one bucket, the
+    bucket covers all of its significant slots, NaN rays keep all 16."""
+    import ctypes as C
+
+    import numpy as np
+
+    from emu.build_emu import load
+
+    n = 5000
+    g = torch.Generator().manual_seed(0)
+    w = torch.rand(n, 16, generator=g) ** 12  # a few large, many tiny
+    w, _ = (w / w.sum(-1, keepdim=True)).sort(dim=-1, descending=True)
+    w[torch.rand(n, 16, generator=g) < 0.2] = 0.0
+    w, _ = w.sort(dim=-1, descending=True)
+    w[7] = float("nan")
+    arr = np.ascontiguousarray(w.numpy(), np.float32)
+    for eps in (0.0, 2.0 ** -24, 1e-4):
+        counts = np.zeros(4, np.int32)
+        lists = np.full((4, n), -1, np.int32)
+        load().emu_bucket_assign(arr.ctypes.data_as(C.c_void_p), C.c_float(eps), C.c_longlong(n),
+                                 counts.ctypes.data_as(C.c_void_p), lists.ctypes.data_as(C.c_void_p))
+        assert counts.sum() == n
+        seen = np.concatenate([lists[b, :counts[b]] for b in range(4)])
+        assert np.array_equal(np.sort(seen), np.arange(n))
+        sig = (~(w < eps)) & (w != 0)
+        k = torch.where(sig.any(-1), 16 - sig.flip(-1).float().argmax(-1), torch.zeros(n, dtype=torch.long)).numpy()
+        for b, slots in enumerate((2, 4, 8, 16)):
+            rays = lists[b, :counts[b]]
+            assert (k[rays] <= slots).all() and (b == 0 or (k[rays] > slots // 2).all())
+            # what is dropped is below the cut-off
+            if slots < 16 and len(rays):
+                dropped = torch.nan_to_num(w[torch.from_numpy(rays).long(), slots:]).sum(-1)
+                assert float(dropped.max()) <= 16 * eps
+        assert 7 in lists[3, :counts[3]]
