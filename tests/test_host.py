@@ -125,3 +125,70 @@ def test_bucket_prepass_body():
                 dropped = torch.nan_to_num(w[torch.from_numpy(rays).long(), slots:]).sum(-1)
                 assert float(dropped.max()) <= 16 * eps
         assert 7 in lists[3, :counts[3]]
+
+
+@pytest.mark.parametrize("slots", [2, 4, 8, 16])
+def test_bucket_kernel_index_arithmetic_model(slots):
+    """A Python model of the warp-level index arithmetic of sam_bucket_kernel<SLOTS> (it cannot be emulated like the
+    per-thread kernels): tile row -> (list entry, slot) in the gather, TMEM row -> lane in the epilogue, the
+    log2(SLOTS)-step halving reduction with its column base, and the store - every (ray, column) of hbar must be
+    written exactly once with sum_slot w * h.  The shuffles are modelled as lane permutations of numpy arrays."""
+    import numpy as np
+
+    rng = np.random.default_rng(slots)
+    rpt, log = 128 // slots, {2: 1, 4: 2, 8: 3, 16: 4}[slots]
+    n_list = 2 * rpt + 5  # two full tiles and a ragged one
+    list_ = rng.permutation(1000)[:n_list]
+    h = rng.standard_normal((1000, 16, 256)).astype(np.float32)   # stands for relu(W1 x) of (ray, slot)
+    w = rng.random((1000, 16)).astype(np.float32)
+    hbar = np.full((1000, 256), np.nan, np.float32)
+    writes = np.zeros((1000, 256), np.int32)
+    n_tiles = (n_list + rpt - 1) // rpt
+    for tile in range(n_tiles):
+        # gather side: 16 warps, lane pairs own rows
+        acc = np.zeros((128, 256), np.float32)
+        s_sw = np.zeros(128, np.float32)
+        for warp in range(8):  # e = 0 warps write the weights; both encodings write disjoint A columns
+            for lane in range(32):
+                row = (warp & 7) * 16 + (lane >> 1)
+                r_loc, slot = row // slots, row % slots
+                li = tile * rpt + r_loc
+                valid = li < n_list
+                ray = list_[li if valid else n_list - 1]
+                s_sw[row] = w[ray, slot] if valid else 0.0
+                acc[row] = h[ray, slot]
+        # epilogue side
+        for warp in range(16):
+            quarter, cq = warp & 3, warp >> 2
+            for chunk in range(2):
+                col0 = cq * 64 + chunk * 32
+                v = np.zeros((32, 32), np.float32)  # [lane][i]
+                for lane in range(32):
+                    erow = quarter * 32 + lane
+                    v[lane] = acc[erow, col0:col0 + 32] * s_sw[erow]
+                base = np.zeros(32, np.int32)
+                for step in range(log):
+                    half = 16 >> step
+                    nv = v.copy()
+                    for lane in range(32):
+                        up = (lane >> step) & 1
+                        peer = lane ^ (1 << step)
+                        peer_up = (peer >> step) & 1
+                        for i in range(half):
+                            keep = v[lane, i + half] if up else v[lane, i]
+                            recv = v[peer, i] if peer_up else v[peer, i + half]  # what the peer sends
+                            nv[lane, i] = keep + recv
+                        base[lane] += half if up else 0
+                    v = nv
+                keep_n = 32 >> log
+                for lane in range(32):
+                    erow = quarter * 32 + lane
+                    li = tile * rpt + erow // slots
+                    if li < n_list:
+                        ray = list_[li]
+                        c = col0 + base[lane]
+                        hbar[ray, c:c + keep_n] = v[lane, :keep_n]
+                        writes[ray, c:c + keep_n] += 1
+    want = (w[list_, :slots, None] * h[list_, :slots]).sum(1)
+    assert (writes[list_] == 1).all() and writes.sum() == n_list * 256
+    np.testing.assert_allclose(hbar[list_], want, rtol=1e-5, atol=1e-5)
