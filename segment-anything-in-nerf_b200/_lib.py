@@ -16,7 +16,7 @@ CSRC = os.path.join(_HERE, "csrc")
 SOURCES = ["api.cu", "march.cu", "sam.cu", "gemm.cu", "query.cu", "raygen.cu", "backward.cu", "sam_bucket.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC", "-shared", "--threads", "0",  # one compile job per source file
 ]
 
 SNRF_MAX_LEVELS = 16
