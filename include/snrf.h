@@ -65,7 +65,7 @@ int snrf_set_engine(snrf_ctx* ctx, int engine);
 int snrf_set_early_termination(snrf_ctx* ctx, float eps);
 /* Feature samples below the precision of their own sum (opt-in; default < 0 = off, every one of the 16 picked
  * samples of every ray is evaluated).  cutoff >= 0: rays are bucketed by the number of leading slots whose sharpened,
- * renormalised weight (sam_model.py:244-248) is >= cutoff (> 0 when cutoff == 0) and only 2 / 4 / 8 / 16 slots of a ray
+ * renormalised weight (sam_model.py:244-248) is >= cutoff (> 0 when cutoff == 0) and only 1 / 2 / 4 / 8 / 16 slots of a ray
  * are gathered and pushed through the MLP accordingly; the weights dropped per ray sum to < 16 * cutoff.  cutoff = 0 is
  * exact up to fp32 summation order; 2^-24 drops less than one fp32 ulp of the accumulated feature.  tcgen05 engine
  * only.  See csrc/sam_bucket.cu. */

@@ -86,7 +86,7 @@ struct SamParams {
 cudaError_t launch_sam(const SamParams& P, bool tcgen05, bool small_cta, int sm_count, cudaStream_t stream);
 
 // ---- kernel B': kernel B over rays bucketed by their number of significant slots (sam_bucket.cu) ---------
-constexpr int kFeatBuckets = 4;  // rays with <= 2, <= 4, <= 8, <= 16 significant slots
+constexpr int kFeatBuckets = 5;  // rays with <= 1, <= 2, <= 4, <= 8, <= 16 significant slots (SLOTS = 1 << bucket)
 struct SamBucketParams {
   const float* origins;
   const float* dirs;
@@ -107,7 +107,7 @@ SNRF_HD void bucket_assign_one(const float* sam_w, float eps, int* counts, int* 
     const float w = sam_w[ray * 16 + s];
     if (!(w < eps) && w != 0.f) k = s + 1;
   }
-  const int b = k <= 2 ? 0 : k <= 4 ? 1 : k <= 8 ? 2 : 3;
+  const int b = k <= 1 ? 0 : k <= 2 ? 1 : k <= 4 ? 2 : k <= 8 ? 3 : 4;
 #ifdef __CUDA_ARCH__
   const int pos = atomicAdd(counts + b, 1);
 #else

@@ -2,10 +2,10 @@
 //
 // The MeanRenderer weights are sharpened with w^10 and renormalised (samnerf/sam_model.py:244-248), so most of a ray's
 // 16 slots end up far below the unit roundoff of the fp32 sum they are accumulated into: on the 800x800 scene-like
-// frame 60 % of the rays have at most 2 slots with w >= 2^-24, 28 % at most 4, 12 % at most 8, 0.4 % more (oracle
+// frame 35 % of the rays have 1 slot with w >= 2^-24, 25 % have 2, 28 % at most 4, 12 % at most 8, 0.4 % more (oracle
 // count; the slots are stored in descending weight order, so the significant ones are a prefix).  Kernel B spends the
 // same 24 levels x 8 corners x 16 B of gathers and the same 128-row tensor-core tile on every slot.  Here a pre-pass
-// sorts the rays into four buckets by their significant-slot count (<= 2, <= 4, <= 8, 16) and one launch per bucket
+// sorts the rays into five buckets by their significant-slot count (<= 1, <= 2, <= 4, <= 8, 16) and one launch per bucket
 // runs tiles of 128 / SLOTS rays x SLOTS slots: same gather code, same tcgen05 tile, a log2(SLOTS)-step row
 // reduction in the epilogue.  Every slot below SLOTS is evaluated with its real weight; only slots >= SLOTS - all
 // of them below the cut-off - are dropped.  cut-off 0 drops exact zeros only (bit-for-bit the same sum up to fp32
@@ -98,6 +98,7 @@ __device__ __forceinline__ int halving_reduce(float (&v)[32], int lane) {
 
 template <int SLOTS>
 struct Log2;
+template <> struct Log2<1> { static constexpr int v = 0; };
 template <> struct Log2<2> { static constexpr int v = 1; };
 template <> struct Log2<4> { static constexpr int v = 2; };
 template <> struct Log2<8> { static constexpr int v = 3; };
@@ -257,12 +258,13 @@ cudaError_t launch_sam_bucketed(const SamBucketParams& P0, const int* counts, co
     SamBucketParams P = P0;
     P.list = lists + static_cast<int64_t>(b) * n_rays;
     P.count = counts + b;
-    const int slots = 2 << b;  // 2, 4, 8, 16
+    const int slots = 1 << b;  // 1, 2, 4, 8, 16
     const int64_t tiles = (n_rays + (128 / slots) - 1) / (128 / slots);
     const int grid = static_cast<int>(tiles < sm_count ? tiles : sm_count);
-    cudaError_t e = b == 0 ? launch_slots<2>(P, std_cfg, grid, stream)
-                  : b == 1 ? launch_slots<4>(P, std_cfg, grid, stream)
-                  : b == 2 ? launch_slots<8>(P, std_cfg, grid, stream)
+    cudaError_t e = b == 0 ? launch_slots<1>(P, std_cfg, grid, stream)
+                  : b == 1 ? launch_slots<2>(P, std_cfg, grid, stream)
+                  : b == 2 ? launch_slots<4>(P, std_cfg, grid, stream)
+                  : b == 3 ? launch_slots<8>(P, std_cfg, grid, stream)
                            : launch_slots<16>(P, std_cfg, grid, stream);
     if (e != cudaSuccess) return e;
     if (launches) *launches += 1;

@@ -108,26 +108,26 @@ def test_bucket_prepass_body():
     w[7] = float("nan")
     arr = np.ascontiguousarray(w.numpy(), np.float32)
     for eps in (0.0, 2.0 ** -24, 1e-4):
-        counts = np.zeros(4, np.int32)
-        lists = np.full((4, n), -1, np.int32)
+        counts = np.zeros(5, np.int32)
+        lists = np.full((5, n), -1, np.int32)
         load().emu_bucket_assign(arr.ctypes.data_as(C.c_void_p), C.c_float(eps), C.c_longlong(n),
                                  counts.ctypes.data_as(C.c_void_p), lists.ctypes.data_as(C.c_void_p))
         assert counts.sum() == n
-        seen = np.concatenate([lists[b, :counts[b]] for b in range(4)])
+        seen = np.concatenate([lists[b, :counts[b]] for b in range(5)])
         assert np.array_equal(np.sort(seen), np.arange(n))
         sig = (~(w < eps)) & (w != 0)
         k = torch.where(sig.any(-1), 16 - sig.flip(-1).float().argmax(-1), torch.zeros(n, dtype=torch.long)).numpy()
-        for b, slots in enumerate((2, 4, 8, 16)):
+        for b, slots in enumerate((1, 2, 4, 8, 16)):
             rays = lists[b, :counts[b]]
             assert (k[rays] <= slots).all() and (b == 0 or (k[rays] > slots // 2).all())
             # what is dropped is below the cut-off
             if slots < 16 and len(rays):
                 dropped = torch.nan_to_num(w[torch.from_numpy(rays).long(), slots:]).sum(-1)
                 assert float(dropped.max()) <= 16 * eps
-        assert 7 in lists[3, :counts[3]]
+        assert 7 in lists[4, :counts[4]]
 
 
-@pytest.mark.parametrize("slots", [2, 4, 8, 16])
+@pytest.mark.parametrize("slots", [1, 2, 4, 8, 16])
 def test_bucket_kernel_index_arithmetic_model(slots):
     """A Python model of the warp-level index arithmetic of sam_bucket_kernel<SLOTS> (it cannot be emulated like the
     per-thread kernels): tile row -> (list entry, slot) in the gather, TMEM row -> lane in the epilogue, the
@@ -136,7 +136,7 @@ def test_bucket_kernel_index_arithmetic_model(slots):
     import numpy as np
 
     rng = np.random.default_rng(slots)
-    rpt, log = 128 // slots, {2: 1, 4: 2, 8: 3, 16: 4}[slots]
+    rpt, log = 128 // slots, {1: 0, 2: 1, 4: 2, 8: 3, 16: 4}[slots]
     n_list = 2 * rpt + 5  # two full tiles and a ragged one
     list_ = rng.permutation(1000)[:n_list]
     h = rng.standard_normal((1000, 16, 256)).astype(np.float32)   # stands for relu(W1 x) of (ray, slot)
