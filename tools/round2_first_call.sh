@@ -10,4 +10,5 @@ echo "== bench (exact)"; timeout 400 python bench.py > gpurun_out/r2_bench.json 
 echo "== bench (early termination 1e-4)"; timeout 300 python bench.py --early-termination 1e-4 --no-cpu-baseline > gpurun_out/r2_bench_et.json 2>> gpurun_out/r2_bench.err; tail -c 400 gpurun_out/r2_bench_et.json
 echo "== bench (bucketed feature kernel, cut-off 2^-24)"; timeout 300 python bench.py --feature-cutoff 5.96e-8 --no-cpu-baseline > gpurun_out/r2_bench_bucket.json 2>> gpurun_out/r2_bench.err; tail -c 400 gpurun_out/r2_bench_bucket.json
 echo "== bench (bucketed feature kernel, exact zeros only)"; timeout 300 python bench.py --feature-cutoff 0 --no-cpu-baseline > gpurun_out/r2_bench_bucket0.json 2>> gpurun_out/r2_bench.err; tail -c 400 gpurun_out/r2_bench_bucket0.json
+echo "== camera in front"; timeout 200 python tools/bench_camera.py > gpurun_out/r2_camera.json 2> gpurun_out/r2_camera.err; cat gpurun_out/r2_camera.json; tail -3 gpurun_out/r2_camera.err
 echo "== training step"; timeout 300 python tools/bench_train.py > gpurun_out/r2_train.json 2> gpurun_out/r2_train.err; cat gpurun_out/r2_train.json; tail -3 gpurun_out/r2_train.err
