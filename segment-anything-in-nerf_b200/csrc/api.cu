@@ -761,10 +761,10 @@ static int render_chunk(snrf_ctx* ctx, const float* origins, const float* dirs, 
       }
       LAUNCH(launch_bucket_assign(M.sam_w, ctx->feat_cutoff, ctx->bucket_counts[slot].as<int>(),
                                   ctx->bucket_lists[slot].as<int>(), n_rays, cs.feat));
-      int64_t launched = 0;
-      CK(launch_sam_bucketed(Bk, ctx->bucket_counts[slot].as<int>(), ctx->bucket_lists[slot].as<int>(), n_rays,
-                             ctx->sm_count, cs.feat, &launched));
-      ctx->launches += launched;
+      Bk.lists = ctx->bucket_lists[slot].as<int>();
+      Bk.counts = ctx->bucket_counts[slot].as<int>();
+      Bk.n_rays = n_rays;
+      LAUNCH(launch_sam_bucketed(Bk, ctx->sm_count, cs.feat));
       if (ctx->timing) {
         cudaEventRecord(e1, cs.feat);
         ctx->ev_used.push_back({1, {e0, e1}});

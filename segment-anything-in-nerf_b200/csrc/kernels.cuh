@@ -95,8 +95,9 @@ struct SamBucketParams {
   GridDev enc[2];
   const __half* w1;    // core-matrix layout, as SamParams
   __half* hbar;        // [N,256]
-  const int* list;     // ray indices of this bucket
-  const int* count;    // number of entries in `list` (device memory, written by the pre-pass)
+  const int* lists;    // [kFeatBuckets][n_rays] ray indices per bucket
+  const int* counts;   // [kFeatBuckets] entries per bucket (device memory, written by the pre-pass)
+  int64_t n_rays;
 };
 // Pre-pass, one thread per ray: significant slots = 1 + index of the last slot whose weight is not below the
 // cut-off (NaN weights - 0/0 rays, sam_model.py:248 - count as significant, so such a ray keeps all 16 slots and
@@ -116,8 +117,7 @@ SNRF_HD void bucket_assign_one(const float* sam_w, float eps, int* counts, int* 
   lists[static_cast<int64_t>(b) * n + pos] = static_cast<int>(ray);
 }
 cudaError_t launch_bucket_assign(const float* sam_w, float eps, int* counts, int* lists, int64_t n, cudaStream_t stream);
-cudaError_t launch_sam_bucketed(const SamBucketParams& P, const int* counts, const int* lists, int64_t n_rays, int sm_count,
-                                cudaStream_t stream, int64_t* launches);
+cudaError_t launch_sam_bucketed(const SamBucketParams& P, int sm_count, cudaStream_t stream);
 
 // ---- kernel C/D: tap GEMM  out = act(sum_t A_t[M,256] x W_t[N,256]^T + bias) ----------------------
 struct GemmParams {

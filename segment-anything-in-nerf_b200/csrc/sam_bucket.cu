@@ -5,8 +5,8 @@
 // frame 35 % of the rays have 1 slot with w >= 2^-24, 25 % have 2, 28 % at most 4, 12 % at most 8, 0.4 % more (oracle
 // count; the slots are stored in descending weight order, so the significant ones are a prefix).  Kernel B spends the
 // same 24 levels x 8 corners x 16 B of gathers and the same 128-row tensor-core tile on every slot.  Here a pre-pass
-// sorts the rays into five buckets by their significant-slot count (<= 1, <= 2, <= 4, <= 8, 16) and one launch per bucket
-// runs tiles of 128 / SLOTS rays x SLOTS slots: same gather code, same tcgen05 tile, a log2(SLOTS)-step row
+// sorts the rays into five buckets by their significant-slot count (<= 1, <= 2, <= 4, <= 8, 16) and one persistent launch
+// runs tiles of 128 / SLOTS rays x SLOTS slots, bucket after bucket: same gather code, same tcgen05 tile, a log2(SLOTS)-step row
 // reduction in the epilogue.  Every slot below SLOTS is evaluated with its real weight; only slots >= SLOTS - all
 // of them below the cut-off - are dropped.  cut-off 0 drops exact zeros only (bit-for-bit the same sum up to fp32
 // summation order); the default 2^-24 drops at most 1.2e-7 of total weight per ray (measured), i.e. less than one
@@ -96,19 +96,43 @@ __device__ __forceinline__ int halving_reduce(float (&v)[32], int lane) {
   return base;
 }
 
-template <int SLOTS>
-struct Log2;
-template <> struct Log2<1> { static constexpr int v = 0; };
-template <> struct Log2<2> { static constexpr int v = 1; };
-template <> struct Log2<4> { static constexpr int v = 2; };
-template <> struct Log2<8> { static constexpr int v = 3; };
-template <> struct Log2<16> { static constexpr int v = 4; };
+// ---- epilogue of one tile out of TMEM: relu, fp16 round, slot weight, sum over the 2^LOG rows of each ray ------
+template <int LOG>
+__device__ __forceinline__ void epilogue_tile(const SamBucketParams& P, uint32_t tmem_base, const float* s_sw,
+                                              uint64_t* s_bar, const int* list, int n_list, int64_t tile, int buf,
+                                              uint32_t parity, int warp, int lane) {
+  constexpr int kKeep = 32 >> LOG;  // columns a lane holds after the row reduction
+  mbar_wait(smem_u32(&s_bar[buf]), parity);
+  tc_fence_after();
+  const int quarter = warp & 3, cq = warp >> 2;
+  const int erow = quarter * 32 + lane;
+  const float wgt = s_sw[buf * 128 + erow];
+  const int64_t li = tile * (128 >> LOG) + (erow >> LOG);
+  const bool valid = li < n_list;
+  const int64_t ray = valid ? list[li] : 0;
+#pragma unroll 1
+  for (int chunk = 0; chunk < 2; ++chunk) {
+    float v[32];
+    const int col0 = cq * 64 + chunk * 32;
+    tmem_ld32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * 256 + col0, v);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = round_f16(fmaxf(v[i], 0.f)) * wgt;
+    const int base = halving_reduce<LOG>(v, lane);
+    if (valid) {
+      __half* dst = P.hbar + ray * kHid + col0 + base;
+#pragma unroll
+      for (int i = 0; i < kKeep; i += 2) *reinterpret_cast<uint32_t*>(dst + i) = f2_to_h2(v[i], v[i + 1]);
+    }
+  }
+  tc_fence_before();
+}
 
-template <uint32_t M0, uint32_t M1, int SLOTS>
+// One persistent launch covers all five buckets: tiles are numbered across the buckets (bucket b contributes
+// ceil(count[b] / (128 >> b)) tiles of 128 >> b rays x 1 << b slots) and strided over the CTAs, so W1 is staged and
+// TMEM allocated once per CTA and the buckets balance against each other.  The gather is the same code for every
+// bucket (row -> (ray, slot) is a shift and a mask); only the epilogue's reduction width is a compile-time variant.
+template <uint32_t M0, uint32_t M1>
 __global__ void __launch_bounds__(kThreads, 1) sam_bucket_kernel(const SamBucketParams P) {
-  constexpr int kRPT = 128 / SLOTS;  // rays per 128-row tile
-  constexpr int LOG = Log2<SLOTS>::v;
-  constexpr int kKeep = 32 >> LOG;   // columns a lane holds after the row reduction
   extern __shared__ __align__(128) unsigned char smem[];
   unsigned char* s_w1 = smem;
   unsigned char* s_a = smem + kW1Bytes;
@@ -132,50 +156,48 @@ __global__ void __launch_bounds__(kThreads, 1) sam_bucket_kernel(const SamBucket
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
 
-  const int n_list = *P.count;  // rays in this bucket (written by the pre-pass on the same stream)
-  const int64_t n_tiles = (static_cast<int64_t>(n_list) + kRPT - 1) / kRPT;
-  const int g = warp & 7, e = warp >> 3;
-  const int s16 = lane >> 1, xb = lane & 1;
-  const int row = g * 16 + s16;           // tile row this lane pair gathers
-  const int r_loc = row / SLOTS, slot = row % SLOTS;
-
-  // ---- epilogue of one tile out of TMEM --------------------------------------------------------
-  auto epilogue = [&](int64_t tile, int buf, uint32_t parity) {
-    mbar_wait(smem_u32(&s_bar[buf]), parity);
-    tc_fence_after();
-    const int quarter = warp & 3, cq = warp >> 2;
-    const int erow = quarter * 32 + lane;
-    const float wgt = s_sw[buf * 128 + erow];
-    const int64_t li = tile * kRPT + erow / SLOTS;
-    const bool valid = li < n_list;
-    const int64_t ray = valid ? P.list[li] : 0;
-#pragma unroll 1
-    for (int chunk = 0; chunk < 2; ++chunk) {
-      float v[32];
-      const int col0 = cq * 64 + chunk * 32;
-      tmem_ld32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * 256 + col0, v);
-#pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = round_f16(fmaxf(v[i], 0.f)) * wgt;
-      const int base = halving_reduce<LOG>(v, lane);
-      if (valid) {
-        __half* dst = P.hbar + ray * kHid + col0 + base;
-#pragma unroll
-        for (int i = 0; i < kKeep; i += 2) *reinterpret_cast<uint32_t*>(dst + i) = f2_to_h2(v[i], v[i + 1]);
-      }
+  // bucket sizes (written by the pre-pass on the same stream) -> first global tile of every bucket
+  const int c0 = P.counts[0], c1 = P.counts[1], c2 = P.counts[2], c3 = P.counts[3], c4 = P.counts[4];
+  const int64_t t1 = (c0 + 127) >> 7, t2 = t1 + ((c1 + 63) >> 6), t3 = t2 + ((c2 + 31) >> 5), t4 = t3 + ((c3 + 15) >> 4),
+                t5 = t4 + ((c4 + 7) >> 3);
+  auto bucket_of = [&](int64_t t, int64_t& first, int& count) -> int {
+    if (t < t1) { first = 0; count = c0; return 0; }
+    if (t < t2) { first = t1; count = c1; return 1; }
+    if (t < t3) { first = t2; count = c2; return 2; }
+    if (t < t4) { first = t3; count = c3; return 3; }
+    first = t4; count = c4; return 4;
+  };
+  auto run_epilogue = [&](int b, int count, int64_t tile, int buf, uint32_t parity) {
+    const int* list = P.lists + static_cast<int64_t>(b) * P.n_rays;
+    switch (b) {
+      case 0: epilogue_tile<0>(P, tmem_base, s_sw, s_bar, list, count, tile, buf, parity, warp, lane); break;
+      case 1: epilogue_tile<1>(P, tmem_base, s_sw, s_bar, list, count, tile, buf, parity, warp, lane); break;
+      case 2: epilogue_tile<2>(P, tmem_base, s_sw, s_bar, list, count, tile, buf, parity, warp, lane); break;
+      case 3: epilogue_tile<3>(P, tmem_base, s_sw, s_bar, list, count, tile, buf, parity, warp, lane); break;
+      default: epilogue_tile<4>(P, tmem_base, s_sw, s_bar, list, count, tile, buf, parity, warp, lane); break;
     }
-    tc_fence_before();
   };
 
+  const int g = warp & 7, e = warp >> 3;
+  const int s16 = lane >> 1, xb = lane & 1;
+  const int row = g * 16 + s16;  // tile row this lane pair gathers
+
+  int prev_b = 0, prev_count = 0;
   int64_t prev_tile = -1;
   int it = 0;
-  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+  for (int64_t t = blockIdx.x; t < t5; t += gridDim.x, ++it) {
     const int buf = it & 1;
     unsigned char* a_tile = s_a + buf * kATileBytes;
-    const int64_t li = tile * kRPT + r_loc;
-    const bool valid = li < n_list;
+    int64_t first;
+    int count;
+    const int b = bucket_of(t, first, count);  // LOG of this tile: 1 << b slots per ray, 128 >> b rays
+    const int64_t tile = t - first;
+    const int r_loc = row >> b, slot = row & ((1 << b) - 1);
+    const int64_t li = tile * (128 >> b) + r_loc;
+    const bool valid = li < count;
     // rows past the end of the list recompute the last ray with weight 0 (their results are never stored), so that
     // every lane of the warp runs the same gather and its full-mask shuffles
-    const int64_t ray = P.list[valid ? li : n_list - 1];
+    const int64_t ray = (P.lists + static_cast<int64_t>(b) * P.n_rays)[valid ? li : count - 1];
     const float tm2 = P.sam_t[ray * kK + slot];
     if (e == 0 && xb == 0) s_sw[buf * 128 + row] = valid ? P.sam_w[ray * kK + slot] : 0.f;
     const float px = __fadd_rn(P.origins[3 * ray + 0], __fmul_rn(P.dirs[3 * ray + 0], tm2) / 2.f);
@@ -202,10 +224,12 @@ __global__ void __launch_bounds__(kThreads, 1) sam_bucket_kernel(const SamBucket
       umma_commit(smem_u32(&s_bar[buf]));
     }
     __syncwarp();
-    if (it > 0) epilogue(prev_tile, buf ^ 1, static_cast<uint32_t>(((it - 1) >> 1) & 1));
+    if (it > 0) run_epilogue(prev_b, prev_count, prev_tile, buf ^ 1, static_cast<uint32_t>(((it - 1) >> 1) & 1));
+    prev_b = b;
+    prev_count = count;
     prev_tile = tile;
   }
-  if (it > 0) epilogue(prev_tile, (it - 1) & 1, static_cast<uint32_t>(((it - 1) >> 1) & 1));
+  if (it > 0) run_epilogue(prev_b, prev_count, prev_tile, (it - 1) & 1, static_cast<uint32_t>(((it - 1) >> 1) & 1));
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
@@ -217,12 +241,12 @@ __global__ void bucket_assign_kernel(const float* sam_w, float eps, int* counts,
 
 constexpr uint32_t kEnc0MaskStd = 0xE00u, kEnc1MaskStd = 0xFFFu;  // as in sam.cu
 
-template <uint32_t M0, uint32_t M1, int SLOTS>
+template <uint32_t M0, uint32_t M1>
 cudaError_t launch_one(const SamBucketParams& P, int grid, cudaStream_t stream) {
   static bool configured_dev[64] = {false};
   int dev_id = 0;
   if (cudaGetDevice(&dev_id) != cudaSuccess || dev_id < 0 || dev_id >= 64) return cudaErrorInvalidDevice;
-  auto* k = sam_bucket_kernel<M0, M1, SLOTS>;
+  auto* k = sam_bucket_kernel<M0, M1>;
   if (!configured_dev[dev_id]) {
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
     if (e != cudaSuccess) return e;
@@ -230,12 +254,6 @@ cudaError_t launch_one(const SamBucketParams& P, int grid, cudaStream_t stream) 
   }
   k<<<grid, kThreads, kSmemBytes, stream>>>(P);
   return cudaGetLastError();
-}
-
-template <int SLOTS>
-cudaError_t launch_slots(const SamBucketParams& P, bool std_cfg, int grid, cudaStream_t stream) {
-  return std_cfg ? launch_one<kEnc0MaskStd, kEnc1MaskStd, SLOTS>(P, grid, stream)
-                 : launch_one<kRuntimeMask, kRuntimeMask, SLOTS>(P, grid, stream);
 }
 
 }  // namespace
@@ -248,28 +266,15 @@ cudaError_t launch_bucket_assign(const float* sam_w, float eps, int* counts, int
   return cudaGetLastError();
 }
 
-// One launch per bucket; the bucket sizes stay on the device (each kernel reads its own count), so the grid is sized
-// for the worst case (every ray in this bucket) and surplus CTAs exit after the prologue.
-cudaError_t launch_sam_bucketed(const SamBucketParams& P0, const int* counts, const int* lists, int64_t n_rays, int sm_count,
-                                cudaStream_t stream, int64_t* launches) {
-  if (n_rays <= 0) return cudaSuccess;
-  const bool std_cfg = hashed_mask(P0.enc[0]) == kEnc0MaskStd && hashed_mask(P0.enc[1]) == kEnc1MaskStd;
-  for (int b = 0; b < kFeatBuckets; ++b) {
-    SamBucketParams P = P0;
-    P.list = lists + static_cast<int64_t>(b) * n_rays;
-    P.count = counts + b;
-    const int slots = 1 << b;  // 1, 2, 4, 8, 16
-    const int64_t tiles = (n_rays + (128 / slots) - 1) / (128 / slots);
-    const int grid = static_cast<int>(tiles < sm_count ? tiles : sm_count);
-    cudaError_t e = b == 0 ? launch_slots<1>(P, std_cfg, grid, stream)
-                  : b == 1 ? launch_slots<2>(P, std_cfg, grid, stream)
-                  : b == 2 ? launch_slots<4>(P, std_cfg, grid, stream)
-                  : b == 3 ? launch_slots<8>(P, std_cfg, grid, stream)
-                           : launch_slots<16>(P, std_cfg, grid, stream);
-    if (e != cudaSuccess) return e;
-    if (launches) *launches += 1;
-  }
-  return cudaSuccess;
+// One persistent launch; the bucket sizes stay on the device (the kernel reads them), so the grid is sized for the worst
+// case - every ray in the 16-slot bucket, n / 8 tiles - and capped at one CTA per SM.
+cudaError_t launch_sam_bucketed(const SamBucketParams& P, int sm_count, cudaStream_t stream) {
+  if (P.n_rays <= 0) return cudaSuccess;
+  const bool std_cfg = hashed_mask(P.enc[0]) == kEnc0MaskStd && hashed_mask(P.enc[1]) == kEnc1MaskStd;
+  const int64_t tiles = (P.n_rays + 7) / 8;
+  const int grid = static_cast<int>(tiles < sm_count ? tiles : sm_count);
+  return std_cfg ? launch_one<kEnc0MaskStd, kEnc1MaskStd>(P, grid, stream)
+                 : launch_one<kRuntimeMask, kRuntimeMask>(P, grid, stream);
 }
 
 }  // namespace snrf

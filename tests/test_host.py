@@ -127,41 +127,60 @@ def test_bucket_prepass_body():
         assert 7 in lists[4, :counts[4]]
 
 
-@pytest.mark.parametrize("slots", [1, 2, 4, 8, 16])
-def test_bucket_kernel_index_arithmetic_model(slots):
-    """A Python model of the warp-level index arithmetic of sam_bucket_kernel<SLOTS> (it cannot be emulated like the
-    per-thread kernels): tile row -> (list entry, slot) in the gather, TMEM row -> lane in the epilogue, the
-    log2(SLOTS)-step halving reduction with its column base, and the store - every (ray, column) of hbar must be
-    written exactly once with sum_slot w * h.  The shuffles are modelled as lane permutations of numpy arrays."""
+def test_bucket_kernel_index_arithmetic_model():
+    """A Python model of the warp-level index arithmetic of sam_bucket_kernel (it cannot be emulated like the
+    per-thread kernels): global tile -> (bucket, local tile), tile row -> (list entry, slot) in the gather, TMEM row
+    -> lane in the epilogue, the log2(SLOTS)-step halving reduction with its column base, and the store - every
+    (ray, column) of hbar must be written exactly once with the sum over the bucket's slots of w * h.  The shuffles
+    are modelled as lane permutations of numpy arrays."""
     import numpy as np
 
-    rng = np.random.default_rng(slots)
-    rpt, log = 128 // slots, {1: 0, 2: 1, 4: 2, 8: 3, 16: 4}[slots]
-    n_list = 2 * rpt + 5  # two full tiles and a ragged one
-    list_ = rng.permutation(1000)[:n_list]
-    h = rng.standard_normal((1000, 16, 256)).astype(np.float32)   # stands for relu(W1 x) of (ray, slot)
-    w = rng.random((1000, 16)).astype(np.float32)
-    hbar = np.full((1000, 256), np.nan, np.float32)
-    writes = np.zeros((1000, 256), np.int32)
-    n_tiles = (n_list + rpt - 1) // rpt
-    for tile in range(n_tiles):
-        # gather side: 16 warps, lane pairs own rows
-        acc = np.zeros((128, 256), np.float32)
+    rng = np.random.default_rng(0)
+    n_rays = 700
+    h = rng.standard_normal((n_rays, 16, 64)).astype(np.float32)   # stands for relu(W1 x) of (ray, slot); 64 of the 256 columns
+    w = rng.random((n_rays, 16)).astype(np.float32)
+    # bucket lists as the pre-pass leaves them: [5][n_rays] with counts (ragged tiles in every bucket)
+    perm = rng.permutation(n_rays)
+    counts = [128 + 5, 64 * 2 + 3, 32 + 7, 16 * 3 + 1, 8 + 2]
+    lists = np.full((5, n_rays), -1, np.int64)
+    o = 0
+    for b, c in enumerate(counts):
+        lists[b, :c] = perm[o:o + c]
+        o += c
+    hbar = np.full((n_rays, 64), np.nan, np.float32)
+    writes = np.zeros((n_rays, 64), np.int32)
+    t1 = (counts[0] + 127) >> 7
+    t2 = t1 + ((counts[1] + 63) >> 6)
+    t3 = t2 + ((counts[2] + 31) >> 5)
+    t4 = t3 + ((counts[3] + 15) >> 4)
+    t5 = t4 + ((counts[4] + 7) >> 3)
+
+    def bucket_of(t):
+        for b, (hi, first) in enumerate(((t1, 0), (t2, t1), (t3, t2), (t4, t3))):
+            if t < hi:
+                return b, first, counts[b]
+        return 4, t4, counts[4]
+
+    for t in range(t5):
+        b, first, count = bucket_of(t)
+        tile = t - first
+        acc = np.zeros((128, 64), np.float32)
         s_sw = np.zeros(128, np.float32)
         for warp in range(8):  # e = 0 warps write the weights; both encodings write disjoint A columns
             for lane in range(32):
                 row = (warp & 7) * 16 + (lane >> 1)
-                r_loc, slot = row // slots, row % slots
-                li = tile * rpt + r_loc
-                valid = li < n_list
-                ray = list_[li if valid else n_list - 1]
+                r_loc, slot = row >> b, row & ((1 << b) - 1)
+                li = tile * (128 >> b) + r_loc
+                valid = li < count
+                ray = lists[b, li if valid else count - 1]
+                assert ray >= 0
                 s_sw[row] = w[ray, slot] if valid else 0.0
                 acc[row] = h[ray, slot]
-        # epilogue side
-        for warp in range(16):
-            quarter, cq = warp & 3, warp >> 2
+        log = b
+        for warp in range(4):  # the 64 modelled columns = column group cq = 0; quarter = warp & 3
+            quarter = warp & 3
             for chunk in range(2):
-                col0 = cq * 64 + chunk * 32
+                col0 = chunk * 32
                 v = np.zeros((32, 32), np.float32)  # [lane][i]
                 for lane in range(32):
                     erow = quarter * 32 + lane
@@ -183,12 +202,17 @@ def test_bucket_kernel_index_arithmetic_model(slots):
                 keep_n = 32 >> log
                 for lane in range(32):
                     erow = quarter * 32 + lane
-                    li = tile * rpt + erow // slots
-                    if li < n_list:
-                        ray = list_[li]
+                    li = tile * (128 >> log) + (erow >> log)
+                    if li < count:
+                        ray = lists[b, li]
                         c = col0 + base[lane]
                         hbar[ray, c:c + keep_n] = v[lane, :keep_n]
                         writes[ray, c:c + keep_n] += 1
-    want = (w[list_, :slots, None] * h[list_, :slots]).sum(1)
-    assert (writes[list_] == 1).all() and writes.sum() == n_list * 256
-    np.testing.assert_allclose(hbar[list_], want, rtol=1e-5, atol=1e-5)
+    used = perm[:sum(counts)]
+    assert (writes[used] == 1).all() and writes.sum() == sum(counts) * 64
+    o = 0
+    for b, c in enumerate(counts):
+        rays = perm[o:o + c]
+        o += c
+        want = (w[rays, :1 << b, None] * h[rays, :1 << b]).sum(1)
+        np.testing.assert_allclose(hbar[rays], want, rtol=1e-5, atol=1e-5)
