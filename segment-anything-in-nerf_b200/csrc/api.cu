@@ -1092,6 +1092,7 @@ int snrf_feature_backward(snrf_ctx* ctx, int which, const float* origins, const 
   B.enc[0] = f.grid[0];
   B.enc[1] = f.grid[1];
   B.d_hbar = ctx->bwd_scratch.as<float>();
+  B.cutoff = ctx->feat_cutoff;  // same significance rule as the forward pass (snrf_set_feature_cutoff); < 0 = all 16 slots
   // a frozen parameter's gradient goes to a sink so that the kernels stay branch-free
   const size_t n_net = 256 * 192 + static_cast<size_t>(f.n_out) * 256;
   const size_t n_g0 = static_cast<size_t>(f.grid[0].lv[11].offset + f.grid[0].lv[11].size) * 8;

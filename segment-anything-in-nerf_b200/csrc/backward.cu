@@ -16,21 +16,25 @@ constexpr int kThreads = 256;
 inline unsigned blocks_for(int64_t items) { return static_cast<unsigned>((items + kThreads - 1) / kThreads); }
 
 __global__ void mlp_dgrad_kernel(const float* dY, int ldy, int ny, const __half* W, int ldw, const __half* X, int ldx,
-                                 float* dX, int lddx, int nx, int64_t items) {
+                                 float* dX, int lddx, int nx, const int* rows_dev, int64_t items) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i < items) mlp_dgrad_one(dY, ldy, ny, W, ldw, X, ldx, dX, lddx, nx, i);
+  if (i < items) mlp_dgrad_one(dY, ldy, ny, W, ldw, X, ldx, dX, lddx, nx, rows_dev, i);
 }
 template <typename TB>
 __global__ void mlp_wgrad_kernel(const float* A, int lda, int na, const TB* B, int ldb, int nb, int64_t rows, float* C,
-                                 int ldc, int64_t items) {
+                                 int ldc, const int* rows_dev, const int* bmap, int64_t items) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i < items) mlp_wgrad_one<TB>(A, lda, na, B, ldb, nb, rows, C, ldc, i);
+  if (i < items) mlp_wgrad_one<TB>(A, lda, na, B, ldb, nb, rows, C, ldc, rows_dev, bmap, i);
 }
 template <int F>
 __global__ void grid_scatter_kernel(const GridDev G, bool linf, bool selector, const float* xyz, const float* dX, int lddx,
-                                    int col0, float* g_table, int64_t items) {
+                                    int col0, float* g_table, const int* rows_dev, int64_t items) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i < items) grid_scatter_one<F>(G, linf, selector, xyz, dX, lddx, col0, g_table, i);
+  if (i < items) grid_scatter_one<F>(G, linf, selector, xyz, dX, lddx, col0, g_table, rows_dev, i);
+}
+__global__ void feat_rows_assign_kernel(const FeatBwdParams P, int64_t items) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < items) feat_rows_assign_one(P, i);
 }
 __global__ void feat_hidden_kernel(const FeatBwdParams P, int64_t items) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -99,28 +103,30 @@ struct DeviceExec {
     conv_bias_grad_kernel<<<blocks_for(items), kThreads, 0, s>>>(dY, rows, g_b, items);
   }
   void dgrad(const float* dY, int ldy, int ny, const __half* W, int ldw, const __half* X, int ldx, float* dX, int lddx,
-             int nx, int64_t rows) {
+             int nx, int64_t rows, const int* rows_dev) {
     const int64_t items = rows * nx;
-    mlp_dgrad_kernel<<<blocks_for(items), kThreads, 0, s>>>(dY, ldy, ny, W, ldw, X, ldx, dX, lddx, nx, items);
+    mlp_dgrad_kernel<<<blocks_for(items), kThreads, 0, s>>>(dY, ldy, ny, W, ldw, X, ldx, dX, lddx, nx, rows_dev, items);
   }
-  void wgrad_h(const float* A, int lda, int na, const __half* B, int ldb, int nb, int64_t rows, float* C, int ldc) {
+  void wgrad_h(const float* A, int lda, int na, const __half* B, int ldb, int nb, int64_t rows, float* C, int ldc,
+               const int* rows_dev, const int* bmap) {
     const int64_t items = mlp_wgrad_items(rows, na, nb);
-    mlp_wgrad_kernel<__half><<<blocks_for(items), kThreads, 0, s>>>(A, lda, na, B, ldb, nb, rows, C, ldc, items);
+    mlp_wgrad_kernel<__half><<<blocks_for(items), kThreads, 0, s>>>(A, lda, na, B, ldb, nb, rows, C, ldc, rows_dev, bmap, items);
   }
   void wgrad_f(const float* A, int lda, int na, const float* B, int ldb, int nb, int64_t rows, float* C, int ldc) {
     const int64_t items = mlp_wgrad_items(rows, na, nb);
-    mlp_wgrad_kernel<float><<<blocks_for(items), kThreads, 0, s>>>(A, lda, na, B, ldb, nb, rows, C, ldc, items);
+    mlp_wgrad_kernel<float><<<blocks_for(items), kThreads, 0, s>>>(A, lda, na, B, ldb, nb, rows, C, ldc, nullptr, nullptr, items);
   }
   void scatter2(const GridDev& G, bool linf, bool sel, const float* xyz, const float* dX, int lddx, int col0, float* g,
-                int64_t points) {
+                int64_t points, const int* rows_dev) {
     const int64_t items = points * G.n_levels;
-    grid_scatter_kernel<2><<<blocks_for(items), kThreads, 0, s>>>(G, linf, sel, xyz, dX, lddx, col0, g, items);
+    grid_scatter_kernel<2><<<blocks_for(items), kThreads, 0, s>>>(G, linf, sel, xyz, dX, lddx, col0, g, rows_dev, items);
   }
   void scatter8(const GridDev& G, bool linf, bool sel, const float* xyz, const float* dX, int lddx, int col0, float* g,
-                int64_t points) {
+                int64_t points, const int* rows_dev) {
     const int64_t items = points * G.n_levels;
-    grid_scatter_kernel<8><<<blocks_for(items), kThreads, 0, s>>>(G, linf, sel, xyz, dX, lddx, col0, g, items);
+    grid_scatter_kernel<8><<<blocks_for(items), kThreads, 0, s>>>(G, linf, sel, xyz, dX, lddx, col0, g, rows_dev, items);
   }
+  void feat_rows_assign(const FeatBwdParams& P, int64_t items) { feat_rows_assign_kernel<<<blocks_for(items), kThreads, 0, s>>>(P, items); }
   void feat_hidden(const FeatBwdParams& P, int64_t items) { feat_hidden_kernel<<<blocks_for(items), kThreads, 0, s>>>(P, items); }
   void feat_positions(const FeatBwdParams& P, int64_t items) { feat_positions_kernel<<<blocks_for(items), kThreads, 0, s>>>(P, items); }
   void sigmoid_bwd(const float* d_rgb, const __half* pre, int ldp, float* d_pre, int64_t items) {
@@ -156,7 +162,8 @@ cudaError_t launch_rgb_bwd(const float* rgb, const float* w, const float* g_out,
 // ---------------------------------------------------------------------------------------------
 size_t feat_bwd_scratch_floats(int64_t n_rays) {
   const int64_t b = n_rays < kBwdBlockRays ? n_rays : kBwdBlockRays;
-  return static_cast<size_t>(b) * (2 * kBwdHid + kBwdK * kBwdHid + kBwdK * kBwdIn + kBwdK * 3);
+  // fp32: d_hbar, hbar [b,256]; dh [b*16,256]; dx [b*16,192]; xyz [b*16,3]; int32: n_rows (4), row_map [b*16], row_start, row_k [b]
+  return static_cast<size_t>(b) * (2 * kBwdHid + kBwdK * kBwdHid + kBwdK * kBwdIn + kBwdK * 3 + kBwdK + 2) + 4;
 }
 
 // P.d_hbar must point at feat_bwd_scratch_floats(P.n_rays) floats; hbar / dh / dx / xyz are carved out of it here.
@@ -177,6 +184,13 @@ cudaError_t launch_feat_backward(const FeatBwdParams& P0, cudaStream_t stream, i
     P.dh = P.hbar + n * kBwdHid;
     P.dx = P.dh + n * kBwdK * kBwdHid;
     P.xyz = P.dx + n * kBwdK * kBwdIn;
+    int* ints = reinterpret_cast<int*>(P.xyz + n * kBwdK * 3);
+    P.n_rows = ints;
+    P.row_map = ints + 4;
+    P.row_start = P.row_map + n * kBwdK;
+    P.row_k = P.row_start + n;
+    cudaError_t em = cudaMemsetAsync(P.n_rows, 0, sizeof(int), stream);
+    if (em != cudaSuccess) return em;
     DeviceExec ex{stream};
     feat_backward_chain(P, ex);
     if (launches) *launches += kFeatBwdLaunches;

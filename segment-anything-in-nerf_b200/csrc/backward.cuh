@@ -66,9 +66,12 @@ SNRF_HD float ld_f32<__half>(const __half* p) { return __half2float(*p); }
 // ---------------------------------------------------------------------------------------------
 // dX[row,i] = (sum_{j<ny} dY[row,j] * W[j,i]) * (X ? X[row,i] > 0 : 1)                 item = (row, i), i < nx
 // (X = the layer's saved post-ReLU input: relu'(pre) = [X > 0])
+// `rows_dev` (optional, device memory): number of valid rows when it is only known on the device (compacted rows of the
+// feature branch); items beyond it return at once.
 SNRF_HD void mlp_dgrad_one(const float* dY, int ldy, int ny, const __half* W, int ldw, const __half* X, int ldx,
-                           float* dX, int lddx, int nx, int64_t item) {
+                           float* dX, int lddx, int nx, const int* rows_dev, int64_t item) {
   const int64_t row = item / nx;
+  if (rows_dev && row >= *rows_dev) return;
   const int i = static_cast<int>(item % nx);
   const float* g = dY + row * ldy;
   float a = 0.f;
@@ -80,16 +83,19 @@ SNRF_HD void mlp_dgrad_one(const float* dY, int ldy, int ny, const __half* W, in
 // C[a,b] += sum_{row in slab} A[row,a] * B[row,b]                                       item = (slab, a, b)
 // Non-finite rows (e.g. rays whose top-k weights are 0/0 = NaN, sam_model.py:248) poison the sum exactly as they do
 // in the reference's dense autograd; nothing is filtered here.
+// `bmap` (optional): row r of A pairs with row bmap[r] of B (compacted rows of the feature branch).
 template <typename TB>
 SNRF_HD void mlp_wgrad_one(const float* A, int lda, int na, const TB* B, int ldb, int nb, int64_t rows, float* C, int ldc,
-                           int64_t item) {
+                           const int* rows_dev, const int* bmap, int64_t item) {
+  if (rows_dev) rows = *rows_dev;
   const int b = static_cast<int>(item % nb);
   const int a = static_cast<int>((item / nb) % na);
   const int64_t slab = item / (static_cast<int64_t>(na) * nb);
   const int64_t r0 = slab * kSlabRows;
+  if (r0 >= rows) return;
   const int64_t r1 = r0 + kSlabRows < rows ? r0 + kSlabRows : rows;
   float acc = 0.f;
-  for (int64_t r = r0; r < r1; ++r) acc += A[r * lda + a] * ld_f32<TB>(B + r * ldb + b);
+  for (int64_t r = r0; r < r1; ++r) acc += A[r * lda + a] * ld_f32<TB>(B + (bmap ? bmap[r] : r) * ldb + b);
   atomic_add_f32(C + static_cast<size_t>(a) * ldc + b, acc);
 }
 SNRF_HD int64_t mlp_wgrad_items(int64_t rows, int na, int nb) {
@@ -102,9 +108,10 @@ SNRF_HD int64_t mlp_wgrad_items(int64_t rows, int na, int nb) {
 // ---------------------------------------------------------------------------------------------
 template <int F>
 SNRF_HD void grid_scatter_one(const GridDev& G, bool linf, bool selector, const float* xyz, const float* dX, int lddx,
-                              int col0, float* g_table, int64_t item) {
+                              int col0, float* g_table, const int* rows_dev, int64_t item) {
   const int l = static_cast<int>(item % G.n_levels);
   const int64_t pt = item / G.n_levels;
+  if (rows_dev && pt >= *rows_dev) return;
   const float* d = dX + pt * lddx + col0 + l * F;
   float g[F];
   bool any = false;
@@ -154,11 +161,39 @@ struct FeatBwdParams {
   float* dh;              // [N*16,256]
   float* dx;              // [N*16,192]
   float* xyz;             // [N*16,3]
+  // Row compaction: only the leading slots of a ray whose weight is not below `cutoff` get a row (the same rule as
+  // the bucketed forward kernel, sam_bucket.cu); cutoff < 0 keeps all 16.  dh / dx / xyz are indexed by compact row.
+  float cutoff;
+  int* n_rows;            // [1] number of compact rows (device counter, zeroed by the launcher)
+  int* row_map;           // [N*16] compact row -> ray*16 + slot
+  int* row_start;         // [N] first compact row of the ray
+  int* row_k;             // [N] rows of the ray
   // outputs, accumulated (+=)
   float* g_w1;            // [256,192]
   float* g_w2;            // [n_out,256]
   float* g_table[2];      // [entries*8] each
 };
+
+// F0: rows of each ray                                                                        item = ray
+SNRF_HD void feat_rows_assign_one(const FeatBwdParams& P, int64_t ray) {
+  int k = kBwdK;
+  if (!(P.cutoff < 0.f)) {
+    k = 0;
+    for (int s = 0; s < kBwdK; ++s) {
+      const float w = P.sam_w[ray * kBwdK + s];
+      if (!(w < P.cutoff) && w != 0.f) k = s + 1;  // NaN weights (0/0 rays) count as significant
+    }
+  }
+#ifdef __CUDA_ARCH__
+  const int pos = atomicAdd(P.n_rows, k);
+#else
+  const int pos = *P.n_rows;
+  *P.n_rows += k;
+#endif
+  P.row_start[ray] = pos;
+  P.row_k[ray] = k;
+  for (int s = 0; s < k; ++s) P.row_map[pos + s] = static_cast<int>(ray * kBwdK + s);
+}
 
 // F1: recompute h[r,k,j] = W1[j,:] . x[r,k,:]; hbar[r,j] = fp16(sum_k w_k * fp16(relu(h)));
 //     dh[r,k,j] = h > 0 ? w_k * d_hbar[r,j] : 0   (d_hbar from mlp_dgrad_one)          item = (ray, j)
@@ -167,22 +202,26 @@ SNRF_HD void feat_hidden_one(const FeatBwdParams& P, int64_t item) {
   const int j = static_cast<int>(item % kBwdHid);
   const __half* wr = P.w1 + static_cast<size_t>(j) * kBwdIn;
   const float g = P.d_hbar[item];
+  const int64_t row0 = P.row_start[r];
+  const int nk = P.row_k[r];
   float hb = 0.f;
-  for (int k = 0; k < kBwdK; ++k) {
+  for (int k = 0; k < nk; ++k) {
     const __half* xr = P.x + (r * kBwdK + k) * kBwdIn;
     float h = 0.f;
     for (int i = 0; i < kBwdIn; ++i) h += __half2float(xr[i]) * __half2float(wr[i]);
     const float w = P.sam_w[r * kBwdK + k];
     hb += w * round_f16(fmaxf(h, 0.f));
-    P.dh[(r * kBwdK + k) * kBwdHid + j] = h > 0.f ? w * g : 0.f;
+    P.dh[(row0 + k) * kBwdHid + j] = h > 0.f ? w * g : 0.f;
   }
   P.hbar[item] = round_f16(hb);
 }
 
 // F2: world positions of the picked samples, op for op as the forward kernel builds them          item = row
 SNRF_HD void feat_positions_one(const FeatBwdParams& P, int64_t row) {
-  const int64_t r = row / kBwdK;
-  const float tm2 = P.sam_t[row];
+  if (row >= *P.n_rows) return;
+  const int64_t orig = P.row_map[row];
+  const int64_t r = orig / kBwdK;
+  const float tm2 = P.sam_t[orig];
   for (int c = 0; c < 3; ++c) P.xyz[3 * row + c] = sample_coord(P.origins[3 * r + c], P.dirs[3 * r + c], tm2);
 }
 
@@ -190,19 +229,21 @@ SNRF_HD void feat_positions_one(const FeatBwdParams& P, int64_t row) {
 // and the host emulation (tests/emu) run the same wiring of buffers, strides and offsets.
 template <class Exec>
 inline void feat_backward_chain(const FeatBwdParams& P, Exec& ex) {
-  const int64_t n = P.n_rays, rows = n * kBwdK;
+  const int64_t n = P.n_rays, rows = n * kBwdK;  // `rows` is the worst case; the real count lives in *P.n_rows
+  ex.feat_rows_assign(P, n);
   // d_hbar = d_out . W2 ; hidden recompute, hbar, dh ; dx = dh . W1
-  ex.dgrad(P.d_out, P.n_out, P.n_out, P.w2, kBwdHid, nullptr, 0, P.d_hbar, kBwdHid, kBwdHid, n);
+  ex.dgrad(P.d_out, P.n_out, P.n_out, P.w2, kBwdHid, nullptr, 0, P.d_hbar, kBwdHid, kBwdHid, n, nullptr);
   ex.feat_hidden(P, n * kBwdHid);
-  ex.dgrad(P.dh, kBwdHid, kBwdHid, P.w1, kBwdIn, nullptr, 0, P.dx, kBwdIn, kBwdIn, rows);
+  ex.dgrad(P.dh, kBwdHid, kBwdHid, P.w1, kBwdIn, nullptr, 0, P.dx, kBwdIn, kBwdIn, rows, P.n_rows);
   // weight gradients
-  ex.wgrad_h(P.dh, kBwdHid, kBwdHid, P.x, kBwdIn, kBwdIn, rows, P.g_w1, kBwdIn);
+  ex.wgrad_h(P.dh, kBwdHid, kBwdHid, P.x, kBwdIn, kBwdIn, rows, P.g_w1, kBwdIn, P.n_rows, P.row_map);
   ex.wgrad_f(P.d_out, P.n_out, P.n_out, P.hbar, kBwdHid, kBwdHid, n, P.g_w2, kBwdHid);
   // table scatter (L2 contraction, no selector: sam_field.py:32,116-118)
   ex.feat_positions(P, rows);
-  for (int e = 0; e < 2; ++e) ex.scatter8(P.enc[e], false, false, P.xyz, P.dx, kBwdIn, e * 96, P.g_table[e], rows);
+  for (int e = 0; e < 2; ++e)
+    ex.scatter8(P.enc[e], false, false, P.xyz, P.dx, kBwdIn, e * 96, P.g_table[e], rows, P.n_rows);
 }
-constexpr int kFeatBwdLaunches = 8;
+constexpr int kFeatBwdLaunches = 9;
 
 // rays per internal block of the feature backward (bounds the fp32 scratch: 30 KB per ray)
 constexpr int64_t kBwdBlockRays = 8192;
@@ -263,21 +304,21 @@ inline void field_backward_chain(const FieldBwdParams& P, Exec& ex) {
   const bool colour = nerfacto && P.d_rgb != nullptr;
   if (colour) {  // rgb = sigmoid(Wh3 relu(Wh2 relu(Wh1 hx))), only outputs 0..2 of the 16 padded ones are used
     ex.sigmoid_bwd(P.d_rgb, P.pre3, 16, P.d_pre3, n * 3);
-    ex.dgrad(P.d_pre3, 3, 3, P.wh3, 64, P.g2, 64, P.d_g2, 64, 64, n);
-    ex.wgrad_h(P.d_pre3, 3, 3, P.g2, 64, 64, n, P.g_head + 64 * 32 + 64 * 64, 64);
-    ex.dgrad(P.d_g2, 64, 64, P.wh2, 64, P.g1, 64, P.d_g1, 64, 64, n);
-    ex.wgrad_h(P.d_g2, 64, 64, P.g1, 64, 64, n, P.g_head + 64 * 32, 64);
-    ex.dgrad(P.d_g1, 64, 64, P.wh1, 32, nullptr, 0, P.d_hx, 32, 32, n);
-    ex.wgrad_h(P.d_g1, 64, 64, P.hx, 32, 32, n, P.g_head, 32);
+    ex.dgrad(P.d_pre3, 3, 3, P.wh3, 64, P.g2, 64, P.d_g2, 64, 64, n, nullptr);
+    ex.wgrad_h(P.d_pre3, 3, 3, P.g2, 64, 64, n, P.g_head + 64 * 32 + 64 * 64, 64, nullptr, nullptr);
+    ex.dgrad(P.d_g2, 64, 64, P.wh2, 64, P.g1, 64, P.d_g1, 64, 64, n, nullptr);
+    ex.wgrad_h(P.d_g2, 64, 64, P.g1, 64, 64, n, P.g_head + 64 * 32, 64, nullptr, nullptr);
+    ex.dgrad(P.d_g1, 64, 64, P.wh1, 32, nullptr, 0, P.d_hx, 32, 32, n, nullptr);
+    ex.wgrad_h(P.d_g1, 64, 64, P.hx, 32, 32, n, P.g_head, 32, nullptr, nullptr);
   }
   // density (output 0) and, for nerfacto, the 15 geo features (outputs 1..15 = head inputs 16..30)
   const int n_o = nerfacto ? 16 : 1;
   ex.density_bwd(P.d_density, P.o, 16, P.sel, colour ? P.d_hx : nullptr, 32, 16, P.d_o, n_o, n * n_o);
-  ex.dgrad(P.d_o, n_o, n_o, P.w2, hidden, P.h1, hidden, P.d_h1, hidden, hidden, n);
-  ex.wgrad_h(P.d_o, n_o, n_o, P.h1, hidden, hidden, n, P.g_base + hidden * k_w, hidden);
-  ex.dgrad(P.d_h1, hidden, hidden, P.w1, k_w, nullptr, 0, P.d_x, width, width, n);
-  ex.wgrad_h(P.d_h1, hidden, hidden, P.x, width, width, n, P.g_base, k_w);
-  ex.scatter2(P.grid, true, true, P.xyz, P.d_x, width, 0, P.g_base + n_net, n);
+  ex.dgrad(P.d_o, n_o, n_o, P.w2, hidden, P.h1, hidden, P.d_h1, hidden, hidden, n, nullptr);
+  ex.wgrad_h(P.d_o, n_o, n_o, P.h1, hidden, hidden, n, P.g_base + hidden * k_w, hidden, nullptr, nullptr);
+  ex.dgrad(P.d_h1, hidden, hidden, P.w1, k_w, nullptr, 0, P.d_x, width, width, n, nullptr);
+  ex.wgrad_h(P.d_h1, hidden, hidden, P.x, width, width, n, P.g_base, k_w, nullptr, nullptr);
+  ex.scatter2(P.grid, true, true, P.xyz, P.d_x, width, 0, P.g_base + n_net, n, nullptr);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -424,14 +465,14 @@ inline void conv_backward_chain(const ConvBwdParams& P, Exec& ex) {
   // second conv
   ex.conv_mean_bwd(P.d_out, P.d_y, n * kConvC);
   ex.bias_grad(P.d_y, n, P.g_b2);
-  ex.wgrad_h(P.d_y, kConvC, kConvC, P.xcol2, kConvK, kConvK, n, P.g_w2, kConvK);
-  ex.dgrad(P.d_y, kConvC, kConvC, P.w2, kConvK, nullptr, 0, P.d_xcol, kConvK, kConvK, n);
+  ex.wgrad_h(P.d_y, kConvC, kConvC, P.xcol2, kConvK, kConvK, n, P.g_w2, kConvK, nullptr, nullptr);
+  ex.dgrad(P.d_y, kConvC, kConvC, P.w2, kConvK, nullptr, 0, P.d_xcol, kConvK, kConvK, n, nullptr);
   ex.col2im(P.d_xcol, P.hid, P.d_hid, n * kConvC);
   // first conv
   ex.bias_grad(P.d_hid, n, P.g_b1);
-  ex.wgrad_h(P.d_hid, kConvC, kConvC, P.xcol1, kConvK, kConvK, n, P.g_w1, kConvK);
+  ex.wgrad_h(P.d_hid, kConvC, kConvC, P.xcol1, kConvK, kConvK, n, P.g_w1, kConvK, nullptr, nullptr);
   if (P.d_feat) {
-    ex.dgrad(P.d_hid, kConvC, kConvC, P.w1, kConvK, nullptr, 0, P.d_xcol, kConvK, kConvK, n);
+    ex.dgrad(P.d_hid, kConvC, kConvC, P.w1, kConvK, nullptr, 0, P.d_xcol, kConvK, kConvK, n, nullptr);
     ex.col2im(P.d_xcol, nullptr, P.d_feat, n * kConvC);
   }
 }

@@ -37,23 +37,27 @@ int emu_generate_rays(const float* intr /*fx fy cx cy*/, int type, int has_dist,
 // executor of the backward chains of backward.cuh: every step is a plain loop over the items of one kernel
 struct HostExec {
   void dgrad(const float* dY, int ldy, int ny, const __half* W, int ldw, const __half* X, int ldx, float* dX, int lddx,
-             int nx, int64_t rows) {
-    for (int64_t i = 0; i < rows * nx; ++i) mlp_dgrad_one(dY, ldy, ny, W, ldw, X, ldx, dX, lddx, nx, i);
+             int nx, int64_t rows, const int* rows_dev) {
+    for (int64_t i = 0; i < rows * nx; ++i) mlp_dgrad_one(dY, ldy, ny, W, ldw, X, ldx, dX, lddx, nx, rows_dev, i);
   }
-  void wgrad_h(const float* A, int lda, int na, const __half* B, int ldb, int nb, int64_t rows, float* C, int ldc) {
-    for (int64_t i = 0; i < mlp_wgrad_items(rows, na, nb); ++i) mlp_wgrad_one<__half>(A, lda, na, B, ldb, nb, rows, C, ldc, i);
+  void wgrad_h(const float* A, int lda, int na, const __half* B, int ldb, int nb, int64_t rows, float* C, int ldc,
+               const int* rows_dev, const int* bmap) {
+    for (int64_t i = 0; i < mlp_wgrad_items(rows, na, nb); ++i)
+      mlp_wgrad_one<__half>(A, lda, na, B, ldb, nb, rows, C, ldc, rows_dev, bmap, i);
   }
   void wgrad_f(const float* A, int lda, int na, const float* B, int ldb, int nb, int64_t rows, float* C, int ldc) {
-    for (int64_t i = 0; i < mlp_wgrad_items(rows, na, nb); ++i) mlp_wgrad_one<float>(A, lda, na, B, ldb, nb, rows, C, ldc, i);
+    for (int64_t i = 0; i < mlp_wgrad_items(rows, na, nb); ++i)
+      mlp_wgrad_one<float>(A, lda, na, B, ldb, nb, rows, C, ldc, nullptr, nullptr, i);
   }
   void scatter2(const GridDev& G, bool linf, bool sel, const float* xyz, const float* dX, int lddx, int col0, float* g,
-                int64_t points) {
-    for (int64_t i = 0; i < points * G.n_levels; ++i) grid_scatter_one<2>(G, linf, sel, xyz, dX, lddx, col0, g, i);
+                int64_t points, const int* rows_dev) {
+    for (int64_t i = 0; i < points * G.n_levels; ++i) grid_scatter_one<2>(G, linf, sel, xyz, dX, lddx, col0, g, rows_dev, i);
   }
   void scatter8(const GridDev& G, bool linf, bool sel, const float* xyz, const float* dX, int lddx, int col0, float* g,
-                int64_t points) {
-    for (int64_t i = 0; i < points * G.n_levels; ++i) grid_scatter_one<8>(G, linf, sel, xyz, dX, lddx, col0, g, i);
+                int64_t points, const int* rows_dev) {
+    for (int64_t i = 0; i < points * G.n_levels; ++i) grid_scatter_one<8>(G, linf, sel, xyz, dX, lddx, col0, g, rows_dev, i);
   }
+  void feat_rows_assign(const FeatBwdParams& P, int64_t items) { for (int64_t i = 0; i < items; ++i) feat_rows_assign_one(P, i); }
   void im2col_f32(const float* X, __half* Xcol, int64_t items) { for (int64_t i = 0; i < items; ++i) conv_im2col_one<float>(X, Xcol, i); }
   void im2col_f16(const __half* X, __half* Xcol, int64_t items) { for (int64_t i = 0; i < items; ++i) conv_im2col_one<__half>(X, Xcol, i); }
   void conv_fwd(const __half* Xcol, const __half* W, const float* b, __half* Y, int relu, int64_t items) {
@@ -93,8 +97,10 @@ static void fill_grid(GridDev& G, const double* levels, int n_levels, int n_feat
 int emu_feature_backward(const float* origins, const float* dirs, const float* sam_t, const float* sam_w, long long n_rays,
                          const float* d_out, int n_out, const unsigned short* x_f16, const unsigned short* w1_f16,
                          const unsigned short* w2_f16, const double* levels /*[2][12][5]*/, float* g_w1, float* g_w2,
-                         float* g_table0, float* g_table1, float* hbar_out /*[N,256] or null*/) {
+                         float* g_table0, float* g_table1, float* hbar_out /*[N,256] or null*/, float cutoff,
+                         int* n_rows_out /*[1] or null*/) {
   FeatBwdParams P;
+  P.cutoff = cutoff;
   P.origins = origins; P.dirs = dirs; P.sam_t = sam_t; P.sam_w = sam_w; P.d_out = d_out;
   P.x = reinterpret_cast<const __half*>(x_f16);
   P.w1 = reinterpret_cast<const __half*>(w1_f16);
@@ -104,10 +110,14 @@ int emu_feature_backward(const float* origins, const float* dirs, const float* s
   const int64_t n = n_rays, rows = n * kBwdK;
   std::vector<float> d_hbar(n * kBwdHid), hbar(n * kBwdHid), dh(rows * kBwdHid), dx(rows * kBwdIn), xyz(rows * 3);
   P.d_hbar = d_hbar.data(); P.hbar = hbar.data(); P.dh = dh.data(); P.dx = dx.data(); P.xyz = xyz.data();
+  std::vector<int> row_map(rows), row_start(n), row_k(n);
+  int n_rows = 0;
+  P.n_rows = &n_rows; P.row_map = row_map.data(); P.row_start = row_start.data(); P.row_k = row_k.data();
   P.g_w1 = g_w1; P.g_w2 = g_w2; P.g_table[0] = g_table0; P.g_table[1] = g_table1;
   HostExec ex;
   feat_backward_chain(P, ex);
   if (hbar_out) for (int64_t i = 0; i < n * kBwdHid; ++i) hbar_out[i] = hbar[i];
+  if (n_rows_out) *n_rows_out = n_rows;
   return 0;
 }
 

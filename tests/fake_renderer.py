@@ -220,7 +220,7 @@ class FakeRenderer:
         ins = [arr(origins), arr(directions), arr(sam_t), arr(sam_w), arr(d_out), bits(enc), bits(w1), bits(w2), lv]
         load().emu_feature_backward(ptr(ins[0]), ptr(ins[1]), ptr(ins[2]), ptr(ins[3]), C.c_longlong(n), ptr(ins[4]), n_out,
                                     ptr(ins[5]), ptr(ins[6]), ptr(ins[7]), ptr(ins[8]), ptr(g_w1), ptr(g_w2), ptr(g_t[0]),
-                                    ptr(g_t[1]), None)
+                                    ptr(g_t[1]), None, C.c_float(-1.0), None)
         full = {"net": torch.from_numpy(np.concatenate([g_w1.ravel(), g_w2.ravel()])), "grid0": torch.from_numpy(g_t[0]),
                 "grid1": torch.from_numpy(g_t[1])}
         grads = {} if grads is None else grads

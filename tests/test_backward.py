@@ -65,8 +65,17 @@ def _assert_grad_close(got, want, what):
     assert float((nz_w & ~nz_g).float().mean()) < 1e-4, what
 
 
-@pytest.mark.parametrize("which,clipseg", [("sam", False), ("clipseg", True)])
-def test_kernel_bodies_match_autograd(which, clipseg):
+def _significant_prefix_mask(sam_w, cutoff):
+    """Slots the kernels keep: everything up to the last slot whose weight is not below the cut-off (all 16 if < 0)."""
+    if cutoff < 0:
+        return torch.ones_like(sam_w, dtype=torch.bool)
+    sig = (~(sam_w < cutoff)) & (sam_w != 0)
+    k = torch.where(sig.any(-1), 16 - sig.flip(-1).float().argmax(-1), torch.zeros(sam_w.shape[0], dtype=torch.long))
+    return torch.arange(16)[None, :] < k[:, None]
+
+
+@pytest.mark.parametrize("which,clipseg,cutoff", [("sam", False, -1.0), ("clipseg", True, -1.0), ("sam", False, 1e-3)])
+def test_kernel_bodies_match_autograd(which, clipseg, cutoff):
     from emu.build_emu import load
 
     cfg, params, orc0 = model_pair("tiny", "scene", 21, clipseg, 1)
@@ -74,9 +83,14 @@ def test_kernel_bodies_match_autograd(which, clipseg):
     o, d, sam_t, sam_w = _branch_inputs(cfg, orc0, n, seed=9, which=which)
     ok = torch.isfinite(sam_w).all(-1)
     o, d, sam_t, sam_w = o[ok], d[ok], sam_t[ok], sam_w[ok]
+    # the march kernel stores the picks in descending weight order (slot = rank); the oracle's topk is unsorted
+    sam_w, order = sam_w.sort(dim=-1, descending=True)
+    sam_t = torch.gather(sam_t, 1, order)
     n = o.shape[0]
+    keep = _significant_prefix_mask(sam_w, cutoff)
+    assert cutoff < 0 or 0.05 < float(keep.float().mean()) < 0.9  # the cut-off really drops rows in this test
     orc, p = _fresh_oracle(cfg, params)
-    out, f = oracle_branch(orc, which, o, d, sam_t, sam_w)
+    out, f = oracle_branch(orc, which, o, d, sam_t, sam_w * keep)  # reference: the dropped slots carry no weight
     g_out = torch.randn(out.shape, generator=torch.Generator().manual_seed(1))
     (out * g_out).sum().backward()
     enc_names = [f"sam_field.{'clip' if which == 'sam' else 'clipseg'}_encs.{i}.params" for i in range(2)]
@@ -104,9 +118,11 @@ def test_kernel_bodies_match_autograd(which, clipseg):
     arr = lambda t: np.ascontiguousarray(t.detach().numpy(), np.float32)
     ptr = lambda a: a.ctypes.data_as(C.c_void_p)
     ins = [arr(o), arr(d), arr(sam_t), arr(sam_w), arr(g_out), _f16_bits(xs), _f16_bits(w1), _f16_bits(w2), _levels(cfg)]
+    n_rows = C.c_int(0)
     lib.emu_feature_backward(ptr(ins[0]), ptr(ins[1]), ptr(ins[2]), ptr(ins[3]), C.c_longlong(n), ptr(ins[4]), n_out,
                              ptr(ins[5]), ptr(ins[6]), ptr(ins[7]), ptr(ins[8]), ptr(g_w1), ptr(g_w2), ptr(g_t[0]),
-                             ptr(g_t[1]), ptr(hbar))
+                             ptr(g_t[1]), ptr(hbar), C.c_float(cutoff), C.byref(n_rows))
+    assert n_rows.value == int(keep.sum())  # one compact row per kept (ray, slot)
     want_net = p[net_name].grad
     _assert_grad_close(g_w1, want_net[: 256 * 192], "dW1")
     _assert_grad_close(g_w2, want_net[256 * 192:], "dW2")
@@ -131,17 +147,21 @@ def test_oracle_gradients_are_straight_through_fp16():
 # ---------------------------------------------------------------------------------------------------------
 @pytest.mark.gpu
 @pytest.mark.hw_unverified
-@pytest.mark.parametrize("which,clipseg", [("sam", False), ("clipseg", True)])
-def test_gpu_backward_matches_autograd(which, clipseg):
+@pytest.mark.parametrize("which,clipseg,cutoff", [("sam", False, -1.0), ("clipseg", True, -1.0), ("sam", False, 1e-3)])
+def test_gpu_backward_matches_autograd(which, clipseg, cutoff):
     from helpers import assert_features_close, make_renderer
 
     cfg, params, orc0 = model_pair("tiny", "scene", 21, clipseg, 1)
     r = make_renderer(cfg, params)
+    r.set_feature_cutoff(cutoff)  # the forward (bucketed kernel) and the backward (compact rows) share the rule
     o, d, sam_t, sam_w = _branch_inputs(cfg, orc0, 700, seed=9, which=which)
     ok = torch.isfinite(sam_w).all(-1)
     o, d, sam_t, sam_w = o[ok], d[ok], sam_t[ok], sam_w[ok]
+    sam_w, order = sam_w.sort(dim=-1, descending=True)  # slot = rank, as the march kernel stores the picks
+    sam_t = torch.gather(sam_t, 1, order)
+    keep = _significant_prefix_mask(sam_w, cutoff)
     orc, p = _fresh_oracle(cfg, params)
-    out, _ = oracle_branch(orc, which, o, d, sam_t, sam_w)
+    out, _ = oracle_branch(orc, which, o, d, sam_t, sam_w * keep)
     g_out = torch.randn(out.shape, generator=torch.Generator().manual_seed(1))
     (out * g_out).sum().backward()
     got_out, enc = r.feature_forward(which, o, d, sam_t, sam_w)
