@@ -291,7 +291,7 @@ class ProposalNetworkSampler:
         edges0 = sp_inv(bins * s_far + (1 - bins) * s_near)
         rs0 = self._samples(ray_bundle, edges0, bins.expand(n, -1) if bins.shape[0] == 1 else bins)
         rs1 = self._samples(ray_bundle, edges1, None)
-        if density_fns and torch.is_grad_enabled():
+        if self.training and density_fns and torch.is_grad_enabled():
             # training (ray_samplers.py:586-593): the proposal weights handed to the interlevel loss carry the
             # gradient of the proposal network; the sample positions themselves are detached (ray_samplers.py:357)
             dens0 = density_fns[0](rs0.frustums.get_positions())
