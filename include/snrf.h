@@ -80,6 +80,10 @@ int snrf_set_pdf_u(snrf_ctx* ctx, const float* u_host, int n);
  * call on ctx, which must carry exactly n_rays rays, and is cleared by it.  NULL clears.  Not for
  * snrf_render_frame / snrf_render_camera (whole frames are eval-mode renders). */
 int snrf_set_jitter(snrf_ctx* ctx, const float* jitter, int64_t n_rays);
+/* Proposal-weight annealing of training (ProposalNetworkSampler.set_anneal, ray_samplers.py:546-548,583;
+ * nerfacto.py:248-256): the PDF sampler sees weights^anneal.  Only calls that carry jitter (training-mode sampling)
+ * use it; eval-mode calls always resample from the raw weights.  Default 1. */
+int snrf_set_anneal(snrf_ctx* ctx, float anneal);
 
 /* ---- parameters: flat fp32 tensors in tcnn order, host OR device pointers --------------------------
  * Each call converts to fp16 and packs into the kernels' layouts once (replaces tcnn's `params` tensors:

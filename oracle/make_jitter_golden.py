@@ -55,6 +55,18 @@ def main():
         "edges1": torch.cat([ray_samples.frustums.starts[..., 0], ray_samples.frustums.ends[:, -1:, 0]], -1).detach().numpy(),
         "spacing1": torch.cat([ray_samples.spacing_starts[..., 0], ray_samples.spacing_ends[:, -1:, 0]], -1).detach().numpy(),
     }
+    # second pass with annealed proposal weights (set_anneal, ray_samplers.py:546-548,583; nerfacto.py:248-256)
+    draws.clear()
+    sampler.set_anneal(0.37)
+    torch.rand = recording_rand
+    try:
+        rs2, wl2, _ = sampler(bundle, density_fns=model.density_fns)
+    finally:
+        torch.rand = real_rand
+    out["anneal"] = np.array(0.37)
+    out["jitter_anneal"] = torch.cat(draws, dim=-1).numpy()
+    out["edges1_anneal"] = torch.cat([rs2.frustums.starts[..., 0], rs2.frustums.ends[:, -1:, 0]], -1).detach().numpy()
+    out["w0_anneal"] = wl2[0][..., 0].detach().numpy()
     path = os.path.join(GOLDEN, "sampler_training.npz")
     np.savez_compressed(path, **out)
     print({k: v.shape for k, v in out.items()}, os.path.getsize(path), "bytes")

@@ -275,6 +275,7 @@ class Oracle:
         background=None,
         return_intermediates: bool = False,
         jitter: Optional[torch.Tensor] = None,
+        anneal: float = 1.0,
     ) -> Dict[str, torch.Tensor]:
         """``SAMModel.forward`` -> ``get_outputs`` in eval mode - samnerf/sam_model.py:226-314
         (collider scene_colliders.py:183-188; sampler driver ray_samplers.py:558-599)."""
@@ -294,7 +295,9 @@ class Oracle:
         dens0 = self.proposal_density(pos0)
         w0 = get_weights(ends0 - starts0, dens0)
         # anneal == 1.0 in eval (ray_samplers.py:545,583)
-        bins1, eu1 = self.pdf_sample(w0, bins0, s_near, s_far, None if jitter is None else jitter[:, 1:2])
+        # proposal-weight annealing (ray_samplers.py:583; 1.0 in eval and after the first 1000 training steps)
+        w_pdf = w0 if anneal == 1.0 else torch.pow(w0, anneal)
+        bins1, eu1 = self.pdf_sample(w_pdf, bins0, s_near, s_far, None if jitter is None else jitter[:, 1:2])
         starts, ends = eu1[:, :-1], eu1[:, 1:]
         pos = o + d * ((starts + ends) / 2)[..., None]
 

@@ -69,6 +69,7 @@ struct snrf_ctx {
   float feat_cutoff = -1.f;  // snrf_set_feature_cutoff: < 0 = kernel B on every slot (default), >= 0 = bucketed kernel B'
   const float* jitter = nullptr;  // snrf_set_jitter: training-mode draws for the next render / sample call
   int64_t jitter_rays = 0;
+  float anneal = 1.f;  // snrf_set_anneal
   std::string err;
   int64_t launches = 0;
   // proposal field
@@ -330,6 +331,12 @@ int snrf_set_pdf_u(snrf_ctx* ctx, const float* u_host, int n) {
   if (!ctx || !u_host || (n != 33 && n != 66)) return fail(ctx, SNRF_E_INVALID, "pdf_u must have 33 (or 33 + 33) entries");
   CK(cudaSetDevice(ctx->device));
   CK(cudaMemcpy(ctx->pdf_u.p, u_host, n * sizeof(float), cudaMemcpyHostToDevice));
+  return SNRF_OK;
+}
+
+int snrf_set_anneal(snrf_ctx* ctx, float anneal) {
+  if (!ctx || !(anneal >= 0.f) || anneal > 1.f) return fail(ctx, SNRF_E_INVALID, "anneal must be in [0, 1]");
+  ctx->anneal = anneal;
   return SNRF_OK;
 }
 
@@ -606,6 +613,7 @@ static int fill_march(snrf_ctx* ctx, MarchParams& M, const float* origins, const
   M.sharpen = o->sharpen;
   M.et_eps = ctx->et_eps;
   M.pdf_u_base = ctx->pdf_u.as<float>() + 33;
+  M.anneal = ctx->anneal;
   if (ctx->jitter) {  // one-shot: consumed by this call
     const float* j = ctx->jitter;
     const int64_t nj = ctx->jitter_rays;

@@ -68,6 +68,7 @@ struct MarchParams {
   float et_eps;       // early-termination transmittance threshold, 0 = exact (see march_kernel<.., ET>)
   const float* jitter;      // [N,2] training-mode single-jitter draws, or null = eval (see march_kernel<.., JIT>)
   const float* pdf_u_base;  // [33] linspace(0, 1 - 1/33, 33) without the eval-mode half-bin offset
+  float anneal;             // proposal-weight annealing exponent (training instantiation only; 1 = off)
 };
 cudaError_t launch_march(const MarchParams& P, int sm_count, cudaStream_t stream);
 

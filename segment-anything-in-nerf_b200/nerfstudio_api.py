@@ -249,11 +249,23 @@ class SAMField(_Field):
 class ProposalNetworkSampler:
     """ray_samplers.py:509-599, eval mode, one proposal iteration (samconfigs.py:84,138)."""
 
-    def __init__(self, renderer: Renderer, train_stratified: bool = True):
+    def __init__(self, renderer: Renderer, train_stratified: bool = True, update_sched: Callable = lambda step: 1):
         self.renderer = renderer
         self.training = False             # set by SAMModel.train()
         self.train_stratified = train_stratified  # ray_samplers.py:67
+        self.update_sched = update_sched  # ray_samplers.py:528,533 (nerfacto.py:196-200 builds the warm-up schedule)
         self.last_jitter: Optional[torch.Tensor] = None
+        self._anneal, self._steps_since_update, self._step = 1.0, 0, 0
+
+    def set_anneal(self, anneal: float) -> None:
+        """ray_samplers.py:546-548."""
+        self._anneal = float(anneal)
+        self.renderer.set_anneal(self._anneal)
+
+    def step_cb(self, step) -> None:
+        """ray_samplers.py:550-553."""
+        self._step = step
+        self._steps_since_update += 1
 
     def _samples(self, bundle: RayBundle, edges: torch.Tensor, spacing: Optional[torch.Tensor]) -> RaySamples:
         o, d = bundle.origins[:, None, :], bundle.directions[:, None, :]
@@ -292,11 +304,14 @@ class ProposalNetworkSampler:
         rs0 = self._samples(ray_bundle, edges0, bins.expand(n, -1) if bins.shape[0] == 1 else bins)
         rs1 = self._samples(ray_bundle, edges1, None)
         if self.training and density_fns and torch.is_grad_enabled():
-            # training (ray_samplers.py:586-593): the proposal weights handed to the interlevel loss carry the
-            # gradient of the proposal network; the sample positions themselves are detached (ray_samplers.py:357)
-            dens0 = density_fns[0](rs0.frustums.get_positions())
-            if dens0.requires_grad:
-                return rs1, [rs0.get_weights(dens0)], [rs0]
+            # training (ray_samplers.py:572,586-596): on "updated" steps the proposal weights handed to the interlevel
+            # loss carry the gradient of the proposal network; the sample positions are detached (ray_samplers.py:357)
+            updated = self._steps_since_update > self.update_sched(self._step) or self._step < 10
+            if updated:
+                self._steps_since_update = 0
+                dens0 = density_fns[0](rs0.frustums.get_positions())
+                if dens0.requires_grad:
+                    return rs1, [rs0.get_weights(dens0)], [rs0]
         return rs1, [w0[..., None]], [rs0]
 
     __call__ = generate_ray_samples

@@ -147,6 +147,10 @@ class Renderer:
         (0 = exact, the default).  See ``snrf_set_early_termination`` for the error bounds."""
         self._check(self.lib.snrf_set_early_termination(self.h, float(eps)))
 
+    def set_anneal(self, anneal: float) -> None:
+        """Proposal-weight annealing exponent for training-mode sampling (``snrf_set_anneal``; 1 = off)."""
+        self._check(self.lib.snrf_set_anneal(self.h, float(anneal)))
+
     def set_feature_cutoff(self, cutoff: float) -> None:
         """Opt-in bucketed feature kernel: only the leading slots of a ray whose sharpened weight is >= ``cutoff`` (in
         buckets of 1 / 2 / 4 / 8 / 16) are evaluated.  ``< 0`` = off (default), ``0`` = drop exact zeros only,

@@ -40,6 +40,9 @@ class FakeRenderer:
                 self.uploads.append(name)
         self.orc = Oracle(self.cfg, self.p)
 
+    def set_anneal(self, anneal):
+        self.anneal = float(anneal)
+
     def upload_density_params(self, name, t):
         from oracle.samnerf_oracle import Oracle
 

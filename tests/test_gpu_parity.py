@@ -231,3 +231,12 @@ def test_training_mode_sampler_matches_reference():
         r.sample(o[:10], d[:10], jitter=jit)
     out = r.render(o, d, get_feature=(), debug=True, jitter=jit)
     assert_mostly_close(out["_edges"], z["edges1"], TOL["edges"], 0.99, "render() with jitter uses the same samples")
+    # annealed proposal weights in front of the PDF sampler (set_anneal, ray_samplers.py:583); reported weights stay raw
+    r.set_anneal(float(z["anneal"]))
+    try:
+        w0a, edges_a, _ = r.sample(o, d, jitter=torch.from_numpy(z["jitter_anneal"]))
+        assert torch.equal(r.sample(o, d)[1], edges_eval)  # eval-mode calls ignore the exponent
+    finally:
+        r.set_anneal(1.0)
+    assert_mostly_close(w0a, z["w0_anneal"], TOL["weights"], FRAC_SMOOTH, "raw proposal weights under annealing")
+    assert_mostly_close(edges_a, z["edges1_anneal"], TOL["edges"], 0.99, "nerf bin edges under annealing")

@@ -72,6 +72,11 @@ def test_training_mode_sampler_matches_reference():
     np.testing.assert_allclose(res["_w0"].numpy(), z["w0"], rtol=1e-5, atol=1e-7)
     np.testing.assert_allclose(res["_bins1"].numpy(), z["spacing1"], rtol=1e-5, atol=1e-6)
     np.testing.assert_allclose(res["_eu1"].numpy(), z["edges1"], rtol=2e-5, atol=1e-6)
+    # annealed proposal weights feed the PDF sampler, the reported weights stay raw (ray_samplers.py:583-593)
+    ja = torch.from_numpy(z["jitter_anneal"])
+    ra = orc.render_rays(o, d, get_feature=(), return_intermediates=True, jitter=ja, anneal=float(z["anneal"]))
+    np.testing.assert_allclose(ra["_w0"].numpy(), z["w0_anneal"], rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(ra["_eu1"].numpy(), z["edges1_anneal"], rtol=2e-5, atol=1e-6)
     # and the jitter really moved the samples away from the eval-mode positions
     ev = orc.render_rays(o, d, get_feature=(), return_intermediates=True)
     assert float((ev["_eu1"] - res["_eu1"]).abs().max()) > 1e-3
