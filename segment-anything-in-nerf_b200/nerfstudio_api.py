@@ -302,7 +302,12 @@ class ProposalNetworkSampler:
         s_near, s_far = sp(nears.to(w0.device)), sp(fars.to(w0.device))
         edges0 = sp_inv(bins * s_far + (1 - bins) * s_near)
         rs0 = self._samples(ray_bundle, edges0, bins.expand(n, -1) if bins.shape[0] == 1 else bins)
-        rs1 = self._samples(ray_bundle, edges1, None)
+        # level-1 spacing bins (what interlevel_loss / distortion_loss read through ray_samples_to_sdist,
+        # model_components/losses.py:100-143): the kernel reports euclidean edges; the spacing transform is invertible
+        spacing1 = (sp(edges1) - s_near) / (s_far - s_near)
+        rs1 = self._samples(ray_bundle, edges1, spacing1)
+        to_euclidean = lambda x: sp_inv(x * s_far + (1 - x) * s_near)  # noqa: E731  ray_samplers.py:115
+        rs0.spacing_to_euclidean_fn = rs1.spacing_to_euclidean_fn = to_euclidean
         if self.training and density_fns and torch.is_grad_enabled():
             # training (ray_samplers.py:572,586-596): on "updated" steps the proposal weights handed to the interlevel
             # loss carry the gradient of the proposal network; the sample positions are detached (ray_samplers.py:357)

@@ -408,6 +408,12 @@ def test_training_step_gradients_match_autograd_end_to_end(monkeypatch):
     loss = ((out["rgb"] - target) ** 2).mean() + (out["weights_list"][0] * c0).mean() + (out["weights_list"][1] * c1).mean()
     loss.backward()
 
+    # the sample lists carry what the reference's interlevel / distortion losses read (losses.py:100-143)
+    rs0, rs1 = out["ray_samples_list"]
+    sd1 = torch.cat([rs1.spacing_starts[..., 0], rs1.spacing_ends[..., -1:, 0]], dim=-1)
+    assert sd1.shape == (48, 33) and bool((sd1[:, 1:] >= sd1[:, :-1] - 1e-6).all()) and float(sd1.min()) >= -1e-6 and float(sd1.max()) <= 1 + 1e-6
+    assert torch.allclose(rs1.spacing_to_euclidean_fn(sd1), torch.cat([rs1.frustums.starts[..., 0], rs1.frustums.ends[..., -1:, 0]], -1),
+                          rtol=1e-4, atol=1e-5)
     # reference: same positions (training near plane 0.05, detached bins), oracle functions under autograd
     names = list(FakeRenderer.DENSITY_PARAMS)
     p = {k: v.clone().requires_grad_(k in names) for k, v in params.items()}
