@@ -221,6 +221,10 @@ def run_native(args):
     # peer-mapped pointers), overlapped with the next chunk's compute; a symmetric-memory barrier ends the frame.
     # Fallback / comparison: NCCL all-gather of the rendered tiles (--gather nccl).
     gather_mode, symm, full = "single", None, {}
+    if args.gather == "auto":
+        # what was measured: copy engines at N = 2 and 4, the fused multicast stores at N = 8 (278.9 Mrays/s,
+        # profiles/r01_multi_gpu.txt; the copy-engine mode has not been run on 8 GPUs yet)
+        args.gather = "mc" if world >= 8 else "dma"
     if world > 1:
         gather_mode = "nccl"
         if args.gather != "nccl":
@@ -230,7 +234,7 @@ def run_native(args):
                 big = symm_mem.empty(n_all * sum(names.values()), dtype=torch.float32, device=dev)
                 symm = symm_mem.rendezvous(big, dist.group.WORLD.group_name)
                 mc = int(getattr(symm, "multicast_ptr", 0) or 0) if args.gather == "mc" else 0
-                if args.gather in ("dma", "auto"):
+                if args.gather == "dma":
                     r.set_replication_mode("dma")
                 off = 0
                 for k, c in names.items():
@@ -239,7 +243,7 @@ def run_native(args):
                     r.set_replication(k, full[k], () if mc else peers, mc + off * 4 if mc else 0)
                     off += n_all * c
                 gather_mode = ("fused multimem.st (NVSwitch multicast)" if mc else
-                               "copy engines (cudaMemcpyAsync to peer buffers per chunk)" if args.gather in ("dma", "auto") else
+                               "copy engines (cudaMemcpyAsync to peer buffers per chunk)" if args.gather == "dma" else
                                "fused peer stores (NVLink P2P)")
             except Exception as e:  # no symmetric memory on this box: say so and use NCCL
                 if rank == 0:
