@@ -263,6 +263,12 @@ int snrf_patch_aggregate_backward(snrf_ctx* ctx, const float* feat_in, int64_t n
 int snrf_field_backward(snrf_ctx* ctx, int which, const float* xyz, const float* dirs, int64_t n,
                         const float* d_density, const float* d_rgb, float* grad_base, float* grad_head, void* stream);
 
+/* Top-k pick + sharpening of the feature samples as a stand-alone ray op (samnerf/sam_model.py:244-255; the fused
+ * snrf_render does the same inside the march kernel): weights / starts / ends [N,S] -> sam_t[N,k] = start + end of the
+ * picked samples, sam_w[N,k] = w^sharpen renormalised, slots in descending weight order (ties by sample index). */
+int snrf_pick_samples(snrf_ctx* ctx, const float* weights, const float* starts, const float* ends, int64_t n, int S,
+                      int k, float sharpen, float* sam_t, float* sam_w, void* stream);
+
 /* Backward of the two ray-wise ops that carry gradients in training (torch autograd in the reference):
  * mode 0  RaySamples.get_weights (rays.py:141-163): a = deltas[N,S], b = densities[N,S], g = dL/dweights[N,S]
  *         -> out_a = dL/ddensities[N,S] (out_b unused; deltas are detached, ray_samplers.py:357);  S <= 64

@@ -89,6 +89,7 @@ SYMBOLS = {
     "snrf_feature_backward": (_I, [_P, _I, _P, _P, _P, _P, _L, _P, _P, _P, _P, _P, _P]),
     "snrf_patch_aggregate_backward": (_I, [_P, _P, _L, _I, _P, _P, _P, _P, _P, _P, _P]),
     "snrf_field_backward": (_I, [_P, _I, _P, _P, _L, _P, _P, _P, _P, _P]),
+    "snrf_pick_samples": (_I, [_P, _P, _P, _P, _L, _I, _I, _F, _P, _P, _P]),
     "snrf_ray_op_backward": (_I, [_P, _I, _P, _P, _P, _P, _P, _L, _I, _I, _P, _P]),
     "snrf_launch_count": (_L, [_P]),
     "snrf_set_timing": (_I, [_P, _I]),

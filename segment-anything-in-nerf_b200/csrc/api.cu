@@ -1189,6 +1189,18 @@ int snrf_field_backward(snrf_ctx* ctx, int which, const float* xyz, const float*
   return SNRF_OK;
 }
 
+int snrf_pick_samples(snrf_ctx* ctx, const float* weights, const float* starts, const float* ends, int64_t n, int S,
+                      int k, float sharpen, float* sam_t, float* sam_w, void* stream) {
+  if (!ctx) return SNRF_E_INVALID;
+  if (!weights || !starts || !ends || !sam_t || !sam_w || n < 0 || S < 1 || k < 1 || k > S)
+    return fail(ctx, SNRF_E_INVALID, "bad argument");
+  if (n == 0) return SNRF_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CK(cudaSetDevice(ctx->device));
+  LAUNCH(launch_pick_samples(weights, starts, ends, n, S, k, sharpen, sam_t, sam_w, s));
+  return SNRF_OK;
+}
+
 int snrf_ray_op_backward(snrf_ctx* ctx, int mode, const float* a, const float* b, const float* g, float* out_a,
                          float* out_b, int64_t n, int S, int bg_mode, const float* bg_host, void* stream) {
   if (!ctx) return SNRF_E_INVALID;

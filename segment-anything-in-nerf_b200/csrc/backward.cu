@@ -86,6 +86,12 @@ __global__ void conv_bias_grad_kernel(const float* dY, int64_t rows, float* g_b,
   if (i < items) conv_bias_grad_one(dY, rows, g_b, i);
 }
 
+__global__ void pick_samples_kernel(const float* w, const float* starts, const float* ends, int S, int k, float sharpen,
+                                    float* sam_t, float* sam_w, int64_t n) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) pick_samples_one(w, starts, ends, S, k, sharpen, sam_t, sam_w, i);
+}
+
 // executor of the backward chains of backward.cuh: every step is one kernel launch on `s`
 struct DeviceExec {
   cudaStream_t s;
@@ -145,6 +151,13 @@ cudaError_t launch_weights_bwd(const float* deltas, const float* dens, const flo
   if (n <= 0) return cudaSuccess;
   if (S < 1 || S > kMaxRaySamples) return cudaErrorInvalidValue;
   weights_bwd_kernel<<<blocks_for(n), kThreads, 0, stream>>>(deltas, dens, g_w, d_dens, S, n);
+  return cudaGetLastError();
+}
+cudaError_t launch_pick_samples(const float* w, const float* starts, const float* ends, int64_t n, int S, int k,
+                                float sharpen, float* sam_t, float* sam_w, cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  if (S < 1 || k < 1 || k > S) return cudaErrorInvalidValue;
+  pick_samples_kernel<<<blocks_for(n), kThreads, 0, stream>>>(w, starts, ends, S, k, sharpen, sam_t, sam_w, n);
   return cudaGetLastError();
 }
 cudaError_t launch_rgb_bwd(const float* rgb, const float* w, const float* g_out, int bg_fixed, const float* bg,

@@ -372,6 +372,30 @@ SNRF_HD void rgb_bwd_one(const float* rgb, const float* w, const float* g_out, i
   for (int ch = 0; ch < 3; ++ch) d_rgb[(ray * S + i) * 3 + ch] = (wi + extra) * G[ch];
   d_w[ray * S + i] = G[0] * (c[0] - b0) + G[1] * (c[1] - b1) + G[2] * (c[2] - b2);
 }
+// Top-k pick + sharpening of the feature samples (samnerf/sam_model.py:244-255) as a stand-alone ray op, so that the
+// training path can take its picks from the weights it differentiates instead of from a second fused render:
+// rank by weight (ties by sample index, like march.cu), keep rank < k, w^sharpen, renormalise; slot = rank, i.e.
+// descending weight.  sam_t = start + end of the picked sample (2 x midpoint).                     item = ray
+SNRF_HD void pick_samples_one(const float* w, const float* starts, const float* ends, int S, int k, float sharpen,
+                              float* sam_t, float* sam_w, int64_t ray) {
+  const float* wr = w + ray * S;
+  float tot = 0.f;
+  for (int i = 0; i < S; ++i) {
+    int rank = 0;
+    for (int j = 0; j < S; ++j) rank += (wr[j] > wr[i]) || (wr[j] == wr[i] && j < i);
+    if (rank < k) tot += powf(wr[i], sharpen);
+  }
+  for (int i = 0; i < S; ++i) {
+    int rank = 0;
+    for (int j = 0; j < S; ++j) rank += (wr[j] > wr[i]) || (wr[j] == wr[i] && j < i);
+    if (rank < k) {
+      sam_t[ray * k + rank] = starts[ray * S + i] + ends[ray * S + i];
+      sam_w[ray * k + rank] = powf(wr[i], sharpen) / tot;
+    }
+  }
+}
+cudaError_t launch_pick_samples(const float* w, const float* starts, const float* ends, int64_t n, int S, int k,
+                                float sharpen, float* sam_t, float* sam_w, cudaStream_t stream);
 cudaError_t launch_weights_bwd(const float* deltas, const float* dens, const float* g_w, float* d_dens, int64_t n, int S,
                                cudaStream_t stream);
 cudaError_t launch_rgb_bwd(const float* rgb, const float* w, const float* g_out, int bg_fixed, const float* bg,

@@ -647,7 +647,7 @@ class SAMModel:
     def _get_outputs_training(self, ray_bundle: RayBundle, get_feature, fast: bool):
         """sam_model.py:226-301 in training mode, component by component like the reference: the samplers' positions
         are detached (ray_samplers.py:357), the two density fields / get_weights / the RGB composite are autograd
-        Functions over libsnrf kernels, and the feature branch takes the top-k picks of the fused render."""
+        Functions over libsnrf kernels, and the feature branch takes its top-k picks from those same weights."""
         cfg, r = self.config, self.renderer
         self._sync_params()
         if ray_bundle.camera_indices is None:  # the field insists on them (nerfacto_field.py:273-275)
@@ -666,10 +666,8 @@ class SAMModel:
         out["weights_list"], out["ray_samples_list"] = weights_list, ray_samples_list
         feats = [f for f in get_feature if Renderer.FEATURE_PARAMS[f][0] in self.params]
         if feats:
-            with torch.no_grad():  # top-k + sharpen of the fused kernel (sam_model.py:244-255)
-                picks = r.render(ray_bundle.origins, ray_bundle.directions, ray_bundle.nears, ray_bundle.fars,
-                                 get_feature=(), fast=True, picks=True, jitter=self.proposal_sampler.last_jitter)
-            sam_t, sam_w = picks["_sam_t"], picks["_sam_w"]
+            # top-k + sharpen on the (detached) weights of this very pass (sam_model.py:244-255)
+            sam_t, sam_w = r.pick_samples(weights, ray_samples.frustums.starts, ray_samples.frustums.ends)
             o = r._prep(ray_bundle.origins, 3)
             d = r._prep(ray_bundle.directions, 3)
             for which in feats:

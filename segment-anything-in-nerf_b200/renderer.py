@@ -513,6 +513,18 @@ class Renderer:
             grads["base"].data_ptr(), _ptr(grads.get("head")), self.stream))
         return grads
 
+    def pick_samples(self, weights: torch.Tensor, starts: torch.Tensor, ends: torch.Tensor):
+        """Top-k + sharpen of the feature samples (sam_model.py:244-255) from ``weights / starts / ends [N,S(,1)]``:
+        returns ``(sam_t[N,k], sam_w[N,k])`` in the layout ``feature_forward`` takes."""
+        cfg = self.cfg
+        n, s = weights.shape[0], weights.shape[1]
+        w, a, b = (t.detach().to(device=self.device, dtype=torch.float32).reshape(n, s).contiguous() for t in (weights, starts, ends))
+        k = cfg.num_sam_samples
+        sam_t, sam_w = torch.empty(n, k, device=self.device), torch.empty(n, k, device=self.device)
+        self._check(self.lib.snrf_pick_samples(self.h, w.data_ptr(), a.data_ptr(), b.data_ptr(), n, s, k,
+                                               float(cfg.sharpening_temperature), sam_t.data_ptr(), sam_w.data_ptr(), self.stream))
+        return sam_t, sam_w
+
     def ray_op_backward(self, mode: int, a, b, g, background=None):
         """Backward of ``ray_op`` mode 0 (get_weights: returns ``d_densities``) or mode 3 (RGB composite: returns
         ``(d_rgb_samples, d_weights)``)."""

@@ -135,6 +135,13 @@ int emu_jittered_bins(const float* t_rand, long long n, int n_bins, float* out) 
   return 0;
 }
 
+// mirrors snrf_pick_samples
+int emu_pick_samples(const float* w, const float* starts, const float* ends, long long n, int S, int k, float sharpen,
+                     float* sam_t, float* sam_w) {
+  for (int64_t i = 0; i < n; ++i) pick_samples_one(w, starts, ends, S, k, sharpen, sam_t, sam_w, i);
+  return 0;
+}
+
 // mirror snrf_ray_op_backward modes 0 and 3
 int emu_weights_backward(const float* deltas, const float* dens, const float* g_w, float* d_dens, long long n, int S) {
   for (int64_t i = 0; i < n; ++i) weights_bwd_one(deltas, dens, g_w, d_dens, S, i);

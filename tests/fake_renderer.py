@@ -82,6 +82,19 @@ class FakeRenderer:
                 return composite_rgb(a, b, background)
             return (a * b[..., None]).sum(-2)
 
+    def pick_samples(self, weights, starts, ends):
+        from emu.build_emu import load
+
+        n, s = weights.shape[0], weights.shape[1]
+        k = self.cfg.num_sam_samples
+        arr = lambda t: np.ascontiguousarray(t.detach().reshape(n, s).numpy(), np.float32)
+        ptr = lambda x: x.ctypes.data_as(C.c_void_p)
+        keep = [arr(weights), arr(starts), arr(ends)]
+        sam_t, sam_w = np.zeros((n, k), np.float32), np.zeros((n, k), np.float32)
+        load().emu_pick_samples(ptr(keep[0]), ptr(keep[1]), ptr(keep[2]), C.c_longlong(n), s, k,
+                                C.c_float(self.cfg.sharpening_temperature), ptr(sam_t), ptr(sam_w))
+        return torch.from_numpy(sam_t), torch.from_numpy(sam_w)
+
     def ray_op_backward(self, mode, a, b, g, background=None):
         from emu.build_emu import load
 

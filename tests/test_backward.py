@@ -622,3 +622,34 @@ def test_gpu_conv_head_backward_matches_autograd():
     for name, w in zip(names, ws):
         _assert_grad_close(g[name].cpu(), w.grad, "d " + name)
     _assert_grad_close(d_feat.cpu(), feat.grad, "d feat")
+
+
+def test_pick_samples_body_matches_reference_topk():
+    """Stand-alone top-k + sharpen (sam_model.py:244-255) against torch.topk / pow / normalise; slot order is
+    descending weight, which is what the bucketed forward kernel and the compact backward rows rely on."""
+    from emu.build_emu import load
+
+    n, S, k, T = 500, 32, 16, 10.0
+    gen = torch.Generator().manual_seed(3)
+    w = torch.rand(n, S, generator=gen) ** 6
+    w[::5, 20:] = 0.0                       # saturated rays: exact ties at zero, broken by sample index
+    starts = torch.rand(n, S, generator=gen)
+    ends = starts + torch.rand(n, S, generator=gen)
+    arr = lambda t: np.ascontiguousarray(t.numpy(), np.float32)
+    ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+    keep = [arr(w), arr(starts), arr(ends)]
+    sam_t, sam_w = np.zeros((n, k), np.float32), np.zeros((n, k), np.float32)
+    load().emu_pick_samples(ptr(keep[0]), ptr(keep[1]), ptr(keep[2]), C.c_longlong(n), S, k, C.c_float(T), ptr(sam_t), ptr(sam_w))
+    ref_w, ids = torch.topk(w, k, dim=-1, sorted=True)  # values descending; the reference uses sorted=False (a set)
+    ref_w = ref_w ** T
+    ref_w = ref_w / ref_w.sum(-1, keepdim=True)
+    got_w, got_t = torch.from_numpy(sam_w), torch.from_numpy(sam_t)
+    assert torch.allclose(got_w, ref_w, rtol=1e-5, atol=1e-12)
+    assert bool((got_w[:, :-1] >= got_w[:, 1:]).all())
+    # slot = rank by (weight descending, sample index ascending): ties - e.g. the zero-weight tail of a saturated ray -
+    # go to the lower index, exactly like the march kernel; torch.topk agrees as a set wherever the k-th weight is untied
+    ids_ranked = torch.sort(-w, dim=-1, stable=True).indices[:, :k]
+    assert torch.equal(got_t, torch.gather(starts + ends, 1, ids_ranked))
+    untied = ref_w[:, -1] > 0
+    assert untied.any() and (~untied).any()
+    assert torch.equal(ids_ranked[untied].sort(-1).values, ids[untied].sort(-1).values)
