@@ -84,6 +84,16 @@ class SAMNeRFConfig:
     far_plane: float = 1000.0  # nerfacto.py:73
     histogram_padding: float = 0.01  # ray_samplers.py:268
     eval_num_rays_per_chunk: int = 1 << 15  # samconfigs.py:79,133
+    # training-side knobs (nerfacto.py:110-125, sam_model.py:143-147)
+    interlevel_loss_mult: float = 1.0
+    distortion_loss_mult: float = 0.002
+    sam_loss_weight: float = 1.0
+    clipseg_loss_weight: float = 1.0
+    use_proposal_weight_anneal: bool = True
+    proposal_weights_anneal_slope: float = 10.0
+    proposal_weights_anneal_max_num_iters: int = 1000
+    proposal_warmup: int = 5000
+    proposal_update_every: int = 5
     # proposal density field (nerfacto.py:105, density_fields.py:50-100)
     proposal_grid: GridConfig = field(default_factory=lambda: GridConfig(5, 2, 17, 16, 128))
     proposal_hidden: int = 16

@@ -542,7 +542,10 @@ class SAMModel:
         self.collider = NearFarCollider(near_plane=0.05, far_plane=config.far_plane)
         self.proposal_networks = [HashMLPDensityField(r)]
         self.density_fns = [n.density_fn for n in self.proposal_networks]
-        self.proposal_sampler = ProposalNetworkSampler(r)
+        from .training import proposal_update_schedule
+
+        self.proposal_sampler = ProposalNetworkSampler(
+            r, update_sched=proposal_update_schedule(config.proposal_warmup, config.proposal_update_every))
         self.field = TCNNNerfactoField(r)
         self.sam_field = SAMField(r) if config.distill_sam else None
         self.renderer_rgb = RGBRenderer(r, background_color="last_sample")
@@ -618,6 +621,31 @@ class SAMModel:
         for name, p in getattr(self, "params", {}).items():
             sd[name] = p.detach().cpu().clone()
         return sd
+
+    # nerfacto.py:316-344 + sam_model.py:316-328
+    def get_metrics_dict(self, outputs, batch) -> Dict[str, torch.Tensor]:
+        from .training import metrics_dict
+
+        return metrics_dict(outputs, batch, self.training)
+
+    def get_loss_dict(self, outputs, batch, metrics_dict=None) -> Dict[str, torch.Tensor]:
+        from .training import loss_dict
+
+        if self.training:
+            assert metrics_dict is not None and "distortion" in metrics_dict  # nerfacto.py:332
+        return loss_dict(outputs, batch, metrics_dict or {}, self.config, self.training)
+
+    # nerfacto.py:242-271: the two per-iteration callbacks of the trainer
+    def before_train_iteration(self, step: int) -> None:
+        from .training import proposal_anneal
+
+        if self.config.use_proposal_weight_anneal:
+            self.proposal_sampler.set_anneal(proposal_anneal(step, self.config.proposal_weights_anneal_max_num_iters,
+                                                             self.config.proposal_weights_anneal_slope))
+
+    def after_train_iteration(self, step: int) -> None:
+        if self.config.use_proposal_weight_anneal:
+            self.proposal_sampler.step_cb(step)
 
     def _sync_params(self) -> None:
         """Push parameters an optimiser step has changed (tensor version counters) back into the library's packed

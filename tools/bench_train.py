@@ -56,13 +56,15 @@ def main():
     for step in range(args.warmup + args.steps):
         opt.zero_grad(set_to_none=False)
         e0 = ev()
+        m.before_train_iteration(step)
         out = m(bundle, get_feature=["sam"])
-        loss = torch.nn.functional.mse_loss(out["rgb"], image) + \
-            torch.nn.functional.mse_loss(out["sam"], feat, reduction="none").mean(dim=-1).nanmean()
+        batch = {"image": image, "sam": feat}
+        loss = sum(m.get_loss_dict(out, batch, m.get_metrics_dict(out, batch)).values())  # rgb + interlevel + distortion + sam
         e1 = ev()
         loss.backward()
         e2 = ev()
         opt.step()
+        m.after_train_iteration(step)
         e3 = ev()
         torch.cuda.synchronize()
         losses.append(float(loss.detach()))
