@@ -566,6 +566,18 @@ class SAMModel:
         self.renderer.load_params(self._loaded)
         self.params = {}  # trainable copies are (re)built by train()
 
+    @classmethod
+    def from_checkpoint(cls, path: str, device: int = 0, engine: str = "tcgen05", base: Optional[SAMNeRFConfig] = None):
+        """Build the model from a reference training checkpoint (``step-*.ckpt`` file or its directory; layout
+        nerfstudio/engine/trainer.py:389-400): the configuration is inferred from the tensors it carries."""
+        from .checkpoint import load_checkpoint
+
+        cfg, params, step = load_checkpoint(path, base)
+        model = cls(cfg, device=device, engine=engine)
+        model.load_state_dict(params)
+        model.step = step
+        return model
+
     # ---- training (SURVEY 8 f-1) -------------------------------------------------------------------
     def train(self, mode: bool = True):
         """Training mode: every flat hot-path tensor becomes an fp32 ``nn.Parameter`` on the device whose gradient

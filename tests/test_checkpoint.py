@@ -131,3 +131,28 @@ def test_feature_files(tmp_path):
     assert ck.crop_sam_embedding(emb, 1060, 1600).shape[-2:] == (43, 64)
     assert ck.crop_sam_embedding(emb, 1600, 1060).shape[-2:] == (64, 43)
     assert ck.crop_sam_embedding(emb, 800, 800).shape[-2:] == (64, 64)
+
+
+def test_model_from_checkpoint(tmp_path, monkeypatch):
+    """SAMModel.from_checkpoint: configuration inferred from the file, parameters handed to the renderer; after a
+    training step, state_dict() -> save_checkpoint -> from_checkpoint carries the trained tensors."""
+    import samnerf_b200.nerfstudio_api as api
+    from fake_renderer import FakeRenderer
+
+    monkeypatch.setattr(api, "Renderer", FakeRenderer)
+    cfg = SAMNeRFConfig.tiny(clipseg=False, patch_size=1)
+    params = {k: v for k, v in make_synthetic_params(cfg, "scene", 4).items() if not k.startswith("conv_head")}
+    path = ck.save_checkpoint(str(tmp_path) + os.sep, params, step=1234, ddp=True)
+    m = api.SAMModel.from_checkpoint(str(tmp_path), base=SAMNeRFConfig.tiny(clipseg=False, patch_size=1))
+    assert m.step == 1234 and m.config == cfg and path.endswith("step-000001234.ckpt")
+    for k, v in params.items():
+        assert torch.equal(m.renderer.p[k], v), k
+    m.train()
+    with torch.no_grad():
+        m.params["sam_field.sam_net.params"].add_(0.25)
+    sd = m.state_dict()
+    ck.save_checkpoint(str(tmp_path) + os.sep, sd, step=1300)
+    m2 = api.SAMModel.from_checkpoint(str(tmp_path), base=SAMNeRFConfig.tiny(clipseg=False, patch_size=1))
+    assert m2.step == 1300
+    assert torch.allclose(m2.renderer.p["sam_field.sam_net.params"], params["sam_field.sam_net.params"] + 0.25)
+    assert torch.equal(m2.renderer.p["field.mlp_base.params"], params["field.mlp_base.params"])
