@@ -659,6 +659,22 @@ class SAMModel:
         if self.config.use_proposal_weight_anneal:
             self.proposal_sampler.step_cb(step)
 
+    def all_reduce_gradients(self, group=None) -> None:
+        """Data-parallel training as the reference runs it (one process per GPU under torch DDP, samnerf/train.py:171-199;
+        DDP averages every gradient across ranks after backward): call between ``backward()`` and ``optimizer.step()``.
+        The parameters are a dozen large flat tensors, so one ``all_reduce`` per tensor is already bucketed."""
+        import torch.distributed as dist
+
+        if not (dist.is_available() and dist.is_initialized()):
+            return
+        world = dist.get_world_size(group)
+        if world == 1:
+            return
+        for p in getattr(self, "params", {}).values():
+            if p.grad is not None:
+                dist.all_reduce(p.grad, op=dist.ReduceOp.SUM, group=group)
+                p.grad.div_(world)
+
     def _sync_params(self) -> None:
         """Push parameters an optimiser step has changed (tensor version counters) back into the library's packed
         fp16 copies - the re-upload SURVEY 8 b asks for."""
