@@ -211,18 +211,23 @@ typedef struct snrf_camera {
   int32_t has_distortion; /* 0: distortion_params is None                          */
   float distortion[6];    /* k1 k2 k3 k4 p1 p2 (camera_utils.py:320-325)           */
   float c2w[12];          /* camera_to_worlds, row-major 3x4                       */
+  int32_t has_aabb;       /* viewer crop box (generate_rays(aabb_box=...), cameras.py:463-482): nears / fars of every
+                             ray = its intersection with the box (nerfstudio/utils/math.py:201-238)                 */
+  float aabb[6];          /* x_min y_min z_min x_max y_max z_max                   */
 } snrf_camera;
 
 /* Rays through the pixel grid rows x cols of `cam` (HOST pointers; NULL = every row / column of the image, in
  * which case n_rows / n_cols must equal height / width).  Ray order: row-major when patch <= 1, else patch-major
  * over patch x patch blocks with row-major order inside a block (n_rows, n_cols divisible by patch) - the order
- * sam_model.py:376-379 produces.  origins[n,3], dirs[n,3] (unit), pixel_area[n] or NULL; n = n_rows * n_cols. */
+ * sam_model.py:376-379 produces.  origins[n,3], dirs[n,3] (unit), pixel_area[n] or NULL; nears[n] / fars[n]: written
+ * when cam->has_aabb (else ignored, may be NULL); n = n_rows * n_cols. */
 int snrf_generate_rays(snrf_ctx* ctx, const snrf_camera* cam, const int32_t* rows_host, int n_rows,
                        const int32_t* cols_host, int n_cols, int patch, float* origins, float* dirs,
-                       float* pixel_area, void* stream);
+                       float* pixel_area, float* nears, float* fars, void* stream);
 /* snrf_generate_rays into library scratch followed by snrf_render_frame over those rays: one call per loop of
  * SAMModel.get_outputs_for_camera_ray_bundle (sam_model.py:354-418).  With SNRF_PATCH in `flags` the ray order is
- * patch-major with p = opts->patch_size and sam is [n/p^2, 256]. */
+ * patch-major with p = opts->patch_size and sam is [n/p^2, 256].  With cam->has_aabb the rays are rendered between
+ * their crop-box intersections (the collider is bypassed, scene_colliders.py:40-44). */
 int snrf_render_camera(snrf_ctx* ctx, const snrf_camera* cam, const int32_t* rows_host, int n_rows,
                        const int32_t* cols_host, int n_cols, int64_t chunk, uint32_t flags,
                        const snrf_render_opts* opts, float* rgb, float* depth, float* acc, float* prop_depth,

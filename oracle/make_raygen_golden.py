@@ -15,6 +15,9 @@ import torch
 from oracle.make_golden import GOLDEN, _install_stubs
 
 
+AABB = torch.tensor([[-0.4, -0.5, -0.3], [0.5, 0.35, 0.45]])  # crop box used for every camera
+
+
 def cases():
     """name -> camera description (shared with tests/test_raygen.py through the npz itself)."""
     from samnerf_b200.synthetic import look_at
@@ -55,7 +58,15 @@ def main():
         xs = torch.linspace(0, c["w"] - 1, 8, dtype=torch.long)
         sub = rb[ys[:, None], xs[None, :]]
         out[f"{name}.sub_directions"] = sub.directions.numpy()
-        print(name, rb.directions.shape, "nan:", int(torch.isnan(rb.directions).sum()))
+        # viewer crop box: nears / fars from the ray-box intersection (cameras.py:463-482, utils/math.py:201-238)
+        from nerfstudio.data.scene_box import SceneBox
+
+        rbx = cam.generate_rays(camera_indices=0, keep_shape=True, aabb_box=SceneBox(aabb=AABB.clone()))
+        out[f"{name}.aabb_nears"] = rbx.nears.numpy()
+        out[f"{name}.aabb_fars"] = rbx.fars.numpy()
+        print(name, rb.directions.shape, "nan:", int(torch.isnan(rb.directions).sum()),
+              "box hits:", int((rbx.nears < 1e9).sum()), "of", rbx.nears.numel())
+    out["aabb"] = AABB.flatten().numpy()
     path = os.path.join(GOLDEN, "raygen.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes")

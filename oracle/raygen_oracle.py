@@ -99,3 +99,18 @@ def feature_grid_pixels(h: int, w: int, fh: int, fw: int, p: int) -> Tuple[torch
     hind = hind.reshape(fh, p, fw, p).transpose(1, 2).flatten()
     wind = wind.reshape(fh, p, fw, p).transpose(1, 2).flatten()
     return hind, wind
+
+
+def intersect_aabb(origins: torch.Tensor, directions: torch.Tensor, aabb: torch.Tensor, max_bound: float = 1e10,
+                   invalid_value: float = 1e10) -> Tuple[torch.Tensor, torch.Tensor]:
+    """``_intersect_aabb`` - nerfstudio/utils/math.py:201-238 (the path taken when nerfacc is absent, :260-270):
+    slab test, distances clamped to ``[0, max_bound]``, a miss reports ``invalid_value`` twice.  ``aabb[6]`` =
+    ``[x_min y_min z_min x_max y_max z_max]``; used by ``Cameras.generate_rays(aabb_box=...)`` (cameras.py:463-482)."""
+    tx_min = (aabb[:3] - origins) / directions
+    tx_max = (aabb[3:] - origins) / directions
+    t_min = torch.max(torch.min(tx_min, tx_max), dim=-1).values
+    t_max = torch.min(torch.max(tx_min, tx_max), dim=-1).values
+    t_min = torch.clamp(t_min, min=0, max=max_bound)
+    t_max = torch.clamp(t_max, min=0, max=max_bound)
+    cond = t_max <= t_min
+    return torch.where(cond, invalid_value, t_min), torch.where(cond, invalid_value, t_max)

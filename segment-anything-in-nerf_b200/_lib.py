@@ -48,7 +48,7 @@ class DebugOut(C.Structure):
 class Camera(C.Structure):
     _fields_ = [("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float), ("width", C.c_int32),
                 ("height", C.c_int32), ("camera_type", C.c_int32), ("has_distortion", C.c_int32),
-                ("distortion", C.c_float * 6), ("c2w", C.c_float * 12)]
+                ("distortion", C.c_float * 6), ("c2w", C.c_float * 12), ("has_aabb", C.c_int32), ("aabb", C.c_float * 6)]
 
 
 # every symbol include/snrf.h declares: name -> (restype, argtypes)
@@ -82,7 +82,7 @@ SYMBOLS = {
     "snrf_set_pipeline": (_I, [_P, _I]),
     "snrf_set_replication": (_I, [_P, _I, _P, _L, _P, C.POINTER(C.c_void_p), _I]),
     "snrf_set_replication_mode": (_I, [_P, _I]),
-    "snrf_generate_rays": (_I, [_P, C.POINTER(Camera), _P, _I, _P, _I, _I, _P, _P, _P, _P]),
+    "snrf_generate_rays": (_I, [_P, C.POINTER(Camera), _P, _I, _P, _I, _I, _P, _P, _P, _P, _P, _P]),
     "snrf_render_camera": (_I, [_P, C.POINTER(Camera), _P, _I, _P, _I, _L, _U, C.POINTER(RenderOpts), _P, _P, _P, _P,
                                 _P, _P, _P]),
     "snrf_feature_forward": (_I, [_P, _I, _P, _P, _P, _P, _L, _P, _P, _P]),

@@ -106,7 +106,7 @@ struct snrf_ctx {
   // misc
   DevBuf pdf_u;
   DevBuf sam_t[2], sam_w[2], hbar[2][2], feat_f16, hid_f16, q_feat, q_h1, q_h2, q_sel, q_x;
-  DevBuf cam_rows, cam_cols, cam_o, cam_d;  // snrf_generate_rays / snrf_render_camera
+  DevBuf cam_rows, cam_cols, cam_o, cam_d, cam_near, cam_far;  // snrf_generate_rays / snrf_render_camera
   DevBuf bwd_scratch, bwd_sink;             // snrf_feature_backward
   DevBuf bucket_lists[2], bucket_counts[2]; // bucketed feature kernel, per pipeline slot
 };
@@ -288,6 +288,7 @@ void snrf_ctx_destroy(snrf_ctx* ctx) {
   for (DevBuf* b : bufs) b->release();
   ctx->sam_t[1].release(); ctx->sam_w[1].release();
   ctx->cam_rows.release(); ctx->cam_cols.release(); ctx->cam_o.release(); ctx->cam_d.release();
+  ctx->cam_near.release(); ctx->cam_far.release();
   ctx->conv_w_rm[0].release(); ctx->conv_w_rm[1].release();
   ctx->bwd_scratch.release(); ctx->bwd_sink.release();
   for (int i = 0; i < 2; ++i) { ctx->bucket_lists[i].release(); ctx->bucket_counts[i].release(); }
@@ -971,6 +972,8 @@ static int fill_raygen(snrf_ctx* ctx, RayGenParams& R, const snrf_camera* cam, c
   R.cam.has_dist = cam->has_distortion != 0;
   memcpy(R.cam.dist, cam->distortion, sizeof(R.cam.dist));
   memcpy(R.cam.c2w, cam->c2w, sizeof(R.cam.c2w));
+  R.has_aabb = cam->has_aabb != 0;
+  memcpy(R.aabb, cam->aabb, sizeof(R.aabb));
   R.n_rows = n_rows;
   R.n_cols = n_cols;
   R.patch = patch > 1 ? patch : 1;
@@ -989,7 +992,7 @@ static int fill_raygen(snrf_ctx* ctx, RayGenParams& R, const snrf_camera* cam, c
 
 int snrf_generate_rays(snrf_ctx* ctx, const snrf_camera* cam, const int32_t* rows_host, int n_rows,
                        const int32_t* cols_host, int n_cols, int patch, float* origins, float* dirs,
-                       float* pixel_area, void* stream) {
+                       float* pixel_area, float* nears, float* fars, void* stream) {
   if (!ctx) return SNRF_E_INVALID;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   CK(cudaSetDevice(ctx->device));
@@ -1001,6 +1004,9 @@ int snrf_generate_rays(snrf_ctx* ctx, const snrf_camera* cam, const int32_t* row
   R.origins = origins;
   R.dirs = dirs;
   R.pixel_area = pixel_area;
+  if (R.has_aabb && (!nears || !fars)) return fail(ctx, SNRF_E_INVALID, "a crop box needs nears / fars outputs");
+  R.nears = nears;
+  R.fars = fars;
   LAUNCH(launch_raygen(R, s));
   return SNRF_OK;
 }
@@ -1023,8 +1029,14 @@ int snrf_render_camera(snrf_ctx* ctx, const snrf_camera* cam, const int32_t* row
   CK(ctx->cam_d.ensure(n * 3 * sizeof(float)));
   R.origins = ctx->cam_o.as<float>();
   R.dirs = ctx->cam_d.as<float>();
+  if (R.has_aabb) {
+    CK(ctx->cam_near.ensure(n * sizeof(float)));
+    CK(ctx->cam_far.ensure(n * sizeof(float)));
+    R.nears = ctx->cam_near.as<float>();
+    R.fars = ctx->cam_far.as<float>();
+  }
   LAUNCH(launch_raygen(R, s));
-  return snrf_render_frame(ctx, R.origins, R.dirs, nullptr, nullptr, n, chunk, flags, opts, rgb, depth, acc, prop_depth,
+  return snrf_render_frame(ctx, R.origins, R.dirs, R.nears, R.fars, n, chunk, flags, opts, rgb, depth, acc, prop_depth,
                            sam, clipseg, stream);
 }
 

@@ -23,6 +23,28 @@ struct CameraDev {
   float c2w[12]; // row-major 3x4 camera-to-world
 };
 
+// Ray / axis-aligned box intersection for the viewer's crop box (Cameras.generate_rays(aabb_box=...),
+// cameras.py:463-482 -> nerfstudio/utils/math.py:201-238): slab test, both distances clamped to [0, 1e10], a miss
+// reports 1e10 for both.  0/0 lanes (a ray inside a slab's plane with zero direction component) give NaN, which
+// torch.min / max propagate; fminf / fmaxf would drop it, hence the explicit tests.
+SNRF_HD void aabb_near_far(const float (&o)[3], const float (&d)[3], const float (&box)[6], float& t_near, float& t_far) {
+  float lo = -INFINITY, hi = INFINITY;
+  bool nan = false;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const float t0 = (box[a] - o[a]) / d[a], t1 = (box[3 + a] - o[a]) / d[a];
+    nan = nan || t0 != t0 || t1 != t1;
+    lo = fmaxf(lo, fminf(t0, t1));
+    hi = fminf(hi, fmaxf(t0, t1));
+  }
+  if (nan) lo = hi = NAN;
+  lo = lo != lo ? lo : fminf(fmaxf(lo, 0.f), 1e10f);
+  hi = hi != hi ? hi : fminf(fmaxf(hi, 0.f), 1e10f);
+  const bool miss = hi <= lo;
+  t_near = miss ? 1e10f : lo;
+  t_far = miss ? 1e10f : hi;
+}
+
 struct RayGenParams {
   CameraDev cam;
   const int* rows;   // [n_rows] pixel rows, or null -> 0..n_rows-1
@@ -32,6 +54,10 @@ struct RayGenParams {
   float* origins;    // [n_rows*n_cols, 3]
   float* dirs;       // [n_rows*n_cols, 3]
   float* pixel_area; // [n_rows*n_cols] or null
+  int has_aabb;      // crop box: also write nears / fars (cameras.py:463-482)
+  float aabb[6];     // x_min y_min z_min x_max y_max z_max
+  float* nears;      // [n_rows*n_cols] or null
+  float* fars;       // [n_rows*n_cols] or null
 };
 
 SNRF_HD void undistort_rt(float& x, float& y, const float (&k)[6]) {
@@ -118,6 +144,10 @@ SNRF_HD void raygen_one(const RayGenParams& P, int64_t i) {
   for (int j = 0; j < 3; ++j) {
     P.origins[3 * i + j] = C.c2w[4 * j + 3];
     P.dirs[3 * i + j] = d[j];
+  }
+  if (P.has_aabb && P.nears && P.fars) {
+    const float o[3] = {C.c2w[3], C.c2w[7], C.c2w[11]};
+    aabb_near_far(o, d, P.aabb, P.nears[i], P.fars[i]);
   }
   if (P.pixel_area) {
     float dxo[3], dyo[3];

@@ -32,11 +32,13 @@ class Camera:
     six distortion parameters ``[k1 k2 k3 k4 p1 p2]``."""
 
     def __init__(self, fx: float, fy: float, cx: float, cy: float, width: int, height: int, camera_to_world,
-                 camera_type: int = 1, distortion_params=None):
+                 camera_type: int = 1, distortion_params=None, aabb=None):
         self.fx, self.fy, self.cx, self.cy = float(fx), float(fy), float(cx), float(cy)
         self.width, self.height, self.camera_type = int(width), int(height), int(camera_type)
         self.camera_to_world = torch.as_tensor(camera_to_world, dtype=torch.float32)[:3, :4].contiguous().cpu()
         self.distortion_params = None if distortion_params is None else [float(v) for v in distortion_params]
+        # viewer crop box ``[x_min y_min z_min x_max y_max z_max]`` (generate_rays(aabb_box=...), cameras.py:463-482)
+        self.aabb = None if aabb is None else [float(v) for v in torch.as_tensor(aabb).flatten().tolist()]
 
     def as_struct(self) -> L.Camera:
         c = L.Camera()
@@ -47,6 +49,9 @@ class Camera:
             c.distortion[i] = v
         for i, v in enumerate(self.camera_to_world.flatten().tolist()):
             c.c2w[i] = v
+        c.has_aabb = int(self.aabb is not None)
+        for i, v in enumerate(self.aabb or [0.0] * 6):
+            c.aabb[i] = v
         return c
 
 
@@ -354,17 +359,20 @@ class Renderer:
     def generate_rays(self, cam: Camera, rows=None, cols=None, patch: int = 1, pixel_area: bool = False):
         """``Cameras.generate_rays`` for one camera (cameras.py:312-482,490-726) over the pixel grid ``rows x cols``
         (``None`` = the whole image), row-major or patch-major (``patch`` > 1, sam_model.py:376-379).
-        Returns ``origins[n,3], directions[n,3], pixel_area[n,1] | None`` on the device."""
+        Returns ``origins[n,3], directions[n,3], pixel_area[n,1] | None`` on the device; with a crop box on the camera
+        (``cam.aabb``) also ``nears[n,1], fars[n,1]``."""
         r, n_rows = _index_list(rows, cam.height)
         c, n_cols = _index_list(cols, cam.width)
         n = n_rows * n_cols
         o = torch.empty(n, 3, device=self.device)
         d = torch.empty(n, 3, device=self.device)
         a = torch.empty(n, 1, device=self.device) if pixel_area else None
+        nr = torch.empty(n, 1, device=self.device) if cam.aabb is not None else None
+        fr = torch.empty(n, 1, device=self.device) if cam.aabb is not None else None
         st = cam.as_struct()
         self._check(self.lib.snrf_generate_rays(self.h, C.byref(st), r, n_rows, c, n_cols, int(patch), o.data_ptr(),
-                                                d.data_ptr(), _ptr(a), self.stream))
-        return o, d, a
+                                                d.data_ptr(), _ptr(a), _ptr(nr), _ptr(fr), self.stream))
+        return (o, d, a) if cam.aabb is None else (o, d, a, nr, fr)
 
     def render_camera(self, cam: Camera, rows=None, cols=None, get_feature: Sequence[str] = ("sam",), patch: bool = False,
                       fast: bool = False, chunk: Optional[int] = None,

@@ -20,8 +20,11 @@ extern "C" {
 // mirrors snrf_generate_rays: all pointers are HOST pointers here
 int emu_generate_rays(const float* intr /*fx fy cx cy*/, int type, int has_dist, const float* dist, const float* c2w,
                       const int* rows, int n_rows, const int* cols, int n_cols, int patch, float* origins, float* dirs,
-                      float* pixel_area) {
+                      float* pixel_area, const float* aabb /*6 or null*/, float* nears, float* fars) {
   RayGenParams P;
+  P.has_aabb = aabb != nullptr;
+  for (int i = 0; i < 6; ++i) P.aabb[i] = aabb ? aabb[i] : 0.f;
+  P.nears = nears; P.fars = fars;
   P.cam.fx = intr[0]; P.cam.fy = intr[1]; P.cam.cx = intr[2]; P.cam.cy = intr[3];
   P.cam.type = type;
   P.cam.has_dist = has_dist;

@@ -35,7 +35,7 @@ def test_oracle_matches_reference(name):
     np.testing.assert_allclose(a.numpy(), c["pixel_area"], rtol=1e-5, atol=0)
 
 
-def _emu_rays(c, rows, cols, patch, want_area=True):
+def _emu_rays(c, rows, cols, patch, want_area=True, aabb=None):
     from emu.build_emu import load
 
     lib = load()
@@ -49,9 +49,11 @@ def _emu_rays(c, rows, cols, patch, want_area=True):
     r = None if rows is None else np.ascontiguousarray(rows, np.int32)
     cc = None if cols is None else np.ascontiguousarray(cols, np.int32)
     p = lambda x: None if x is None else x.ctypes.data_as(C.c_void_p)
+    box = None if aabb is None else np.ascontiguousarray(aabb, np.float32)
+    nr, fr = np.empty((n,), np.float32), np.empty((n,), np.float32)
     lib.emu_generate_rays(p(intr), c["type"], int(c["dist"] is not None), p(dist), p(c2w), p(r), n_rows, p(cc), n_cols, patch,
-                          p(o), p(d), p(a) if want_area else None)
-    return o, d, a
+                          p(o), p(d), p(a) if want_area else None, p(box), p(nr), p(fr))
+    return (o, d, a) if aabb is None else (o, d, a, nr, fr)
 
 
 @pytest.mark.parametrize("name", CASES)
@@ -67,6 +69,28 @@ def test_kernel_body_matches_reference(name):
     xs = torch.linspace(0, c["w"] - 1, 8, dtype=torch.long).numpy()
     _, d2, _ = _emu_rays(c, ys, xs, 1, want_area=False)
     np.testing.assert_allclose(d2.reshape(4, 8, 3), c["sub_directions"], rtol=0, atol=DIR_ATOL)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_crop_box_near_far(name):
+    """Viewer crop box (generate_rays(aabb_box=...), cameras.py:463-482): oracle and kernel body against the
+    reference's nears / fars; misses report 1e10 twice."""
+    z = np.load(GOLDEN)
+    c = _case(name)
+    box = z["aabb"]
+    ys, xs = RO.full_image_pixels(c["h"], c["w"])
+    o, d, _ = RO.generate_rays(c["fx"], c["fy"], c["cx"], c["cy"], c["c2w"], ys, xs, c["type"], c["dist"])
+    tn, tf = RO.intersect_aabb(o.reshape(-1, 3), d.reshape(-1, 3), torch.from_numpy(box))
+    want_n, want_f = z[f"{name}.aabb_nears"].reshape(-1), z[f"{name}.aabb_fars"].reshape(-1)
+    np.testing.assert_allclose(tn.numpy(), want_n, rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(tf.numpy(), want_f, rtol=1e-5, atol=1e-6)
+    _, _, _, nr, fr = _emu_rays(c, None, None, 1, want_area=False, aabb=box)
+    hit = want_n < 1e9
+    assert hit.any() and (~hit).any()
+    assert np.array_equal(nr < 1e9, hit)                      # same hit / miss decision for every ray
+    np.testing.assert_allclose(nr[hit], want_n[hit], rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(fr[hit], want_f[hit], rtol=2e-5, atol=2e-6)
+    assert (nr[~hit] == 1e10).all() and (fr[~hit] == 1e10).all()
 
 
 def test_kernel_body_patch_major_order():
@@ -172,3 +196,26 @@ def test_gpu_model_from_camera_equals_model_from_ray_bundle():
     assert set(got) == set(want)
     for k in want:
         assert torch.equal(got[k], want[k]), k
+
+
+@pytest.mark.gpu
+@pytest.mark.hw_unverified
+def test_gpu_crop_box_render():
+    """snrf_render_camera with a crop box == snrf_render with the nears / fars snrf_generate_rays reports."""
+    from helpers import make_renderer, model_pair
+    from samnerf_b200.renderer import Camera
+    from samnerf_b200.synthetic import look_at
+
+    z = np.load(GOLDEN)
+    cfg, params, _ = model_pair("tiny", "scene", 5, False, 1)
+    r = make_renderer(cfg, params)
+    c = _case("perspective")
+    cam = Camera(c["fx"], c["fy"], c["cx"], c["cy"], c["w"], c["h"], c["c2w"], aabb=z["aabb"])
+    o, d, _, nr, fr = r.generate_rays(cam)
+    np.testing.assert_allclose(nr.cpu().numpy().reshape(-1), z["perspective.aabb_nears"].reshape(-1), rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(fr.cpu().numpy().reshape(-1), z["perspective.aabb_fars"].reshape(-1), rtol=2e-5, atol=2e-6)
+    want = r.render(o, d, nears=nr, fars=fr, get_feature=("sam",))
+    got = r.render_camera(cam, get_feature=("sam",))
+    torch.cuda.synchronize()
+    for k in ("rgb", "depth", "accumulation", "sam"):
+        assert torch.equal(torch.nan_to_num(got[k]), torch.nan_to_num(want[k])), k
