@@ -240,3 +240,28 @@ def test_training_mode_sampler_matches_reference():
         r.set_anneal(1.0)
     assert_mostly_close(w0a, z["w0_anneal"], TOL["weights"], FRAC_SMOOTH, "raw proposal weights under annealing")
     assert_mostly_close(edges_a, z["edges1_anneal"], TOL["edges"], 0.99, "nerf bin edges under annealing")
+
+
+@pytest.mark.hw_unverified
+def test_boundary_inputs_against_reference_golden():
+    """Per-ray nears / fars, background override and fast mode through snrf_render against the reference's own model
+    (tests/golden/chunk_tiny_boundary.npz)."""
+    from samnerf_b200 import SAMNeRFConfig, make_synthetic_params
+
+    z = np.load(os.path.join(GOLDEN, "chunk_tiny_boundary.npz"))
+    cfg = SAMNeRFConfig.tiny(clipseg=False, patch_size=1)
+    r = make_renderer(cfg, make_synthetic_params(cfg, "scene", 9))
+    o, d, nr, fr = (torch.from_numpy(z[k]) for k in ("_origins", "_directions", "_nears", "_fars"))
+    bg = tuple(float(v) for v in z["_bg"])
+    for fast in (False, True):
+        out = r.render(o, d, nears=nr, fars=fr, get_feature=("sam",), fast=fast, background=bg)
+        torch.cuda.synchronize()
+        pre = "fast." if fast else ""
+        assert_mostly_close(out["rgb"], z[pre + "rgb"], TOL["rgb"], 0.99, pre + "rgb", per_row=True)
+        assert_mostly_close(out["depth"], z[pre + "depth"], TOL["depth"], FRAC_DISCRETE - 0.02, pre + "depth")
+        assert_features_close(out["sam"], z[pre + "sam"], pre + "sam", row_frac=FRAC_DISCRETE - 0.02)
+        if not fast:
+            assert_mostly_close(out["accumulation"], z["accumulation"], TOL["accumulation"], 0.99, "accumulation")
+            assert_mostly_close(out["prop_depth_0"], z["prop_depth_0"], TOL["depth"], FRAC_DISCRETE - 0.02, "prop_depth_0")
+        else:
+            assert "accumulation" not in out

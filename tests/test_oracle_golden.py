@@ -80,3 +80,24 @@ def test_training_mode_sampler_matches_reference():
     # and the jitter really moved the samples away from the eval-mode positions
     ev = orc.render_rays(o, d, get_feature=(), return_intermediates=True)
     assert float((ev["_eu1"] - res["_eu1"]).abs().max()) > 1e-3
+
+
+def test_boundary_inputs_match_reference():
+    """Rays that arrive with nears / fars (collider bypass, scene_colliders.py:40-44), a background colour override
+    (renderers.py:46-55,100-101) and ``fast`` mode (sam_model.py:284-299), through the reference's own model
+    (oracle/make_boundary_golden.py)."""
+    from samnerf_b200 import SAMNeRFConfig
+
+    z = np.load(os.path.join(GOLDEN, "chunk_tiny_boundary.npz"))
+    cfg = SAMNeRFConfig.tiny(clipseg=False, patch_size=1)
+    orc = Oracle(cfg, make_synthetic_params(cfg, "scene", 9))
+    o, d, nr, fr = (torch.from_numpy(z[k]) for k in ("_origins", "_directions", "_nears", "_fars"))
+    bg = tuple(float(v) for v in z["_bg"])
+    for fast in (False, True):
+        out = orc.render_rays(o, d, nr, fr, get_feature=("sam",), fast=fast, background=bg)
+        pre = "fast." if fast else ""
+        keys = [k[len(pre):] for k in z.files if not k.startswith("_") and (k.startswith("fast.") == fast)]
+        assert set(keys) == set(out), (keys, sorted(out))
+        for k in keys:
+            np.testing.assert_allclose(out[k].numpy(), z[pre + k], rtol=1e-5, atol=1e-6, err_msg=pre + k)
+    assert float(torch.from_numpy(z["depth"]).max()) <= float(fr.max())
