@@ -295,6 +295,15 @@ void snrf_ctx_destroy(snrf_ctx* ctx) {
   ctx->hbar[0][1].release(); ctx->hbar[1][0].release(); ctx->hbar[1][1].release();
   if (ctx->aux_feat) cudaStreamDestroy(ctx->aux_feat);
   if (ctx->aux_out) cudaStreamDestroy(ctx->aux_out);
+  for (int i = 0; i < 4; ++i) {
+    if (ctx->copy_stream[i]) cudaStreamDestroy(ctx->copy_stream[i]);
+    if (ctx->ev_copy[i]) cudaEventDestroy(ctx->ev_copy[i]);
+  }
+  cudaEvent_t own[] = {ctx->ev_out[0], ctx->ev_out[1], ctx->ev_march[0], ctx->ev_march[1], ctx->ev_feat[0][0],
+                       ctx->ev_feat[0][1], ctx->ev_feat[1][0], ctx->ev_feat[1][1], ctx->ev_feat_done[0],
+                       ctx->ev_feat_done[1], ctx->ev_out_done[0], ctx->ev_out_done[1], ctx->ev_join, ctx->ev_join2};
+  for (cudaEvent_t e : own)
+    if (e) cudaEventDestroy(e);
   for (auto& u : ctx->ev_used) {
     cudaEventDestroy(u.second.first);
     cudaEventDestroy(u.second.second);
