@@ -119,9 +119,21 @@ __device__ __forceinline__ void epilogue_tile(const SamBucketParams& P, uint32_t
     for (int i = 0; i < 32; ++i) v[i] = round_f16(fmaxf(v[i], 0.f)) * wgt;
     const int base = halving_reduce<LOG>(v, lane);
     if (valid) {
+      // kKeep consecutive fp16 columns of this ray; col0 and base are multiples of kKeep, so the widest store that
+      // covers them is aligned (kKeep * 2 bytes: 64 / 32 / 16 / 8 / 4 for LOG = 0..4)
       __half* dst = P.hbar + ray * kHid + col0 + base;
+      uint32_t pk[kKeep / 2];
 #pragma unroll
-      for (int i = 0; i < kKeep; i += 2) *reinterpret_cast<uint32_t*>(dst + i) = f2_to_h2(v[i], v[i + 1]);
+      for (int i = 0; i < kKeep / 2; ++i) pk[i] = f2_to_h2(v[2 * i], v[2 * i + 1]);
+      if (kKeep >= 8) {
+#pragma unroll
+        for (int i = 0; i < kKeep / 8; ++i)
+          reinterpret_cast<uint4*>(dst)[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+      } else if (kKeep == 4) {
+        *reinterpret_cast<uint2*>(dst) = make_uint2(pk[0], pk[1]);
+      } else {
+        *reinterpret_cast<uint32_t*>(dst) = pk[0];
+      }
     }
   }
   tc_fence_before();
