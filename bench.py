@@ -311,6 +311,12 @@ def run_native(args):
     r.set_timing(False)
     r.set_pipeline(args.pipeline)
     ktimes = r.kernel_times()
+    slot_stats = None
+    if args.feature_cutoff >= 0:
+        r.feature_slot_stats(reset=True)
+        frame()  # one untimed frame to count the slots the bucketed kernel really evaluates
+        barrier()
+        slot_stats = r.feature_slot_stats(reset=True)
     clk = clocks.stop() if rank == 0 else None
     total_ms = sum(s.elapsed_time(e) for s, e in ev)
     t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
@@ -372,6 +378,10 @@ def run_native(args):
         g_ms, g_cnt = ktimes["tapgemm"]
         rays_per_launch = n_loc * args.steps / max(f_cnt, 1)
         ach = BYTES_PER_RAY["sam"] * rays_per_launch / (f_ms / max(f_cnt, 1) * 1e-3) / 1e9 if f_ms > 0 else None
+        if slot_stats is not None and f_ms > 0:
+            # bucketed kernel: state the roofline on the slots it gathers (3 072 B each), not on all 16 per ray
+            slots_per_ray = slot_stats[1] / max(n_loc, 1)
+            ach = 3072.0 * slots_per_ray * rays_per_launch / (f_ms / max(f_cnt, 1) * 1e-3) / 1e9
         path_bytes = sum(BYTES_PER_RAY.values())
         line = {
             "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
@@ -390,7 +400,12 @@ def run_native(args):
                          "traffic_note": "ncu dram bytes of one launch (profiles/r01_traffic.json): far below the "
                                          "algorithmic bytes - the launch's table footprint is L2/L1-resident; the kernel "
                                          "is bound by the L1 tag stage and issue, not HBM (DESIGN.md section 4 B)",
-                         "algorithmic_bytes_per_launch": BYTES_PER_RAY["sam"] * rays_per_launch,
+                         "algorithmic_bytes_per_launch": (BYTES_PER_RAY["sam"] if slot_stats is None else
+                                                          3072.0 * slot_stats[1] / max(n_loc, 1)) * rays_per_launch,
+                         "feature_slots": None if slot_stats is None else {
+                             "rays_per_bucket_1_2_4_8_16": slot_stats[0], "slots_per_ray": slot_stats[1] / max(n_loc, 1),
+                             "note": "bucketed kernel: achieved / algorithmic bytes count the evaluated slots only; "
+                                     "all 16 slots would be 49152 B/ray"},
                          "avg_launch_ms": f_ms / max(f_cnt, 1), "launches_timed": f_cnt,
                          "timing_note": "CUDA events around each launch, instrumented repeat of the K timed steps (same inputs, L2 flushed)",
                          "path": {"bytes_per_ray": path_bytes, "achieved": value * 1e6 * path_bytes / 1e9 / world,

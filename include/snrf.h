@@ -70,6 +70,10 @@ int snrf_set_early_termination(snrf_ctx* ctx, float eps);
  * exact up to fp32 summation order; 2^-24 drops less than one fp32 ulp of the accumulated feature.  tcgen05 engine
  * only.  See csrc/sam_bucket.cu. */
 int snrf_set_feature_cutoff(snrf_ctx* ctx, float cutoff);
+/* Rays the bucketed feature kernel has put into its 1 / 2 / 4 / 8 / 16-slot buckets since the last reset
+ * (rays_per_bucket[5], host): sum_b rays[b] << b is the number of (ray, sample) slots actually gathered, 3 072 B each -
+ * the algorithmic bytes bench.py states the roofline on when the cut-off is on.  Synchronises the device. */
+int snrf_feature_slot_stats(snrf_ctx* ctx, int64_t* rays_per_bucket, int reset);
 /* eval-mode PDF sample positions u[33] = linspace(0, 1-1/33, 33) + 1/66 (ray_samplers.py:325-327).  The
  * library computes the same table itself; a host may override it so that both sides share the bits.  n = 66:
  * followed by the 33 linspace values without the offset (the base of the training-mode positions, :314-322). */

@@ -64,6 +64,7 @@ SYMBOLS = {
     "snrf_set_jitter": (_I, [_P, _P, _L]),
     "snrf_set_feature_cutoff": (_I, [_P, _F]),
     "snrf_set_anneal": (_I, [_P, _F]),
+    "snrf_feature_slot_stats": (_I, [_P, C.POINTER(C.c_int64), _I]),
     "snrf_upload_proposal": (_I, [_P, _P, _L, C.POINTER(GridDesc), _P]),
     "snrf_upload_field_base": (_I, [_P, _P, _L, C.POINTER(GridDesc), _P]),
     "snrf_upload_field_head": (_I, [_P, _P, _L, _P]),

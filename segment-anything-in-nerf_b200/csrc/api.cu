@@ -109,6 +109,7 @@ struct snrf_ctx {
   DevBuf cam_rows, cam_cols, cam_o, cam_d, cam_near, cam_far;  // snrf_generate_rays / snrf_render_camera
   DevBuf bwd_scratch, bwd_sink;             // snrf_feature_backward
   DevBuf bucket_lists[2], bucket_counts[2]; // bucketed feature kernel, per pipeline slot
+  DevBuf bucket_totals;                     // rays per bucket since the last snrf_feature_slot_stats reset
 };
 
 namespace {
@@ -292,6 +293,7 @@ void snrf_ctx_destroy(snrf_ctx* ctx) {
   ctx->conv_w_rm[0].release(); ctx->conv_w_rm[1].release();
   ctx->bwd_scratch.release(); ctx->bwd_sink.release();
   for (int i = 0; i < 2; ++i) { ctx->bucket_lists[i].release(); ctx->bucket_counts[i].release(); }
+  ctx->bucket_totals.release();
   ctx->hbar[0][1].release(); ctx->hbar[1][0].release(); ctx->hbar[1][1].release();
   if (ctx->aux_feat) cudaStreamDestroy(ctx->aux_feat);
   if (ctx->aux_out) cudaStreamDestroy(ctx->aux_out);
@@ -334,6 +336,19 @@ int snrf_set_early_termination(snrf_ctx* ctx, float eps) {
 int snrf_set_feature_cutoff(snrf_ctx* ctx, float cutoff) {
   if (!ctx || cutoff != cutoff || cutoff > 1e-2f) return fail(ctx, SNRF_E_INVALID, "feature cut-off must be < 0 (off) or in [0, 1e-2]");
   ctx->feat_cutoff = cutoff;
+  return SNRF_OK;
+}
+
+int snrf_feature_slot_stats(snrf_ctx* ctx, int64_t* rays_per_bucket, int reset) {
+  if (!ctx || !rays_per_bucket) return fail(ctx, SNRF_E_INVALID, "null argument");
+  CK(cudaSetDevice(ctx->device));
+  unsigned long long host[kFeatBuckets] = {0, 0, 0, 0, 0};
+  if (ctx->bucket_totals.p) {
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(host, ctx->bucket_totals.p, sizeof(host), cudaMemcpyDeviceToHost));
+    if (reset) CK(cudaMemset(ctx->bucket_totals.p, 0, sizeof(host)));
+  }
+  for (int b = 0; b < kFeatBuckets; ++b) rays_per_bucket[b] = static_cast<int64_t>(host[b]);
   return SNRF_OK;
 }
 
@@ -777,8 +792,13 @@ static int render_chunk(snrf_ctx* ctx, const float* origins, const float* dirs, 
         e0 = get_event(ctx); e1 = get_event(ctx);
         cudaEventRecord(e0, cs.feat);
       }
+      if (!ctx->bucket_totals.p) {
+        CK(ctx->bucket_totals.ensure(kFeatBuckets * sizeof(unsigned long long)));
+        CK(cudaMemsetAsync(ctx->bucket_totals.p, 0, kFeatBuckets * sizeof(unsigned long long), cs.feat));
+      }
       LAUNCH(launch_bucket_assign(M.sam_w, ctx->feat_cutoff, ctx->bucket_counts[slot].as<int>(),
-                                  ctx->bucket_lists[slot].as<int>(), n_rays, cs.feat));
+                                  ctx->bucket_lists[slot].as<int>(), n_rays, ctx->bucket_totals.as<unsigned long long>(),
+                                  cs.feat));
       Bk.lists = ctx->bucket_lists[slot].as<int>();
       Bk.counts = ctx->bucket_counts[slot].as<int>();
       Bk.n_rays = n_rays;

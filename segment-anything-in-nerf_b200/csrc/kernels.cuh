@@ -103,7 +103,9 @@ struct SamBucketParams {
 // Pre-pass, one thread per ray: significant slots = 1 + index of the last slot whose weight is not below the
 // cut-off (NaN weights - 0/0 rays, sam_model.py:248 - count as significant, so such a ray keeps all 16 slots and
 // yields the same NaN row as kernel B); cut-off 0 keeps every non-zero weight.  lists: [kFeatBuckets][n].
-SNRF_HD void bucket_assign_one(const float* sam_w, float eps, int* counts, int* lists, int64_t n, int64_t ray) {
+// totals (optional): running number of rays per bucket over all launches (snrf_feature_slot_stats).
+SNRF_HD void bucket_assign_one(const float* sam_w, float eps, int* counts, int* lists, int64_t n, int64_t ray,
+                               unsigned long long* totals = nullptr) {
   int k = 0;
   for (int s = 0; s < 16; ++s) {
     const float w = sam_w[ray * 16 + s];
@@ -112,12 +114,15 @@ SNRF_HD void bucket_assign_one(const float* sam_w, float eps, int* counts, int* 
   const int b = k <= 1 ? 0 : k <= 2 ? 1 : k <= 4 ? 2 : k <= 8 ? 3 : 4;
 #ifdef __CUDA_ARCH__
   const int pos = atomicAdd(counts + b, 1);
+  if (totals) atomicAdd(totals + b, 1ull);
 #else
   const int pos = counts[b]++;
+  if (totals) totals[b] += 1ull;
 #endif
   lists[static_cast<int64_t>(b) * n + pos] = static_cast<int>(ray);
 }
-cudaError_t launch_bucket_assign(const float* sam_w, float eps, int* counts, int* lists, int64_t n, cudaStream_t stream);
+cudaError_t launch_bucket_assign(const float* sam_w, float eps, int* counts, int* lists, int64_t n,
+                                 unsigned long long* totals, cudaStream_t stream);
 cudaError_t launch_sam_bucketed(const SamBucketParams& P, int sm_count, cudaStream_t stream);
 
 // ---- kernel C/D: tap GEMM  out = act(sum_t A_t[M,256] x W_t[N,256]^T + bias) ----------------------

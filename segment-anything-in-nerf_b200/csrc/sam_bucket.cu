@@ -246,9 +246,10 @@ __global__ void __launch_bounds__(kThreads, 1) sam_bucket_kernel(const SamBucket
   if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
-__global__ void bucket_assign_kernel(const float* sam_w, float eps, int* counts, int* lists, int64_t n) {
+__global__ void bucket_assign_kernel(const float* sam_w, float eps, int* counts, int* lists, int64_t n,
+                                     unsigned long long* totals) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i < n) bucket_assign_one(sam_w, eps, counts, lists, n, i);
+  if (i < n) bucket_assign_one(sam_w, eps, counts, lists, n, i, totals);
 }
 
 constexpr uint32_t kEnc0MaskStd = 0xE00u, kEnc1MaskStd = 0xFFFu;  // as in sam.cu
@@ -270,11 +271,12 @@ cudaError_t launch_one(const SamBucketParams& P, int grid, cudaStream_t stream) 
 
 }  // namespace
 
-cudaError_t launch_bucket_assign(const float* sam_w, float eps, int* counts, int* lists, int64_t n, cudaStream_t stream) {
+cudaError_t launch_bucket_assign(const float* sam_w, float eps, int* counts, int* lists, int64_t n,
+                                 unsigned long long* totals, cudaStream_t stream) {
   if (n <= 0) return cudaSuccess;
   cudaError_t e = cudaMemsetAsync(counts, 0, kFeatBuckets * sizeof(int), stream);
   if (e != cudaSuccess) return e;
-  bucket_assign_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(sam_w, eps, counts, lists, n);
+  bucket_assign_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(sam_w, eps, counts, lists, n, totals);
   return cudaGetLastError();
 }
 

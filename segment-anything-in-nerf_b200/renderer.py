@@ -162,6 +162,14 @@ class Renderer:
         ``2**-24`` = drop what is below one fp32 ulp of the accumulated feature.  See ``snrf_set_feature_cutoff``."""
         self._check(self.lib.snrf_set_feature_cutoff(self.h, float(cutoff)))
 
+    def feature_slot_stats(self, reset: bool = True):
+        """Rays per bucket (1 / 2 / 4 / 8 / 16 slots) of the bucketed feature kernel since the last reset, and the
+        number of (ray, sample) slots that were actually gathered."""
+        a = (C.c_int64 * 5)()
+        self._check(self.lib.snrf_feature_slot_stats(self.h, a, int(reset)))
+        rays = [int(v) for v in a]
+        return rays, sum(r << b for b, r in enumerate(rays))
+
     def set_engine(self, engine: str) -> None:
         """``tcgen05`` (default) or ``mma_sync`` (the recompiled-legacy comparison path)."""
         self.engine = engine

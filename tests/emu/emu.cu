@@ -127,7 +127,7 @@ int emu_feature_backward(const float* origins, const float* dirs, const float* s
 // pre-pass of the bucketed feature kernel (sam_bucket.cu): counts[4], lists[4][n]
 int emu_bucket_assign(const float* sam_w, float eps, long long n, int* counts, int* lists) {
   for (int b = 0; b < kFeatBuckets; ++b) counts[b] = 0;
-  for (int64_t r = 0; r < n; ++r) bucket_assign_one(sam_w, eps, counts, lists, n, r);
+  for (int64_t r = 0; r < n; ++r) bucket_assign_one(sam_w, eps, counts, lists, n, r, nullptr);
   return 0;
 }
 
