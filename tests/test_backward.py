@@ -194,6 +194,7 @@ def test_gpu_training_step_reduces_the_loss():
     m = SAMModel(cfg)
     m.load_state_dict(params)
     m.train()
+    m.proposal_sampler.train_stratified = False  # same samples every step, so that the loss is comparable
     o, d = test_rays(512, seed=4)
     from samnerf_b200.nerfstudio_api import RayBundle
 
@@ -518,6 +519,7 @@ def test_gpu_full_training_step_lowers_rgb_and_feature_losses():
     m = SAMModel(cfg)
     m.load_state_dict(params)
     m.train()
+    m.proposal_sampler.train_stratified = False  # same samples every step, so that the losses are comparable
     o, d = test_rays(1024, seed=6)
     bundle = RayBundle(origins=o.cuda(), directions=d.cuda())
     gen = torch.Generator().manual_seed(3)
