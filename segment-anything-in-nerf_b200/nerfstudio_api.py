@@ -675,6 +675,17 @@ class SAMModel:
                 dist.all_reduce(p.grad, op=dist.ReduceOp.SUM, group=group)
                 p.grad.div_(world)
 
+    def get_training_callbacks(self, training_callback_attributes=None) -> List:
+        """nerfacto.py:242-271: the anneal setter before, the sampler's step counter after every iteration."""
+        from .training import TrainingCallback, TrainingCallbackLocation
+
+        if not self.config.use_proposal_weight_anneal:
+            return []
+        return [
+            TrainingCallback([TrainingCallbackLocation.BEFORE_TRAIN_ITERATION], self.before_train_iteration, update_every_num_iters=1),
+            TrainingCallback([TrainingCallbackLocation.AFTER_TRAIN_ITERATION], self.proposal_sampler.step_cb, update_every_num_iters=1),
+        ]
+
     def _sync_params(self) -> None:
         """Push parameters an optimiser step has changed (tensor version counters) back into the library's packed
         fp16 copies - the re-upload SURVEY 8 b asks for."""

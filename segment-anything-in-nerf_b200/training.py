@@ -10,7 +10,9 @@ Restated from (paths relative to /root/reference):
 """
 from __future__ import annotations
 
-from typing import Dict, List
+from enum import Enum, auto
+from inspect import signature
+from typing import Callable, Dict, List, Optional, Tuple
 
 import numpy as np
 import torch
@@ -94,3 +96,34 @@ def proposal_anneal(step: int, max_num_iters: int = 1000, slope: float = 10.0) -
 def proposal_update_schedule(warmup: int = 5000, update_every: int = 5):
     """nerfacto.py:196-200: steps between proposal-network updates, ramping up over the warm-up."""
     return lambda step: float(np.clip(np.interp(step, [0, warmup], [0, update_every]), 1, update_every))
+
+
+class TrainingCallbackLocation(Enum):
+    """nerfstudio/engine/callbacks.py:42-46."""
+
+    BEFORE_TRAIN_ITERATION = auto()
+    AFTER_TRAIN_ITERATION = auto()
+
+
+class TrainingCallback:
+    """nerfstudio/engine/callbacks.py:49-110: ``func(step=...)`` every ``update_every_num_iters`` iterations (or at the
+    listed ``iters``), at the places named in ``where_to_run``.  What ``Model.get_training_callbacks`` hands the trainer."""
+
+    def __init__(self, where_to_run: List[TrainingCallbackLocation], func: Callable, update_every_num_iters: Optional[int] = None,
+                 iters: Optional[Tuple[int, ...]] = None, args: Optional[List] = None, kwargs: Optional[Dict] = None):
+        assert "step" in signature(func).parameters, f"'step: int' must be an argument of the callback {func}"
+        self.where_to_run, self.func = where_to_run, func
+        self.update_every_num_iters, self.iters = update_every_num_iters, iters
+        self.args, self.kwargs = args or [], kwargs or {}
+
+    def run_callback(self, step: int) -> None:
+        if self.update_every_num_iters is not None:
+            if step % self.update_every_num_iters == 0:
+                self.func(*self.args, **self.kwargs, step=step)
+        elif self.iters is not None:
+            if step in self.iters:
+                self.func(*self.args, **self.kwargs, step=step)
+
+    def run_callback_at_location(self, step: int, location: TrainingCallbackLocation) -> None:
+        if location in self.where_to_run:
+            self.run_callback(step=step)

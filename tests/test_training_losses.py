@@ -65,6 +65,15 @@ def test_model_loss_dict_and_callbacks(monkeypatch):
         assert all(p.grad is not None and torch.isfinite(p.grad).all() and float(p.grad.abs().max()) > 0 for p in groups[name]), name
     m.after_train_iteration(100)
     assert m.proposal_sampler._step == 100 and m.proposal_sampler._steps_since_update == 1
+    # the same two hooks as trainer callbacks (nerfacto.py:242-271, engine/callbacks.py:49-110)
+    cbs = m.get_training_callbacks()
+    assert [c.where_to_run[0] for c in cbs] == [T.TrainingCallbackLocation.BEFORE_TRAIN_ITERATION, T.TrainingCallbackLocation.AFTER_TRAIN_ITERATION]
+    for c in cbs:
+        c.run_callback_at_location(step=500, location=T.TrainingCallbackLocation.BEFORE_TRAIN_ITERATION)
+    assert abs(m.renderer.anneal - T.proposal_anneal(500)) < 1e-7 and m.proposal_sampler._step == 100
+    cbs[1].run_callback_at_location(step=101, location=T.TrainingCallbackLocation.AFTER_TRAIN_ITERATION)
+    assert m.proposal_sampler._step == 101 and m.proposal_sampler._steps_since_update == 2
+    m.proposal_sampler._steps_since_update = 1
     # step 100 >= 10 and one step since the last update <= schedule(100) = 1: this pass keeps the proposal net frozen
     for p in groups["proposal_networks"]:
         p.grad = None
