@@ -26,6 +26,15 @@ def build(force: bool = False) -> str:
 
 
 def load() -> ctypes.CDLL:
+    """Build if needed and load.  Without nvcc (and without a prebuilt library) the calling test is skipped: the
+    emulation is a checker for the build container, not a requirement of the package."""
+    import shutil
+
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    if not os.path.exists(LIB) and not (os.path.exists(nvcc) or shutil.which("nvcc")):
+        import pytest
+
+        pytest.skip("nvcc not available: cannot build the host emulation of the kernel bodies")
     return ctypes.CDLL(build())
 
 
