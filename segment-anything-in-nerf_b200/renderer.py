@@ -86,6 +86,14 @@ class Renderer:
         u = torch.cat([base + 1.0 / (2 * nb), base]).contiguous()  # eval positions, then the training-mode base (:314-322)
         self._check(self.lib.snrf_set_pdf_u(self.h, u.data_ptr(), 2 * nb))
         self.have_sam = self.have_clipseg = self.have_conv = False
+        # opt-in knobs from the environment, so that a whole test / bench run can be put through them unchanged
+        # (e.g. SNRF_FEATURE_CUTOFF=5.96e-8 pytest -m gpu runs every parity test through the bucketed feature kernel)
+        import os
+
+        if os.environ.get("SNRF_FEATURE_CUTOFF"):
+            self.set_feature_cutoff(float(os.environ["SNRF_FEATURE_CUTOFF"]))
+        if os.environ.get("SNRF_EARLY_TERMINATION"):
+            self.set_early_termination(float(os.environ["SNRF_EARLY_TERMINATION"]))
 
     # ------------------------------------------------------------------------------------------
     def _check(self, rc: int) -> None:
