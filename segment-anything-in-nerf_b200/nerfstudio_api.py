@@ -530,8 +530,8 @@ class SAMModel:
 
     ``get_outputs`` / ``forward`` run one fused ``snrf_render`` call per chunk; the component objects
     (``proposal_sampler``, ``field``, ``sam_field``, renderers) expose the same pieces individually.
-    Prompt lifting and mask decoding (sam_model.py:420-548) consume the rendered feature map and are out of
-    scope here (SURVEY.md section 8 f, row 4).
+    Prompt lifting / projection (sam_model.py:426-475) is done here as in the reference; the 2-D mask decoders that
+    consume the prompts and the rendered feature map (sam_model.py:485-548) are out of scope.
     """
 
     def __init__(self, config: SAMNeRFConfig, device: int = 0, engine: str = "tcgen05"):
@@ -803,7 +803,37 @@ class SAMModel:
                 for i in range(0, len(cb), chunk):
                     feats.append(self.forward(cb[i:i + chunk], get_feature=["clipseg"])["clipseg"])
                 outputs["clipseg"] = torch.cat(feats).view(32, 32, -1)
+        self._handle_prompts(outputs, points, intrin, c2w)
         return outputs
+
+    def _handle_prompts(self, outputs: Dict[str, torch.Tensor], points, intrin, c2w) -> None:
+        """The prompt bookkeeping of sam_model.py:426-475 up to the point where the 2-D decoders take over: new clicks are
+        lifted to 3-D once (at the rendered depth minus ``TOR``) and remembered in ``self.prompts``; every frame the
+        remembered prompts are projected into the current view and the ones inside the image become
+        ``outputs["prompt_points"]`` - what the reference hands to ``SamPredictor.predict`` (with
+        ``outputs["sam_embedding"]``, the zero-padded ``[1,256,S,S]`` feature map, sam_model.py:485 / predictor.py:100-127).
+        ``masked_rgb`` stays the plain rgb, as in the reference before a mask exists (sam_model.py:426)."""
+        from . import prompts as P
+
+        outputs["masked_rgb"] = outputs["rgb"]
+        if "sam" in outputs:
+            outputs["sam_embedding"] = P.pad_feature_map(outputs["sam"])
+        if points is None:
+            self.prompts = None
+            return
+        assert intrin is not None and c2w is not None
+        intrin, c2w = torch.as_tensor(intrin, dtype=torch.float32).cpu(), torch.as_tensor(c2w, dtype=torch.float32).cpu()
+        if len(points) > 0:
+            pts = torch.as_tensor(points).to(torch.long)
+            known = 0 if getattr(self, "prompts", None) is None else self.prompts.shape[0]
+            if len(pts) > known:  # only the clicks that arrived since the last frame are lifted (sam_model.py:437-444)
+                new = P.lift_points(pts[known:], outputs["depth"].detach().cpu(), intrin, c2w)
+                self.prompts = new if known == 0 else torch.cat([self.prompts, new], dim=0)
+        else:
+            self.prompts = None
+        if getattr(self, "prompts", None) is not None:
+            h, w = outputs["rgb"].shape[:2]
+            outputs["prompt_points"] = P.prompts_in_image(self.prompts, intrin, c2w, w, h)
 
     @torch.no_grad()
     def get_outputs_for_camera(self, camera: Camera, fast: bool = False) -> Dict[str, torch.Tensor]:
@@ -824,4 +854,5 @@ class SAMModel:
                 hi = torch.linspace(0, h - 1, 32, dtype=torch.long)
                 wi = torch.linspace(0, w - 1, 32, dtype=torch.long)
                 outputs["clipseg"] = r.render_camera(camera, rows=hi, cols=wi, get_feature=("clipseg",))["clipseg"].view(32, 32, -1)
+        self._handle_prompts(outputs, None, None, None)
         return outputs

@@ -51,3 +51,33 @@ def test_clipseg_activations_layout():
     assert len(acts) == 3 and all(a.shape == (1025, 1, 64) for a in acts)
     assert torch.equal(acts[1][1:, 0], m[..., 64:128].reshape(-1, 64))
     assert torch.allclose(acts[2][0, 0], m[..., 128:].reshape(-1, 64).mean(0))
+
+
+def test_model_prompt_bookkeeping(monkeypatch):
+    """get_outputs_for_camera_ray_bundle(points, intrin, c2w): clicks are lifted once, remembered, re-projected into
+    every later view, and dropped again when the viewer sends an empty list (sam_model.py:426-475)."""
+    import samnerf_b200.nerfstudio_api as api
+    from fake_renderer import FakeRenderer
+    from helpers import model_pair
+    from samnerf_b200.synthetic import look_at, pinhole_rays
+
+    monkeypatch.setattr(api, "Renderer", FakeRenderer)
+    cfg, params, _ = model_pair("tiny", "scene", 6, False, 1)  # patch 1: the 43 x 64 feature grid stays small for the CPU
+    m = api.SAMModel(cfg)
+    m.load_state_dict(params)
+    H, W, f = 8, 12, 12.0
+    c2w = look_at((1.1, 0.6, 0.45))[:3, :4]
+    intrin = torch.tensor([[f, 0.0, W / 2.0], [0.0, f, H / 2.0], [0.0, 0.0, 1.0]])
+    o, d = pinhole_rays(H, W, f, f, look_at((1.1, 0.6, 0.45)))
+    bundle = api.RayBundle(origins=o, directions=d, pixel_area=torch.ones(H, W, 1), camera_indices=torch.zeros(H, W, 1, dtype=torch.long))
+    out = m.get_outputs_for_camera_ray_bundle(bundle)
+    assert "prompt_points" not in out and out["masked_rgb"] is out["rgb"] and out["sam_embedding"].shape == (1, 256, 64, 64)
+    clicks = np.array([[3, 2], [9, 5]])
+    out = m.get_outputs_for_camera_ray_bundle(bundle, points=clicks, intrin=intrin, c2w=c2w)
+    assert m.prompts.shape == (2, 3)
+    assert int((out["prompt_points"] - torch.from_numpy(clicks).to(torch.int32)).abs().max()) <= 1
+    first = m.prompts.clone()
+    out = m.get_outputs_for_camera_ray_bundle(bundle, points=np.concatenate([clicks, [[6, 6]]]), intrin=intrin, c2w=c2w)
+    assert m.prompts.shape == (3, 3) and torch.equal(m.prompts[:2], first)   # old clicks are not lifted again
+    m.get_outputs_for_camera_ray_bundle(bundle, points=np.zeros((0, 2)), intrin=intrin, c2w=c2w)
+    assert m.prompts is None
