@@ -197,6 +197,7 @@ def run_native(args):
     params = make_synthetic_params(cfg, args.regime, 0)
     r = Renderer(cfg, device=local, engine=args.engine)
     r.load_params(params)
+    brick_levels = r.set_brick_budget(args.brick_gb) if args.brick_gb >= 0 else None
     if args.early_termination > 0:
         r.set_early_termination(args.early_termination)  # opt-in, not the reference's exact arithmetic: see config
     if args.feature_cutoff >= 0:
@@ -399,6 +400,7 @@ def run_native(args):
                                  "frame ends with a symmetric-memory barrier") if world > 1 else "single GPU",
                        "early_termination": args.early_termination or None,
                        "feature_cutoff": args.feature_cutoff if args.feature_cutoff >= 0 else None,
+                       "bricks": None if brick_levels is None else {"budget_gib": args.brick_gb, "proposal_levels": brick_levels[0], "field_levels": brick_levels[1]},
                        "chunk": chunk, "pipeline": "chunks pipelined over 3 streams" if (args.pipeline == 2 or (args.pipeline == 1 and world > 1 and symm is not None and args.gather in ("mc", "peer"))) else "sequential"},
             "roofline": {"bound": "hbm", "kernel": "sam_kernel (feature-field gather + MLP layer 1 + weighted sum)",
                          "achieved": ach, "peak": peak, "unit": "GB/s", "frac": (ach / peak) if ach else None,
@@ -451,6 +453,9 @@ def main():
                     help="opt-in bucketed feature kernel: evaluate only the leading picked samples of a ray whose "
                          "sharpened weight is >= this (0 = drop exact zeros, 5.96e-8 = below one fp32 ulp of the sum); "
                          "< 0 = every sample (default and headline configuration)")
+    ap.add_argument("--brick-gb", type=float, default=-1.0,
+                    help="HBM budget (GiB) for the cell-major brick copies of the leading grid levels (library default 4; "
+                         "0 = off; a pure re-layout, results are bit-identical)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-rays", type=int, default=32768,
                     help="rays of the bounded CPU-baseline sample (one reference chunk, timed twice: ~4 s of host work at "

@@ -63,6 +63,13 @@ int snrf_set_engine(snrf_ctx* ctx, int engine);
  * eps < 0.5 up to the eps-weighted tail; per-sample debug outputs of skipped samples read 0.  The reference never
  * terminates early, hence opt-in. */
 int snrf_set_early_termination(snrf_ctx* ctx, float eps);
+/* HBM budget (bytes) for "bricks": cell-major copies of the leading levels of the proposal and nerfacto grids, in which
+ * the 8 corner entries of a cell are 32 contiguous bytes (one sector, one 256-bit load per sample and level instead of
+ * 8 scattered gathers; csrc/bricks.cu).  Pure re-layout: rendered values are bit-identical with any budget.  The
+ * longest prefix of levels that fits is used (nerfacto 16..2048 x 16 levels: 11 levels = 3.5 GB, 12 = 9.3 GB,
+ * 13 = 24.5 GB, 14 = 64.5 GB); rebuilt by every snrf_upload_proposal / snrf_upload_field_base.  Default 4 GiB
+ * (environment SNRF_BRICK_GB overrides), 0 = off.  Optionally returns the number of bricked levels.  Synchronises. */
+int snrf_set_brick_budget(snrf_ctx* ctx, int64_t bytes, int* prop_levels, int* field_levels);
 /* Feature samples below the precision of their own sum (opt-in; default < 0 = off, every one of the 16 picked
  * samples of every ray is evaluated).  cutoff >= 0: rays are bucketed by the number of leading slots whose sharpened,
  * renormalised weight (sam_model.py:244-248) is >= cutoff (> 0 when cutoff == 0) and only 1 / 2 / 4 / 8 / 16 slots of a ray

@@ -13,7 +13,7 @@ import sys
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SNRF_LIB_PATH") or os.path.join(_HERE, "libsnrf.so")
 CSRC = os.path.join(_HERE, "csrc")
-SOURCES = ["api.cu", "march.cu", "sam.cu", "gemm.cu", "query.cu", "raygen.cu", "backward.cu", "sam_bucket.cu"]
+SOURCES = ["api.cu", "march.cu", "march_v1.cu", "sam.cu", "gemm.cu", "query.cu", "raygen.cu", "backward.cu", "sam_bucket.cu", "bricks.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared", "--threads", "0",  # one compile job per source file
@@ -63,6 +63,7 @@ SYMBOLS = {
     "snrf_set_early_termination": (_I, [_P, _F]),
     "snrf_set_jitter": (_I, [_P, _P, _L]),
     "snrf_set_feature_cutoff": (_I, [_P, _F]),
+    "snrf_set_brick_budget": (_I, [_P, _L, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "snrf_set_anneal": (_I, [_P, _F]),
     "snrf_feature_slot_stats": (_I, [_P, C.POINTER(C.c_int64), _I]),
     "snrf_upload_proposal": (_I, [_P, _P, _L, C.POINTER(GridDesc), _P]),
@@ -107,7 +108,8 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + srcs
+    extra = os.environ.get("SNRF_NVCC_EXTRA", "").split()  # e.g. -DSNRF_MARCH_MIN_CTAS=4 for a tuning variant
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + srcs
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if proc.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + proc.stdout + proc.stderr)

@@ -65,6 +65,11 @@ struct snrf_ctx {
   int device = 0;
   int sm_count = 148;
   int engine = 1;
+  // cell-major copies of the leading grid levels for the march kernel (snrf_set_brick_budget, bricks.cu)
+  int64_t brick_budget = 4ll << 30;
+  DevBuf prop_brick_store, field_brick_store;
+  BrickDev prop_bricks = {}, field_bricks = {};
+  bool march_v1 = false;  // SNRF_MARCH=v1: the round-1 march kernel (A/B measurements only)
   float et_eps = 0.f;  // snrf_set_early_termination
   float feat_cutoff = -1.f;  // snrf_set_feature_cutoff: < 0 = kernel B on every slot (default), >= 0 = bucketed kernel B'
   const float* jitter = nullptr;  // snrf_set_jitter: training-mode draws for the next render / sample call
@@ -197,6 +202,54 @@ int stage(snrf_ctx* ctx, const float* src, int64_t n, DevBuf& tmp, cudaStream_t 
   return SNRF_OK;
 }
 
+// (Re)build the bricks of one F = 2 grid: the longest prefix of levels whose bricks fit `budget` bytes.
+// Returns the bytes used through *used.
+int build_bricks(snrf_ctx* ctx, const GridDev& G, int64_t budget, DevBuf& store, BrickDev& B, int64_t* used, cudaStream_t s) {
+  memset(&B, 0, sizeof(B));
+  *used = 0;
+  int n = 0;
+  size_t total = 0;
+  size_t off[kMaxLevels];
+  for (int l = 0; l < G.n_levels; ++l) {
+    const uint64_t r = G.lv[l].res;
+    const uint64_t cells = r * r * r;
+    if (cells > 0xFFFFFFFFull / 2) break;  // cell indices (and 2 x cell) stay 32-bit in the kernel
+    const size_t bytes = static_cast<size_t>(cells) * 32;
+    if (static_cast<int64_t>(total + bytes) > budget) break;
+    off[l] = total;
+    total += bytes;
+    n = l + 1;
+  }
+  if (n == 0) {
+    store.release();
+    return SNRF_OK;
+  }
+  if (store.bytes < total || store.bytes > total + (64u << 20)) store.release();  // shrink when the budget drops
+  CK(store.ensure(total));
+  for (int l = 0; l < n; ++l) {
+    uint4* dst = reinterpret_cast<uint4*>(static_cast<char*>(store.p) + off[l]);
+    LAUNCH(launch_brick_build(G, l, dst, s));
+    B.lv[l] = dst;
+  }
+  B.n = n;
+  *used = static_cast<int64_t>(total);
+  return SNRF_OK;
+}
+
+int rebuild_all_bricks(snrf_ctx* ctx, cudaStream_t s) {
+  int64_t used_p = 0, used_f = 0;
+  if (ctx->have_prop) {
+    int rc = build_bricks(ctx, ctx->prop_grid, ctx->brick_budget, ctx->prop_brick_store, ctx->prop_bricks, &used_p, s);
+    if (rc) return rc;
+  }
+  if (ctx->have_base) {
+    int rc = build_bricks(ctx, ctx->field_grid, ctx->brick_budget - used_p, ctx->field_brick_store, ctx->field_bricks, &used_f, s);
+    if (rc) return rc;
+  }
+  CK(cudaStreamSynchronize(s));
+  return SNRF_OK;
+}
+
 void default_pdf_u(float* u, int n_bins) {
   // u[0..n):   torch.linspace(0, 1 - 1/n_bins, n_bins) (float32, symmetric fill) + 1/(2 n_bins)   ray_samplers.py:325-327
   // u[n..2n):  the same linspace without the offset (training mode adds rand / n_bins instead, :314-322)
@@ -251,6 +304,8 @@ int snrf_ctx_create(int device, snrf_ctx** out) {
   snrf_ctx* ctx = new snrf_ctx();
   ctx->device = device;
   ctx->sm_count = prop.multiProcessorCount;
+  if (const char* e = getenv("SNRF_MARCH")) ctx->march_v1 = strcmp(e, "v1") == 0;
+  if (const char* e = getenv("SNRF_BRICK_GB")) ctx->brick_budget = static_cast<int64_t>(atof(e) * (1ll << 30));
   if (prop.major != 10) {
     // this library is compiled for sm_100a only; refuse loudly instead of failing at the first launch
     fprintf(stderr, "libsnrf: device %d is sm_%d%d, built for sm_100a\n", device, prop.major, prop.minor);
@@ -294,6 +349,7 @@ void snrf_ctx_destroy(snrf_ctx* ctx) {
   ctx->bwd_scratch.release(); ctx->bwd_sink.release();
   for (int i = 0; i < 2; ++i) { ctx->bucket_lists[i].release(); ctx->bucket_counts[i].release(); }
   ctx->bucket_totals.release();
+  ctx->prop_brick_store.release(); ctx->field_brick_store.release();
   ctx->hbar[0][1].release(); ctx->hbar[1][0].release(); ctx->hbar[1][1].release();
   if (ctx->aux_feat) cudaStreamDestroy(ctx->aux_feat);
   if (ctx->aux_out) cudaStreamDestroy(ctx->aux_out);
@@ -330,6 +386,18 @@ int snrf_set_engine(snrf_ctx* ctx, int engine) {
 int snrf_set_early_termination(snrf_ctx* ctx, float eps) {
   if (!ctx || !(eps >= 0.f) || eps >= 0.5f) return fail(ctx, SNRF_E_INVALID, "early-termination threshold must be in [0, 0.5)");
   ctx->et_eps = eps;
+  return SNRF_OK;
+}
+
+int snrf_set_brick_budget(snrf_ctx* ctx, int64_t bytes, int* prop_levels, int* field_levels) {
+  if (!ctx || bytes < 0) return fail(ctx, SNRF_E_INVALID, "brick budget must be >= 0 bytes");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaDeviceSynchronize());  // no render may still be reading the old bricks
+  ctx->brick_budget = bytes;
+  int rc = rebuild_all_bricks(ctx, nullptr);
+  if (rc) return rc;
+  if (prop_levels) *prop_levels = ctx->prop_bricks.n;
+  if (field_levels) *field_levels = ctx->field_bricks.n;
   return SNRF_OK;
 }
 
@@ -460,7 +528,7 @@ int snrf_upload_proposal(snrf_ctx* ctx, const float* params, int64_t n, const sn
   tmp.release();
   ctx->prop_grid = to_dev(grid, ctx->prop_table.as<__half>());
   ctx->have_prop = true;
-  return SNRF_OK;
+  return rebuild_all_bricks(ctx, s);
 }
 
 int snrf_upload_field_base(snrf_ctx* ctx, const float* params, int64_t n, const snrf_grid_desc* grid, void* stream) {
@@ -488,7 +556,7 @@ int snrf_upload_field_base(snrf_ctx* ctx, const float* params, int64_t n, const 
   tmp.release();
   ctx->field_grid = to_dev(grid, ctx->field_table.as<__half>());
   ctx->have_base = true;
-  return SNRF_OK;
+  return rebuild_all_bricks(ctx, s);
 }
 
 int snrf_upload_field_head(snrf_ctx* ctx, const float* params, int64_t n, void* stream) {
@@ -627,6 +695,8 @@ static int fill_march(snrf_ctx* ctx, MarchParams& M, const float* origins, const
   M.far_default = o->far_plane;
   M.prop = ctx->prop_grid;
   M.field = ctx->field_grid;
+  M.prop_bricks = ctx->prop_bricks;
+  M.field_bricks = ctx->field_bricks;
   M.wfrag = ctx->wfrag.as<uint2>();
   M.pdf_u = ctx->pdf_u.as<float>();
   M.hist_padding = o->hist_padding;
@@ -748,7 +818,7 @@ static int render_chunk(snrf_ctx* ctx, const float* origins, const float* dirs, 
     M.dbg_density = dbg->density;
     M.dbg_rgb = dbg->rgb_samples;
   }
-  TIMED_LAUNCH(0, cs.march, launch_march(M, ctx->sm_count, cs.march));
+  TIMED_LAUNCH(0, cs.march, ctx->march_v1 ? launch_march_v1(M, ctx->sm_count, cs.march) : launch_march(M, ctx->sm_count, cs.march));
   if (dbg && dbg->sam_t) {
     CK(cudaMemcpyAsync(dbg->sam_t, M.sam_t, n_rays * 16 * 4, cudaMemcpyDeviceToDevice, cs.march));
     if (dbg->sam_w) CK(cudaMemcpyAsync(dbg->sam_w, M.sam_w, n_rays * 16 * 4, cudaMemcpyDeviceToDevice, cs.march));
@@ -1273,7 +1343,7 @@ int snrf_sample(snrf_ctx* ctx, const float* origins, const float* dirs, const fl
   M.dbg_w0 = prop_weights;
   M.dbg_edges = edges;
   M.prop_depth = prop_depth;
-  LAUNCH(launch_march(M, ctx->sm_count, s));
+  LAUNCH(ctx->march_v1 ? launch_march_v1(M, ctx->sm_count, s) : launch_march(M, ctx->sm_count, s));
   return SNRF_OK;
 }
 

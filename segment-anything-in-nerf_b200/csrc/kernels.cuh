@@ -36,6 +36,18 @@ __device__ __forceinline__ void store_rep(float* local, const OutRep& R, int64_t
   }
 }
 
+// "Bricks": a level of an F = 2 grid re-laid-out by cell.  Brick c = gx + gy res + gz res^2 holds the 8 corner
+// entries of cell (gx,gy,gz) - corner dx + 2 dy + 4 dz, fetched with the level's own index rule (dense with wrap, or
+// the hash) - as 32 contiguous, 32-byte aligned bytes: one sector and one LDG.256 per (sample, level) instead of 8
+// scattered 4-byte gathers.  Values are copies of table entries, so results are bit-identical; the price is HBM
+// capacity (res^3 x 32 B per level: 9.3 GB for levels 0-11 of the nerfacto grid), which a 180 GB part has to spare.
+// Built by snrf_set_brick_budget / the upload calls (bricks.cu); lv[l] is valid for l < n (a prefix of the levels).
+struct BrickDev {
+  const uint4* lv[kMaxLevels];
+  int n;
+};
+cudaError_t launch_brick_build(const GridDev& G, int level, uint4* out, cudaStream_t stream);
+
 struct MarchParams {
   const float* origins;  // [N,3]
   const float* dirs;     // [N,3]
@@ -45,6 +57,8 @@ struct MarchParams {
   float near_default, far_default;
   GridDev prop;          // 5 levels x 2
   GridDev field;         // 16 levels x 2
+  BrickDev prop_bricks;  // cell-major copies of the leading levels (n = 0: none)
+  BrickDev field_bricks;
   const uint2* wfrag;    // kMarchFragTiles x 32 fragment words
   const float* pdf_u;    // [33] eval-mode PDF sample positions
   float hist_padding;
@@ -71,6 +85,8 @@ struct MarchParams {
   float anneal;             // proposal-weight annealing exponent (training instantiation only; 1 = off)
 };
 cudaError_t launch_march(const MarchParams& P, int sm_count, cudaStream_t stream);
+// round-1 kernel (march_v1.cu), kept for A/B measurements: SNRF_MARCH=v1
+cudaError_t launch_march_v1(const MarchParams& P, int sm_count, cudaStream_t stream);
 
 // ---- kernel B: feature-field gather + first MLP layer + weighted sample reduction ---------------
 struct SamParams {

@@ -160,6 +160,14 @@ class Renderer:
         (0 = exact, the default).  See ``snrf_set_early_termination`` for the error bounds."""
         self._check(self.lib.snrf_set_early_termination(self.h, float(eps)))
 
+    def set_brick_budget(self, gigabytes: float):
+        """HBM budget for the cell-major "brick" copies of the leading proposal / nerfacto grid levels
+        (``snrf_set_brick_budget``; default 4 GiB, 0 = off; results are bit-identical with any budget).
+        Returns ``(proposal_levels, field_levels)`` bricked."""
+        a, b = C.c_int(0), C.c_int(0)
+        self._check(self.lib.snrf_set_brick_budget(self.h, int(gigabytes * (1 << 30)), C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def set_anneal(self, anneal: float) -> None:
         """Proposal-weight annealing exponent for training-mode sampling (``snrf_set_anneal``; 1 = off)."""
         self._check(self.lib.snrf_set_anneal(self.h, float(anneal)))
@@ -569,8 +577,10 @@ class Renderer:
         Returns the device tensor so that the caller keeps it alive across the launch."""
         if jitter is None:
             return None
-        j = jitter.to(device=self.device, dtype=torch.float32).reshape(n, 2).contiguous()
-        self._check(self.lib.snrf_set_jitter(self.h, j.data_ptr(), n))
+        j = jitter.to(device=self.device, dtype=torch.float32).reshape(-1, 2).contiguous()
+        # the library compares the row count with the ray count of the call that consumes the draws and refuses a
+        # mismatch (SNRF_E_INVALID, "snrf_set_jitter was given ..."), so hand over what was really given
+        self._check(self.lib.snrf_set_jitter(self.h, j.data_ptr(), j.shape[0]))
         return j
 
     def sample(self, origins, directions, nears=None, fars=None, jitter: Optional[torch.Tensor] = None):

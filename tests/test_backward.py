@@ -33,6 +33,23 @@ def oracle_branch(orc, which, o, d, sam_t, sam_w):
     return (sam_w[..., None] * f[which]).sum(dim=-2), f
 
 
+def oracle_branch_at(orc, which, o, d, sam_t, sam_w, enc_saved):
+    """``oracle_branch`` evaluated at saved encoder outputs: the value of the hash-grid encoding is ``enc_saved``
+    (what the device forward stored for its backward), its gradient is the oracle encoder's."""
+    from oracle import tcnn_spec as T
+    from oracle.samnerf_oracle import contract
+
+    n = o.shape[0]
+    pos = o[:, None, :] + d[:, None, :] * sam_t[..., None] / 2.0
+    x = (contract(pos.reshape(-1, 3), None) + 2.0) / 4.0
+    stem = "clip" if which == "sam" else "clipseg"
+    enc = torch.cat([T.hash_grid_encode(x, orc.p[f"sam_field.{stem}_encs.{i}.params"], lv, g.n_features)
+                     for i, (lv, g) in enumerate(zip(orc.sam_levels, orc.cfg.sam_grids))], dim=-1)
+    enc = enc + (enc_saved.reshape(enc.shape).float() - enc).detach()
+    f = T.mlp_forward(enc, orc.sam_w if which == "sam" else orc.clipseg_w).view(n, sam_t.shape[1], -1)
+    return (sam_w[..., None] * f).sum(dim=-2)
+
+
 def _fresh_oracle(cfg, params):
     from oracle.samnerf_oracle import Oracle
 
@@ -146,7 +163,6 @@ def test_oracle_gradients_are_straight_through_fp16():
 
 # ---------------------------------------------------------------------------------------------------------
 @pytest.mark.gpu
-@pytest.mark.hw_unverified
 @pytest.mark.parametrize("which,clipseg,cutoff", [("sam", False, -1.0), ("clipseg", True, -1.0), ("sam", False, 1e-3)])
 def test_gpu_backward_matches_autograd(which, clipseg, cutoff):
     from helpers import assert_features_close, make_renderer
@@ -160,14 +176,20 @@ def test_gpu_backward_matches_autograd(which, clipseg, cutoff):
     sam_w, order = sam_w.sort(dim=-1, descending=True)  # slot = rank, as the march kernel stores the picks
     sam_t = torch.gather(sam_t, 1, order)
     keep = _significant_prefix_mask(sam_w, cutoff)
-    orc, p = _fresh_oracle(cfg, params)
-    out, _ = oracle_branch(orc, which, o, d, sam_t, sam_w * keep)
-    g_out = torch.randn(out.shape, generator=torch.Generator().manual_seed(1))
-    (out * g_out).sum().backward()
     got_out, enc = r.feature_forward(which, o, d, sam_t, sam_w)
     with torch.no_grad():  # the training forward evaluates every slot (it saves all encoder outputs)
         out_full, _ = oracle_branch(orc0, which, o, d, sam_t, sam_w)
     assert_features_close(got_out, out_full, which + " forward", row_frac=0.99)
+    # Reference gradient = autograd through the oracle AT THE FORWARD THE DEVICE COMPUTED: the saved fp16 encoder
+    # outputs replace the oracle's own (value only - the gradient still flows into the oracle's tables).  Without this
+    # the comparison is ill-posed at this size: a 1-ulp fp16 flip of one encoder output moves a hidden pre-activation
+    # by ~1e-5, which flips the ReLU mask of a unit sitting that close to zero (expected a handful of times among
+    # 700 x 16 x 256 units), and one flipped unit of a heavy sample changes a row of dW1 by O(|w g x|) ~ 0.5 - that
+    # is a property of differentiating a rounded forward, not an error of either side.
+    orc, p = _fresh_oracle(cfg, params)
+    out = oracle_branch_at(orc, which, o, d, sam_t, sam_w * keep, enc.cpu())
+    g_out = torch.randn(out.shape, generator=torch.Generator().manual_seed(1))
+    (out * g_out).sum().backward()
     grads = r.feature_backward(which, o, d, sam_t, sam_w, enc, g_out)
     torch.cuda.synchronize()
     enc_names = [f"sam_field.{'clip' if which == 'sam' else 'clipseg'}_encs.{i}.params" for i in range(2)]
@@ -175,17 +197,20 @@ def test_gpu_backward_matches_autograd(which, clipseg, cutoff):
     for i in range(2):
         _assert_grad_close(grads[f"grid{i}"].cpu(), p[enc_names[i]].grad, f"d table {i}")
     # properties that hold at any size: linear in d_out, accumulating (+=), frozen parameters untouched
+    # (the sums are fp32 atomics in launch order: two runs agree to rounding of the largest terms, not of the result)
+    def same(a, b):
+        return float((a - b).abs().max()) <= 2e-5 * float(b.abs().max())
+
     g2 = r.feature_backward(which, o, d, sam_t, sam_w, enc, 2.0 * g_out)
-    assert torch.allclose(g2["net"], 2.0 * grads["net"], rtol=1e-4, atol=1e-7)
+    assert same(g2["net"], 2.0 * grads["net"]) and same(g2["grid0"], 2.0 * grads["grid0"])
     acc = {k: v.clone() for k, v in grads.items()}
     r.feature_backward(which, o, d, sam_t, sam_w, enc, g_out, grads=acc)
-    assert torch.allclose(acc["grid1"], 2.0 * grads["grid1"], rtol=1e-4, atol=1e-7)
+    assert same(acc["grid1"], 2.0 * grads["grid1"]) and same(acc["net"], 2.0 * grads["net"])
     only_net = r.feature_backward(which, o, d, sam_t, sam_w, enc, g_out, want=("net",))
-    assert set(only_net) == {"net"} and torch.allclose(only_net["net"], grads["net"], rtol=1e-4, atol=1e-7)
+    assert set(only_net) == {"net"} and same(only_net["net"], grads["net"])
 
 
 @pytest.mark.gpu
-@pytest.mark.hw_unverified
 def test_gpu_training_step_reduces_the_loss():
     """Autograd shim: one Adam step on the sam_field parameters through libsnrf lowers an MSE distillation loss."""
     from samnerf_b200.nerfstudio_api import SAMModel
@@ -443,7 +468,6 @@ def test_training_step_gradients_match_autograd_end_to_end(monkeypatch):
 # the same comparisons through the C ABI on a GPU
 # ---------------------------------------------------------------------------------------------------------
 @pytest.mark.gpu
-@pytest.mark.hw_unverified
 @pytest.mark.parametrize("which", ["field", "proposal"])
 def test_gpu_field_backward_matches_autograd(which):
     from helpers import make_renderer
@@ -482,7 +506,6 @@ def test_gpu_field_backward_matches_autograd(which):
 
 
 @pytest.mark.gpu
-@pytest.mark.hw_unverified
 def test_gpu_ray_op_backward_matches_autograd():
     from helpers import make_renderer
     from oracle.samnerf_oracle import composite_rgb, get_weights
@@ -511,9 +534,9 @@ def test_gpu_ray_op_backward_matches_autograd():
 
 
 @pytest.mark.gpu
-@pytest.mark.hw_unverified
 def test_gpu_full_training_step_lowers_rgb_and_feature_losses():
     from samnerf_b200.nerfstudio_api import RayBundle, SAMModel
+    from samnerf_b200.training import interlevel_loss
 
     cfg, params, _ = model_pair("tiny", "scene", 25, False, 1)
     m = SAMModel(cfg)
@@ -533,7 +556,10 @@ def test_gpu_full_training_step_lowers_rgb_and_feature_losses():
         out = m(bundle, get_feature=["sam"])
         rgb_loss = torch.nn.functional.mse_loss(out["rgb"], image)
         sam_loss = torch.nn.functional.mse_loss(out["sam"], feat, reduction="none").mean(dim=-1).nanmean()
-        (rgb_loss + sam_loss).backward()
+        # the proposal network only learns from the interlevel loss (the sampler detaches its bins, ray_samplers.py:357;
+        # nerfacto.py:324-327), exactly as in the reference: without it its gradient is None there too
+        prop_loss = interlevel_loss(out["weights_list"], out["ray_samples_list"])
+        (rgb_loss + sam_loss + prop_loss).backward()
         assert all(q.grad is not None and torch.isfinite(q.grad).all() for g in groups.values() for q in g)
         opt.step()
         hist.append((float(rgb_loss.detach()), float(sam_loss.detach())))
@@ -603,7 +629,6 @@ def test_conv_head_kernel_bodies_match_autograd():
 
 
 @pytest.mark.gpu
-@pytest.mark.hw_unverified
 def test_gpu_conv_head_backward_matches_autograd():
     from helpers import make_renderer
 

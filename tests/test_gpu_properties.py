@@ -60,6 +60,28 @@ def test_chunking_and_determinism(full):
         assert torch.equal(a[k][perm], c[k]), f"{k}: depends on position in the batch"
 
 
+def test_bricks_are_a_pure_relayout(full):
+    """Cell-major "brick" copies of the leading grid levels (snrf_set_brick_budget, csrc/bricks.cu) hold verbatim table
+    entries: any budget - none, the dense levels only, the default prefix - renders the same bits, per-sample debug
+    outputs included."""
+    cfg, r = full
+    o, d = test_rays(3000, seed=8)
+    o, d = o.cuda(), d.cuda()
+    outs, levels = {}, {}
+    try:
+        for gb in (0.0, 0.02, 1.5, 4.0):
+            levels[gb] = r.set_brick_budget(gb)
+            outs[gb] = r.render(o, d, get_feature=("sam",), debug=True)
+            torch.cuda.synchronize()
+    finally:
+        r.set_brick_budget(4.0)
+    assert levels[0.0] == (0, 0) and levels[4.0][0] == 5 and levels[4.0][1] >= 10, levels
+    assert levels[0.0] < levels[0.02] < levels[1.5] <= levels[4.0], levels
+    for gb in (0.02, 1.5, 4.0):
+        for k in ("rgb", "depth", "accumulation", "prop_depth_0", "sam", "_prop_weights", "_edges", "_density", "_weights"):
+            assert torch.equal(outs[0.0][k], outs[gb][k]), f"{k}: bricks ({gb} GB -> {levels[gb]} levels) change the result"
+
+
 def test_edge_cases(full):
     cfg, r = full
     o, d = test_rays(64, seed=4)
@@ -139,7 +161,6 @@ def test_replication_descriptor_is_validated(full):
     assert torch.equal(frame, mirror) and torch.isfinite(frame).any()
 
 
-@pytest.mark.hw_unverified
 def test_early_termination_stays_within_its_bounds(full):
     """Opt-in early termination (snrf_set_early_termination): rgb / accumulation within eps, depth and features
     unchanged up to the eps-weighted tail; switching it off restores the exact bits."""
@@ -166,7 +187,6 @@ def test_early_termination_stays_within_its_bounds(full):
         r.set_early_termination(0.7)
 
 
-@pytest.mark.hw_unverified
 @pytest.mark.parametrize("cutoff,rel", [(0.0, 2e-4), (2.0 ** -24, 2e-4)])
 def test_bucketed_feature_kernel_matches_kernel_b(full, cutoff, rel):
     """snrf_set_feature_cutoff: rays bucketed by their significant-slot count give the same feature rows as the

@@ -119,7 +119,6 @@ def test_oracle_reproduces_the_synthetic_orbit_camera():
 
 # ---------------------------------------------------------------------------------------------------------
 @pytest.mark.gpu
-@pytest.mark.hw_unverified
 @pytest.mark.parametrize("name", CASES)
 def test_gpu_kernel_matches_oracle(name):
     from samnerf_b200 import SAMNeRFConfig
@@ -147,7 +146,6 @@ def test_gpu_kernel_matches_oracle(name):
 
 
 @pytest.mark.gpu
-@pytest.mark.hw_unverified
 def test_gpu_render_camera_equals_render_frame():
     from helpers import make_renderer, model_pair
     from samnerf_b200.renderer import Camera
@@ -175,7 +173,6 @@ def test_gpu_render_camera_equals_render_frame():
 
 
 @pytest.mark.gpu
-@pytest.mark.hw_unverified
 def test_gpu_model_from_camera_equals_model_from_ray_bundle():
     """SAMModel.get_outputs_for_camera == get_outputs_for_camera_ray_bundle on the rays of the same camera."""
     from helpers import model_pair
@@ -199,7 +196,6 @@ def test_gpu_model_from_camera_equals_model_from_ray_bundle():
 
 
 @pytest.mark.gpu
-@pytest.mark.hw_unverified
 def test_gpu_crop_box_render():
     """snrf_render_camera with a crop box == snrf_render with the nears / fars snrf_generate_rays reports."""
     from helpers import make_renderer, model_pair
