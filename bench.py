@@ -1,25 +1,29 @@
 #!/usr/bin/env python
 """Headline benchmark: Mrays/s rendering RGB + 256-d SAM features at 800x800 (BASELINE.json), 1/2/4/8 B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--config sam|rgb|clipseg_patch]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \\
         bench.py --gpus N --steps K --warmup W
 
-One "step" = one 800x800 frame of the `samnerf_distill` model (SURVEY.md 8 d config 3): 640 000 rays, every ray
-rendered to rgb / median depth / accumulation / proposal depth AND the 256-d SAM feature (k = 16 top samples,
-sharpening 10, patch 1), in the reference's chunks of 32 768 rays, through `libsnrf` (C ABI).  With N > 1 the frame is
-cut into N contiguous row blocks ("screen tiles"), one per rank, and the rendered tiles are exchanged into every
-rank's frame buffer (symmetric memory): by copy engines per chunk (default), by the kernels' own multicast / peer
-stores, or by an NCCL all-gather (--gather).  Total work is fixed, so scaling is "strong".  Synthetic scene-like
-parameters (seed 0), synthetic orbit camera.
+One "step" = one frame.  Default `--config sam` is BASELINE.json configs[2] (the configuration the metric is quoted
+on; SURVEY.md 8 d config 3): the `samnerf_distill` model, 800x800 = 640 000 rays, every ray rendered to rgb / median
+depth / accumulation / proposal depth AND the 256-d SAM feature (k = 16 top samples, sharpening 10, patch 1) through
+`libsnrf` (C ABI).  `--config rgb` is configs[1] (RGB-only), `--config clipseg_patch` is configs[3] (1600x1060 frame +
+patch-aggregated SAM map + ClipSeg map through SAMModel.get_outputs_for_camera_ray_bundle).  With N > 1 the frame is cut
+into N contiguous row blocks ("screen tiles"), one per rank, and the rendered tiles are exchanged into every rank's
+frame buffer (symmetric memory): by copy engines per chunk, by the kernels' own multicast / peer stores, or by an NCCL
+all-gather (--gather).  Total work is fixed, so scaling is "strong".  Synthetic scene-like parameters (seed 0),
+synthetic orbit camera.
 
 `--impl reference` times the reference's own CPU path: the reference is Python + the CUDA-only tinycudann, so its CPU
 implementation is the oracle port (oracle/samnerf_oracle.py, validated against the reference's own modules by
-oracle/make_golden.py), all host threads, on a bounded sample of the same frame per step.
+oracle/make_golden.py), all host threads, on a bounded sample of the same frame per step.  `cpu_baseline` of the
+native line is the same code on the same sample definition.
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -33,10 +37,23 @@ if ROOT not in sys.path:
 
 import torch  # noqa: E402
 
-H = W = 800
-BYTES_PER_RAY = {"proposal": 10240, "field": 16384, "sam": 49152}  # SURVEY.md 8 d / BASELINE.md section 3
-METRIC = "Mrays/s rendering RGB+256-d SAM features at 800x800"
-WORKLOAD = "samnerf_distill 800x800 RGB+256-d SAM (k=16, p=1): 640000 rays in chunks of 32768"
+# algorithmic bytes per ray of each kernel (SURVEY.md 8 d / BASELINE.md section 3):
+#   march:   64 proposal samples x 5 levels x 8 corners x 4 B + 32 nerf samples x 16 levels x 8 corners x 4 B
+#   feature: 16 picked samples x 24 levels x 8 corners x 16 B (every slot), or 3 072 B per evaluated slot (bucketed)
+#   tapgemm: 512 B of fp16 hidden sums read + 1 024 B of fp32 features written per ray
+BYTES_PER_RAY = {"march": 10240 + 16384, "feature": 49152, "tapgemm": 1536}
+CPU_SAMPLE_RAYS = 16384  # one definition for `cpu_baseline` and `--impl reference`
+
+CONFIGS = {
+    "sam": dict(metric="Mrays/s rendering RGB+256-d SAM features at 800x800", H=800, W=800, focal=800.0,
+                workload="samnerf_distill 800x800 RGB+256-d SAM (k=16, p=1): 640000 rays", features=("sam",)),
+    "rgb": dict(metric="Mrays/s rendering RGB only at 800x800 (BASELINE.json configs[1])", H=800, W=800, focal=800.0,
+                workload="samnerf_no_distill 800x800 RGB-only volumetric render: 640000 rays", features=()),
+    "clipseg_patch": dict(metric="Mrays/s rendering the 1600x1060 frame + patch-aggregated SAM map + ClipSeg map (BASELINE.json configs[3])",
+                          H=1060, W=1600, focal=1600.0,
+                          workload="samnerf_distill + ClipSeg head, 1600x1060 through get_outputs_for_camera_ray_bundle "
+                                   "(loops A/B/C: 1696000 + 44032 + 1024 rays, p=4)", features=("sam", "clipseg")),
+}
 
 
 def measured_peaks():
@@ -47,15 +64,37 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic(rays_per_launch: float):
-    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed ncu capture, scaled
-    to this run's rays per launch (None when no capture is committed)."""
-    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    if not os.path.exists(path):
-        return None
-    with open(path) as f:
-        t = json.load(f)["sam_kernel"]
-    return (t["dram_bytes_read"] + t["dram_bytes_write"]) * rays_per_launch / t["rays_per_launch"]
+def source_digest() -> str:
+    """Digest of the CUDA sources: ties committed ncu captures to the build being benchmarked."""
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "segment-anything-in-nerf_b200", "csrc")
+    for name in sorted(os.listdir(d)):
+        if name.endswith((".cu", ".cuh")):
+            with open(os.path.join(d, name), "rb") as f:
+                h.update(name.encode() + b"\0" + f.read())
+    return h.hexdigest()[:16]
+
+
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of each hot kernel from the newest committed ncu
+    capture (profiles/r*_traffic.json, written by tools/ncu_traffic.py from `ncu --set full` reports of bench.py).
+    Returns ({kernel: bytes per ray}, note)."""
+    d = os.path.join(ROOT, "profiles")
+    files = sorted(f for f in os.listdir(d) if f.endswith("_traffic.json")) if os.path.isdir(d) else []
+    if not files:
+        return {}, "no ncu capture committed"
+    with open(os.path.join(d, files[-1])) as f:
+        t = json.load(f)
+    per_ray = {}
+    for k in ("march", "feature", "tapgemm"):
+        e = t.get(k) or t.get(k + "_kernel") or (t.get("sam_kernel") if k == "feature" else None)
+        if e:
+            per_ray[k] = (e["dram_bytes_read"] + e["dram_bytes_write"]) / e["rays_per_launch"]
+    same = t.get("source_digest") == source_digest()
+    note = (f"profiles/{files[-1]}: ncu --set full, dram bytes per launch of bench.py's workload scaled to this run's rays per launch; "
+            + ("captured from exactly these CUDA sources" if same else
+               f"STALE: captured from sources {t.get('source_digest', '(round 1, unrecorded)')}, this build is {source_digest()}"))
+    return per_ray, note
 
 
 class ClockSampler:
@@ -111,98 +150,181 @@ class ClockSampler:
         return out
 
 
-def frame_rays():
+def frame_rays(conf):
     from samnerf_b200.synthetic import orbit_rays
 
-    o, d = orbit_rays(H, W, 800.0)
+    o, d = orbit_rays(conf["H"], conf["W"], conf["focal"])
     return o.reshape(-1, 3).contiguous(), d.reshape(-1, 3).contiguous()
 
 
-def cpu_reference_rate(n_rays: int, repeats: int, cfg, params):
-    """Oracle port on a strided sample of the frame, all host threads.  Returns (Mrays/s best, cores, sample text)."""
-    from oracle.samnerf_oracle import Oracle
+def model_config(name):
+    from samnerf_b200 import SAMNeRFConfig
 
+    if name == "clipseg_patch":
+        return SAMNeRFConfig.distill(clipseg=True, patch_size=4)
+    return SAMNeRFConfig.distill(clipseg=False, patch_size=1)
+
+
+# ---- the CPU arm: one sample definition for `cpu_baseline` (native line) and `--impl reference` -----------------------
+def cpu_sample(o, d, step: int, n: int = CPU_SAMPLE_RAYS):
+    """`n` rays strided over the frame, shifted by `step` so that successive steps see different rays."""
+    idx = ((torch.arange(n) * (o.shape[0] // n)) + step) % o.shape[0]
+    return o[idx].contiguous(), d[idx].contiguous()
+
+
+CPU_SAMPLE_TEXT = (f"{CPU_SAMPLE_RAYS} rays strided over the frame per step (bounded sample of the frame; the stride start moves by one "
+                   "ray per step), oracle port in torch CPU fp32 on all host threads, mean over the timed steps")
+
+
+def cpu_rate(conf_name: str, steps: int, warmup: int, regime: str):
+    """Mrays/s of the oracle port.  Returns (value, ms per step, cores)."""
+    from oracle.samnerf_oracle import Oracle
+    from samnerf_b200 import make_synthetic_params
+
+    conf = CONFIGS[conf_name]
+    cfg = model_config(conf_name)
+    params = make_synthetic_params(cfg, regime, 0)
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     orc = Oracle(cfg, params)
-    o, d = frame_rays()
-    idx = (torch.arange(n_rays) * (o.shape[0] // n_rays)).long()
-    o, d = o[idx].contiguous(), d[idx].contiguous()
-    best = float("inf")
-    for _ in range(repeats):
+    o, d = frame_rays(conf)
+    feats = tuple(conf["features"])
+    times = []
+    for step in range(warmup + steps):
+        oo, dd = cpu_sample(o, d, step)
         t0 = time.perf_counter()
         with torch.no_grad():
-            orc.render_rays(o, d, get_feature=("sam",))
-        best = min(best, time.perf_counter() - t0)
-    return n_rays / best / 1e6, cores, f"{n_rays} rays strided over the 800x800 frame, best of {repeats}, torch CPU fp32"
+            orc.render_rays(oo, dd, get_feature=feats)
+        if step >= warmup:
+            times.append(time.perf_counter() - t0)
+    total = sum(times)
+    return CPU_SAMPLE_RAYS * len(times) / total / 1e6, 1e3 * total / len(times), cores
 
 
 def run_reference(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    if int(os.environ.get("RANK", "0")) != 0:
         return
-    from samnerf_b200 import SAMNeRFConfig, make_synthetic_params
-    from oracle.samnerf_oracle import Oracle
-
-    cfg = SAMNeRFConfig.distill(clipseg=False, patch_size=1)
-    params = make_synthetic_params(cfg, args.regime, 0)
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    orc = Oracle(cfg, params)
-    o, d = frame_rays()
-    n = args.ref_rays
-    times = []
-    for step in range(args.warmup + args.steps):
-        idx = ((torch.arange(n) * (o.shape[0] // n)) + step) % o.shape[0]
-        oo, dd = o[idx].contiguous(), d[idx].contiguous()
-        t0 = time.perf_counter()
-        with torch.no_grad():
-            orc.render_rays(oo, dd, get_feature=("sam",))
-        dt = time.perf_counter() - t0
-        if step >= args.warmup:
-            times.append(dt)
-    total = sum(times)
-    value = n * len(times) / total / 1e6
-    sample = f"{n} rays strided over the 800x800 frame per step (bounded sample of the 640000-ray frame)"
+    conf = CONFIGS[args.config]
+    value, ms, cores = cpu_rate(args.config, args.steps, args.warmup, args.regime)
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True,
+        "impl": "reference", "metric": conf["metric"], "value": value, "unit": "Mrays/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "regime": args.regime, "note": "reference CPU path = oracle port (tinycudann is CUDA-only)"},
-        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": conf["workload"], "regime": args.regime,
+                   "note": "reference CPU path = oracle port (the reference's tinycudann dependency is CUDA-only)"},
+        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": CPU_SAMPLE_TEXT},
         "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
+# ---- config 4: the reference-faithful whole-image call through the model shim -----------------------------------------
+def run_clipseg_patch(args, dev):
+    from samnerf_b200 import make_synthetic_params
+    from samnerf_b200.config import get_feature_size
+    from samnerf_b200.nerfstudio_api import RayBundle, SAMModel
+
+    conf = CONFIGS["clipseg_patch"]
+    cfg = model_config("clipseg_patch")
+    m = SAMModel(cfg)
+    m.load_state_dict(make_synthetic_params(cfg, args.regime, 0))
+    if args.brick_gb >= 0:
+        m.renderer.set_brick_budget(args.brick_gb)
+    H, W = conf["H"], conf["W"]
+    o, d = frame_rays(conf)
+    o_host, d_host = o.view(H, W, 3).pin_memory(), d.view(H, W, 3).pin_memory()
+    area = torch.ones(H, W, 1, device=dev)
+    cam = torch.zeros(H, W, 1, dtype=torch.long, device=dev)
+    bundle = RayBundle(origins=o_host.to(dev), directions=d_host.to(dev), pixel_area=area, camera_indices=cam)
+    fh, fw = get_feature_size(H, W)
+    n_rays = H * W + fh * 4 * fw * 4 + 1024
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    for _ in range(max(args.warmup, 3)):
+        outs = m.get_outputs_for_camera_ray_bundle(bundle)
+    torch.cuda.synchronize()
+    launches0 = m.renderer.launch_count
+    clocks = ClockSampler(dev.index)
+    clocks.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for s, e in ev:
+        flush.zero_()
+        s.record()
+        outs = m.get_outputs_for_camera_ray_bundle(bundle)
+        e.record()
+    torch.cuda.synchronize()
+    launches = m.renderer.launch_count - launches0
+    ms = sum(s.elapsed_time(e) for s, e in ev) / args.steps
+    # end to end: pinned host rays in, every output tensor of the call back on the host, inside the timed region
+    keys = [k for k, v in outs.items() if torch.is_tensor(v)]
+    host = {k: torch.empty(outs[k].shape, dtype=outs[k].dtype).pin_memory() for k in keys}
+    e2e_steps = max(3, min(args.steps, 5))
+    ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(e2e_steps)]
+    for i in range(2 + e2e_steps):
+        if i >= 2:
+            ev2[i - 2][0].record()
+        b = RayBundle(origins=o_host.to(dev, non_blocking=True), directions=d_host.to(dev, non_blocking=True),
+                      pixel_area=area, camera_indices=cam)
+        res = m.get_outputs_for_camera_ray_bundle(b)
+        for k in keys:
+            host[k].copy_(res[k], non_blocking=True)
+        if i >= 2:
+            ev2[i - 2][1].record()
+    torch.cuda.synchronize()
+    e2e_ms = sum(s.elapsed_time(e) for s, e in ev2) / e2e_steps
+    clk = clocks.stop()
+    line = {
+        "metric": conf["metric"], "value": n_rays / ms / 1e3, "unit": "Mrays/s", "n_gpus": 1, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f16 operands / f32 accumulate", "data": "synthetic",
+        "config": {"workload": conf["workload"], "regime": args.regime, "rays_per_frame": n_rays,
+                   "sam_map": [fh, fw, 256], "clipseg_map": [32, 32, 192],
+                   "l2": "256 MiB buffer zeroed between timed frames (untimed)"},
+        "roofline": None,
+        "e2e": {"value": n_rays / e2e_ms / 1e3, "unit": "Mrays/s", "h2d_bytes_per_step": 2 * H * W * 3 * 4,
+                "d2h_bytes_per_step": int(sum(host[k].numel() * host[k].element_size() for k in keys)), "steps": e2e_steps,
+                "api": "SAMModel.get_outputs_for_camera_ray_bundle, pinned host ray bundle in, every output tensor copied back"},
+        "gpu_launches": launches, "clocks": clk,
+    }
+    if not args.no_cpu_baseline:
+        v, _, cores = cpu_rate("clipseg_patch", 2, 1, args.regime)
+        line["cpu_baseline"] = {"value": v, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": CPU_SAMPLE_TEXT}
+    print(json.dumps(line), flush=True)
+
+
 def run_native(args):
     import torch.distributed as dist
 
-    from samnerf_b200 import SAMNeRFConfig, make_synthetic_params
+    from samnerf_b200 import make_synthetic_params
     from samnerf_b200.renderer import Renderer
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
-        if world == 1 and args.gpus > 1:
-            raise SystemExit("--gpus N > 1 must be launched with torch.distributed.run (one rank per GPU)")
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        raise SystemExit("--gpus N > 1 must be launched with torch.distributed.run (one rank per GPU)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    if args.config == "clipseg_patch":
+        if world > 1:
+            raise SystemExit("--config clipseg_patch is a single-GPU configuration (BASELINE.json configs[3])")
+        return run_clipseg_patch(args, dev)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    cfg = SAMNeRFConfig.distill(clipseg=False, patch_size=1)
+    conf = CONFIGS[args.config]
+    H, W = conf["H"], conf["W"]
+    feats = conf["features"]
+    cfg = model_config(args.config)
     params = make_synthetic_params(cfg, args.regime, 0)
     r = Renderer(cfg, device=local, engine=args.engine)
     r.load_params(params)
-    brick_levels = r.set_brick_budget(args.brick_gb) if args.brick_gb >= 0 else None
+    brick_gb = args.brick_gb if args.brick_gb >= 0 else 4.0
+    brick_levels = r.set_brick_budget(brick_gb)
     if args.early_termination > 0:
         r.set_early_termination(args.early_termination)  # opt-in, not the reference's exact arithmetic: see config
-    if args.feature_cutoff >= 0:
-        r.set_feature_cutoff(args.feature_cutoff)  # opt-in bucketed feature kernel: see config
-    o_all, d_all = frame_rays()
+    r.set_feature_cutoff(args.feature_cutoff)
+    o_all, d_all = frame_rays(conf)
     n_all = o_all.shape[0]
     assert H % world == 0
     n_loc = n_all // world
@@ -210,22 +332,20 @@ def run_native(args):
     o_host = o_all[lo:lo + n_loc].contiguous().pin_memory()
     d_host = d_all[lo:lo + n_loc].contiguous().pin_memory()
     o_dev, d_dev = o_host.to(dev), d_host.to(dev)
-    # reference chunk size on one GPU; with N ranks the tile is cut finer so that the NVLink exchange of chunk c
-    # overlaps the compute of chunk c+1 (the chunk size is caller-tunable in the reference too, eval_utils.py:90-91)
-    # measured: 32768 is best up to 2 ranks, 16384 at 4 and 8 (profiles/r01_multi_gpu.txt)
-    chunk = args.chunk or (cfg.eval_num_rays_per_chunk if world <= 2 else 16384)
+    # Rays per launch.  The reference's eval_num_rays_per_chunk (32768, samconfigs.py:79) caps the [N,S,C] intermediates
+    # its PyTorch path materialises; this path has none (128 B + 512 B of scratch per ray), so a launch covers 131072 rays
+    # on one GPU (fewer launch tails; measured +8 %), and the tile is cut finer with N ranks so that the exchange of
+    # chunk c overlaps the compute of chunk c+1 (the chunk size is caller-tunable in the reference too, eval_utils.py:90-91)
+    chunk = args.chunk or (131072 if world == 1 else 32768 if world == 2 else 16384)
 
-    # frame-sized outputs; with N > 1 each rank renders into its row block of the gathered frame (in-place all-gather)
-    names = {"rgb": 3, "depth": 1, "accumulation": 1, "prop_depth_0": 1, "sam": cfg.sam_out}
-    # With N > 1 the rendered tiles are exchanged by the kernels themselves: every output row is stored into every
-    # rank's frame buffer over NVLink (one multimem.st through the NVSwitch multicast alias when available, else
-    # peer-mapped pointers), overlapped with the next chunk's compute; a symmetric-memory barrier ends the frame.
-    # Fallback / comparison: NCCL all-gather of the rendered tiles (--gather nccl).
+    names = {"rgb": 3, "depth": 1, "accumulation": 1, "prop_depth_0": 1}
+    if "sam" in feats:
+        names["sam"] = cfg.sam_out
+    # With N > 1 the rendered tiles are exchanged into every rank's frame buffer over NVLink, overlapped with the next
+    # chunk's compute; a symmetric-memory barrier ends the frame.  Fallback / comparison: NCCL all-gather (--gather nccl).
     gather_mode, symm, full = "single", None, {}
     if args.gather == "auto":
-        # what was measured: copy engines at N = 2 and 4, the fused multicast stores at N = 8 (278.9 Mrays/s,
-        # profiles/r01_multi_gpu.txt; the copy-engine mode has not been run on 8 GPUs yet)
-        args.gather = "mc" if world >= 8 else "dma"
+        args.gather = "dma"
     if world > 1:
         gather_mode = "nccl"
         if args.gather != "nccl":
@@ -234,16 +354,12 @@ def run_native(args):
 
                 big = symm_mem.empty(n_all * sum(names.values()), dtype=torch.float32, device=dev)
                 symm = symm_mem.rendezvous(big, dist.group.WORLD.group_name)
-                mc = int(getattr(symm, "multicast_ptr", 0) or 0) if args.gather == "mc" else 0
-                if args.gather == "dma":
-                    r.set_replication_mode("dma")
+                has_mc = bool(int(getattr(symm, "multicast_ptr", 0) or 0)) and args.gather == "mc"
                 off = 0
                 for k, c in names.items():
                     full[k] = big[off:off + n_all * c].view(n_all, c)
-                    peers = [int(symm.buffer_ptrs[p]) + off * 4 for p in range(world) if p != rank]
-                    r.set_replication(k, full[k], () if mc else peers, mc + off * 4 if mc else 0)
                     off += n_all * c
-                gather_mode = ("fused multimem.st (NVSwitch multicast)" if mc else
+                gather_mode = ("fused multimem.st (NVSwitch multicast)" if has_mc else
                                "copy engines (cudaMemcpyAsync to peer buffers per chunk)" if args.gather == "dma" else
                                "fused peer stores (NVLink P2P)")
             except Exception as e:  # no symmetric memory on this box: say so and use NCCL
@@ -254,6 +370,19 @@ def run_native(args):
         if k not in full:
             full[k] = torch.empty(n_all, c, device=dev)
     mine = {k: v[lo:lo + n_loc] for k, v in full.items()}
+
+    def point_replication_at_peers():
+        if symm is None:
+            return
+        mc = int(getattr(symm, "multicast_ptr", 0) or 0) if args.gather == "mc" else 0
+        r.set_replication_mode("dma" if args.gather == "dma" else "stores")
+        off = 0
+        for k, c in names.items():
+            peers = [int(symm.buffer_ptrs[p]) + off * 4 for p in range(world) if p != rank]
+            r.set_replication(k, full[k], () if mc else peers, mc + off * 4 if mc else 0)
+            off += n_all * c
+
+    point_replication_at_peers()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     from samnerf_b200.tiles import all_gather_tiles, ray_block
@@ -262,7 +391,7 @@ def run_native(args):
     r.set_pipeline(args.pipeline)
 
     def frame():
-        r.render_frame(o_dev, d_dev, get_feature=("sam",), chunk=chunk, out=mine)
+        r.render_frame(o_dev, d_dev, get_feature=feats, chunk=chunk, out=mine)
         if world > 1:
             if symm is not None:
                 symm.barrier()  # every rank's stores have landed in every frame buffer
@@ -277,15 +406,30 @@ def run_native(args):
     for _ in range(max(args.warmup, 3)):
         frame()
     barrier()
+    exchange_check = None
     if world > 1:
-        # every rank must now hold the same complete frame: compare per-tile checksums across ranks (untimed)
-        sums = torch.stack([full["sam"][p * n_loc:(p + 1) * n_loc].double().nan_to_num().abs().sum() for p in range(world)]
-                           + [full["rgb"].double().sum()])
+        # (1) every rank must hold the same complete frame: per-tile checksums across ranks; (2) rank 0 renders the whole
+        # frame alone into a private buffer and compares it with the gathered one bit for bit (both untimed)
+        sums = torch.stack([full[k][p * n_loc:(p + 1) * n_loc].double().nan_to_num().abs().sum() for p in range(world)
+                            for k in names])
         allsums = [torch.empty_like(sums) for _ in range(world)]
         dist.all_gather(allsums, sums)
         for p in range(1, world):
             if not torch.equal(allsums[0], allsums[p]) or float(allsums[0].min()) <= 0.0:
                 raise SystemExit(f"tile exchange ({gather_mode}) is wrong: rank 0 {allsums[0].tolist()} vs rank {p} {allsums[p].tolist()}")
+        if rank == 0:
+            for k in names:
+                r.set_replication(k, None)
+            solo = r.render_frame(o_all.to(dev), d_all.to(dev), get_feature=feats, chunk=chunk)
+            torch.cuda.synchronize()
+            bad = [k for k in names if not torch.equal(torch.nan_to_num(solo[k]), torch.nan_to_num(full[k]))]
+            if bad:
+                raise SystemExit(f"gathered frame differs from the single-GPU render of the same rays in {bad}")
+            exchange_check = ("gathered frame on rank 0 is bit-identical to a single-GPU render of all rays; "
+                              "tile checksums agree on every rank")
+            del solo
+            point_replication_at_peers()
+        barrier()
     launches0 = r.launch_count
     clocks = ClockSampler(local)
     if rank == 0:
@@ -300,8 +444,8 @@ def run_native(args):
     barrier()
     launches = r.launch_count - launches0
     # Per-kernel durations for the roofline: the same K steps again with CUDA events around every launch of the
-    # three hot kernels (on the launching stream).  Kept out of the region that produces `value` because 60 event
-    # pairs per frame cost ~2 % of it; clocks are sampled across both passes.
+    # three hot kernels (on the launching stream).  Kept out of the region that produces `value` because the event
+    # pairs cost ~2 % of it; clocks are sampled across both passes.
     r.kernel_times()
     r.set_timing(True)
     r.set_pipeline(0)  # serial launches, so an event pair brackets exactly one kernel
@@ -313,12 +457,11 @@ def run_native(args):
     r.set_pipeline(args.pipeline)
     ktimes = r.kernel_times()
     slot_stats = None
-    if args.feature_cutoff >= 0:
+    if args.feature_cutoff >= 0 and "sam" in feats and args.engine == "tcgen05":
         r.feature_slot_stats(reset=True)
         frame()  # one untimed frame to count the slots the bucketed kernel really evaluates
         barrier()
         slot_stats = r.feature_slot_stats(reset=True)
-    clk = clocks.stop() if rank == 0 else None
     total_ms = sum(s.elapsed_time(e) for s, e in ev)
     t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
     if world > 1:
@@ -327,43 +470,26 @@ def run_native(args):
     value = n_all * args.steps / (total_ms * 1e-3) / 1e6
 
     # ---- end to end: pinned host rays in, host images + features out, copies inside the timed region ----------
+    # The library's copy-engine exchange takes any UVA destination, so the pinned host buffer is registered as the one
+    # "peer": each chunk's feature rows leave for host memory as soon as its output layer has finished, overlapped with
+    # the next chunk's render; the caller's stream resumes when the last copy has landed.  Every rank feeds and drains
+    # its own tile over its own PCIe link (no NVLink exchange here: the frame is assembled in host memory).
     out_host = {k: torch.empty(n_loc, c).pin_memory() for k, c in names.items()}
-    s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
     o_stage, d_stage = torch.empty_like(o_dev), torch.empty_like(d_dev)
+    r.set_replication_mode("dma")
+    for k, c in names.items():
+        r.set_replication(k, full[k], [out_host[k].data_ptr() - lo * c * 4], 0)  # offset-preserving alias of this tile
+    e2e_chunk = args.chunk or 32768
 
     def frame_e2e():
-        cur = torch.cuda.current_stream(dev)
-        done = []
-        for i in range(0, n_loc, chunk):
-            sl = slice(i, min(i + chunk, n_loc))
-            with torch.cuda.stream(s_in):
-                o_stage[sl].copy_(o_host[sl], non_blocking=True)
-                d_stage[sl].copy_(d_host[sl], non_blocking=True)
-                ready = torch.cuda.Event()
-                ready.record(s_in)
-            cur.wait_event(ready)
-            r.render(o_stage[sl], d_stage[sl], get_feature=("sam",), out={k: v[sl] for k, v in mine.items()})
-            rendered = torch.cuda.Event()
-            rendered.record(cur)
-            last = i + chunk >= n_loc
-            with torch.cuda.stream(s_out):
-                s_out.wait_event(rendered)
-                # the 256-d features (98 % of the bytes) leave chunk by chunk, overlapped with the next chunk's
-                # render; the four small per-ray outputs go once, after the last chunk (4 copies instead of 4 per chunk)
-                out_host["sam"][sl].copy_(mine["sam"][sl], non_blocking=True)
-                if last:
-                    for k in names:
-                        if k != "sam":
-                            out_host[k].copy_(mine[k], non_blocking=True)
-                fin = torch.cuda.Event()
-                fin.record(s_out)
-            done.append(fin)
-        for f in done:
-            cur.wait_event(f)
+        o_stage.copy_(o_host, non_blocking=True)
+        d_stage.copy_(d_host, non_blocking=True)
+        r.render_frame(o_stage, d_stage, get_feature=feats, chunk=e2e_chunk, out=mine)
 
     for _ in range(2):
         frame_e2e()
     barrier()
+    e2e_ok = all(torch.equal(torch.nan_to_num(out_host[k]), torch.nan_to_num(mine[k].cpu())) for k in names)
     e2e_steps = max(3, min(args.steps, 5))
     ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(e2e_steps)]
     for s, e in ev2:
@@ -371,63 +497,81 @@ def run_native(args):
         frame_e2e()
         e.record()
     barrier()
+    clk = clocks.stop() if rank == 0 else None
+    for k in names:
+        r.set_replication(k, None)
     t2 = torch.tensor([sum(s.elapsed_time(e) for s, e in ev2)], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t2, op=dist.ReduceOp.MAX)
     e2e_value = n_all * e2e_steps / (float(t2.item()) * 1e-3) / 1e6
     h2d = 2 * n_all * 3 * 4
     d2h = n_all * sum(names.values()) * 4
+    if not e2e_ok:
+        raise SystemExit("end-to-end path: the host copy differs from the device frame")
 
     if rank == 0:
         peak, peak_src = measured_peaks()
-        f_ms, f_cnt = ktimes["feature"]
-        m_ms, m_cnt = ktimes["march"]
-        g_ms, g_cnt = ktimes["tapgemm"]
-        rays_per_launch = n_loc * args.steps / max(f_cnt, 1)
-        ach = BYTES_PER_RAY["sam"] * rays_per_launch / (f_ms / max(f_cnt, 1) * 1e-3) / 1e9 if f_ms > 0 else None
-        if slot_stats is not None and f_ms > 0:
-            # bucketed kernel: state the roofline on the slots it gathers (3 072 B each), not on all 16 per ray
-            slots_per_ray = slot_stats[1] / max(n_loc, 1)
-            ach = 3072.0 * slots_per_ray * rays_per_launch / (f_ms / max(f_cnt, 1) * 1e-3) / 1e9
-        path_bytes = sum(BYTES_PER_RAY.values())
+        traffic, traffic_note = ncu_traffic()
+        kernels = {}
+        for k in ("march", "feature", "tapgemm"):
+            ms, cnt = ktimes[k]
+            if cnt == 0:
+                continue
+            rays_per_launch = n_loc * args.steps / cnt
+            bpr = BYTES_PER_RAY[k]
+            extra = {}
+            if k == "feature" and slot_stats is not None:
+                slots_per_ray = slot_stats[1] / max(n_loc, 1)
+                bpr = 3072.0 * slots_per_ray
+                extra = {"feature_slots": {"rays_per_bucket_1_2_4_8_16": slot_stats[0], "slots_per_ray": slots_per_ray,
+                                           "note": "bucketed kernel: achieved / algorithmic bytes count the evaluated slots only "
+                                                   "(3072 B each); all 16 slots of every ray would be 49152 B/ray"}}
+            ach = bpr * rays_per_launch / (ms / cnt * 1e-3) / 1e9
+            kernels[k] = {"ms_per_step": ms / args.steps, "avg_launch_ms": ms / cnt, "launches_timed": cnt,
+                          "algorithmic_bytes_per_ray": bpr, "algorithmic_bytes_per_launch": bpr * rays_per_launch,
+                          "achieved": ach, "frac": ach / peak,
+                          "traffic": traffic[k] * rays_per_launch if k in traffic else None, **extra}
+        top = max(kernels, key=lambda k: kernels[k]["ms_per_step"])
+        names_long = {"march": "march_kernel (proposal sampling + nerfacto field + compositing + top-k)",
+                      "feature": ("sam_bucket_kernel" if slot_stats is not None else "sam_kernel") +
+                                 " (feature-field gather + MLP layer 1 + weighted sum)",
+                      "tapgemm": "tapgemm_kernel (feature MLP output layer)"}
+        path_bytes = sum(kernels[k]["algorithmic_bytes_per_ray"] for k in kernels)
         line = {
-            "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
+            "metric": conf["metric"], "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f16 operands / f32 accumulate", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "regime": args.regime, "engine": args.engine,
-                       "l2": "256 MiB buffer zeroed between timed frames (untimed); tables 158 MB + outputs 668 MB > 126 MB L2",
-                       "tiles": (f"{world} row blocks of {H // world} rows; 256-d features exchanged by {gather_mode}, "
+            "config": {"workload": conf["workload"], "regime": args.regime, "engine": args.engine,
+                       "l2": "256 MiB buffer zeroed between timed frames (untimed); tables + bricks + outputs > 126 MB L2",
+                       "tiles": (f"{world} row blocks of {H // world} rows; outputs exchanged by {gather_mode}, "
                                  "frame ends with a symmetric-memory barrier") if world > 1 else "single GPU",
+                       "exchange_check": exchange_check,
                        "early_termination": args.early_termination or None,
                        "feature_cutoff": args.feature_cutoff if args.feature_cutoff >= 0 else None,
-                       "bricks": None if brick_levels is None else {"budget_gib": args.brick_gb, "proposal_levels": brick_levels[0], "field_levels": brick_levels[1]},
-                       "chunk": chunk, "pipeline": "chunks pipelined over 3 streams" if (args.pipeline == 2 or (args.pipeline == 1 and world > 1 and symm is not None and args.gather in ("mc", "peer"))) else "sequential"},
-            "roofline": {"bound": "hbm", "kernel": "sam_kernel (feature-field gather + MLP layer 1 + weighted sum)",
-                         "achieved": ach, "peak": peak, "unit": "GB/s", "frac": (ach / peak) if ach else None,
-                         "traffic": ncu_traffic(rays_per_launch), "peak_source": peak_src,
-                         "traffic_note": "ncu dram bytes of one launch (profiles/r01_traffic.json): far below the "
-                                         "algorithmic bytes - the launch's table footprint is L2/L1-resident; the kernel "
-                                         "is bound by the L1 tag stage and issue, not HBM (DESIGN.md section 4 B)",
-                         "algorithmic_bytes_per_launch": (BYTES_PER_RAY["sam"] if slot_stats is None else
-                                                          3072.0 * slot_stats[1] / max(n_loc, 1)) * rays_per_launch,
-                         "feature_slots": None if slot_stats is None else {
-                             "rays_per_bucket_1_2_4_8_16": slot_stats[0], "slots_per_ray": slot_stats[1] / max(n_loc, 1),
-                             "note": "bucketed kernel: achieved / algorithmic bytes count the evaluated slots only; "
-                                     "all 16 slots would be 49152 B/ray"},
-                         "avg_launch_ms": f_ms / max(f_cnt, 1), "launches_timed": f_cnt,
-                         "timing_note": "CUDA events around each launch, instrumented repeat of the K timed steps (same inputs, L2 flushed)",
+                       "bricks": {"budget_gib": brick_gb, "proposal_levels": brick_levels[0], "field_levels": brick_levels[1]},
+                       "chunk": chunk, "e2e_chunk": e2e_chunk,
+                       "pipeline": "chunks pipelined over 3 streams" if (args.pipeline == 2 or (args.pipeline == 1 and world > 1 and symm is not None and args.gather in ("mc", "peer"))) else "sequential"},
+            "roofline": {"bound": "hbm", "kernel": names_long[top],
+                         "achieved": kernels[top]["achieved"], "peak": peak, "unit": "GB/s", "frac": kernels[top]["frac"],
+                         "traffic": kernels[top]["traffic"], "peak_source": peak_src, "traffic_note": traffic_note,
+                         "algorithmic_bytes_per_launch": kernels[top]["algorithmic_bytes_per_launch"],
+                         "avg_launch_ms": kernels[top]["avg_launch_ms"], "launches_timed": kernels[top]["launches_timed"],
+                         "why_this_kernel": "largest share of the step (kernel_share_ms_per_step); every kernel's own figures are under `kernels`",
+                         "timing_note": "CUDA events around each launch on the launching stream, instrumented repeat of the K timed steps (same inputs, L2 flushed)",
+                         "kernels": {names_long[k].split(" ")[0]: v for k, v in kernels.items()},
                          "path": {"bytes_per_ray": path_bytes, "achieved": value * 1e6 * path_bytes / 1e9 / world,
                                   "frac": value * 1e6 * path_bytes / 1e9 / world / peak},
-                         "kernel_share_ms_per_step": {"march": m_ms / args.steps, "feature": f_ms / args.steps,
-                                                      "tapgemm": g_ms / args.steps}},
+                         "kernel_share_ms_per_step": {k: v["ms_per_step"] for k, v in kernels.items()}},
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "api": "Renderer.render per chunk, pinned host buffers, 3-stream pipeline"},
+                    "steps": e2e_steps,
+                    "api": "Renderer.render_frame on pinned host rays; the library's copy engines push each chunk's rows to pinned host "
+                           "memory while the next chunk renders (per rank: its own tile over its own PCIe link)"},
             "gpu_launches": launches,
             "clocks": clk,
         }
         if world == 1 and not args.no_cpu_baseline:
-            v, cores, sample = cpu_reference_rate(args.cpu_rays, 2, cfg, params)
-            line["cpu_baseline"] = {"value": v, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample}
+            v, _, cores = cpu_rate(args.config, 3, 1, args.regime)
+            line["cpu_baseline"] = {"value": v, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": CPU_SAMPLE_TEXT}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -439,28 +583,26 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["native", "reference"], default="native")
+    ap.add_argument("--config", choices=sorted(CONFIGS), default="sam",
+                    help="sam = BASELINE.json configs[2] (headline, default); rgb = configs[1]; clipseg_patch = configs[3]")
     ap.add_argument("--regime", choices=["scene", "init"], default="scene")
     ap.add_argument("--engine", choices=["tcgen05", "mma_sync"], default="tcgen05")
     ap.add_argument("--gather", choices=["auto", "mc", "peer", "dma", "nccl"], default="auto",
-                    help="N > 1: how the feature tiles are exchanged (fused multicast / peer stores, or NCCL)")
-    ap.add_argument("--chunk", type=int, default=0, help="rays per chunk (default: 32768, finer with N > 1)")
+                    help="N > 1: how the tiles are exchanged (copy engines = auto, fused multicast / peer stores, or NCCL)")
+    ap.add_argument("--chunk", type=int, default=0, help="rays per launch (default: 131072 on one GPU, finer with N > 1)")
     ap.add_argument("--pipeline", type=int, default=1, choices=[0, 1, 2],
                     help="chunk pipelining over 3 streams: 0 off, 1 auto (only with replicated outputs, N > 1), 2 always")
     ap.add_argument("--early-termination", type=float, default=0.0,
-                    help="opt-in transmittance threshold below which a ray's last 16 nerf samples are skipped "
+                    help="opt-in transmittance threshold below which the MLPs of a ray's last 16 nerf samples are skipped "
                          "(0 = exact, the default and the headline configuration)")
-    ap.add_argument("--feature-cutoff", type=float, default=-1.0,
-                    help="opt-in bucketed feature kernel: evaluate only the leading picked samples of a ray whose "
-                         "sharpened weight is >= this (0 = drop exact zeros, 5.96e-8 = below one fp32 ulp of the sum); "
-                         "< 0 = every sample (default and headline configuration)")
+    ap.add_argument("--feature-cutoff", type=float, default=2.0 ** -24,
+                    help="bucketed feature kernel: evaluate only the leading picked samples of a ray whose sharpened weight is "
+                         ">= this (library default 2^-24 = below one fp32 ulp of the sum; 0 = drop exact zeros); "
+                         "< 0 = every sample of every ray through the un-bucketed kernel")
     ap.add_argument("--brick-gb", type=float, default=-1.0,
                     help="HBM budget (GiB) for the cell-major brick copies of the leading grid levels (library default 4; "
                          "0 = off; a pure re-layout, results are bit-identical)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-rays", type=int, default=32768,
-                    help="rays of the bounded CPU-baseline sample (one reference chunk, timed twice: ~4 s of host work at "
-                         "the ~0.017 Mrays/s measured on the GPU box, ~45 s on a slow 8-core host)")
-    ap.add_argument("--ref-rays", type=int, default=4096)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

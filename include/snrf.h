@@ -70,12 +70,14 @@ int snrf_set_early_termination(snrf_ctx* ctx, float eps);
  * 13 = 24.5 GB, 14 = 64.5 GB); rebuilt by every snrf_upload_proposal / snrf_upload_field_base.  Default 4 GiB
  * (environment SNRF_BRICK_GB overrides), 0 = off.  Optionally returns the number of bricked levels.  Synchronises. */
 int snrf_set_brick_budget(snrf_ctx* ctx, int64_t bytes, int* prop_levels, int* field_levels);
-/* Feature samples below the precision of their own sum (opt-in; default < 0 = off, every one of the 16 picked
- * samples of every ray is evaluated).  cutoff >= 0: rays are bucketed by the number of leading slots whose sharpened,
- * renormalised weight (sam_model.py:244-248) is >= cutoff (> 0 when cutoff == 0) and only 1 / 2 / 4 / 8 / 16 slots of a ray
- * are gathered and pushed through the MLP accordingly; the weights dropped per ray sum to < 16 * cutoff.  cutoff = 0 is
- * exact up to fp32 summation order; 2^-24 drops less than one fp32 ulp of the accumulated feature.  tcgen05 engine
- * only.  See csrc/sam_bucket.cu. */
+/* Feature samples below the precision of their own sum.  cutoff >= 0: rays are bucketed by the number of leading slots
+ * whose sharpened, renormalised weight (sam_model.py:244-248) is >= cutoff (> 0 when cutoff == 0) and only 1 / 2 / 4 / 8 /
+ * 16 slots of a ray are gathered and pushed through the MLP accordingly; the weights dropped per ray sum to
+ * < 16 * cutoff.  DEFAULT 2^-24: what is dropped is less than one fp32 ulp of the accumulated feature (which is then
+ * rounded to fp16), 3.0 instead of 16 slots per ray on the 800x800 benchmark frame; the whole parity suite runs through
+ * it.  cutoff = 0 drops exact zeros only; cutoff < 0 evaluates every one of the 16 picked samples of every ray with the
+ * un-bucketed kernel (csrc/sam.cu).  tcgen05 engine only (the mma.sync engine always evaluates every slot).
+ * snrf_feature_backward applies the same rule to its rows.  See csrc/sam_bucket.cu. */
 int snrf_set_feature_cutoff(snrf_ctx* ctx, float cutoff);
 /* Rays the bucketed feature kernel has put into its 1 / 2 / 4 / 8 / 16-slot buckets since the last reset
  * (rays_per_bucket[5], host): sum_b rays[b] << b is the number of (ray, sample) slots actually gathered, 3 072 B each -

@@ -214,6 +214,9 @@ def fixture_specs():
         "chunk_tiny_patch4": dict(cfg="tiny", clipseg=False, patch=4, regime="scene", seed=5, rays="plumbing", n=256),
         "chunk_full_scene": dict(cfg="full", clipseg=False, patch=1, regime="scene", seed=0, rays="orbit", n=192),
         "image_tiny": dict(cfg="tiny", clipseg=True, patch=4, regime="scene", seed=6, rays="image", n=24 * 32),
+        # the shipped full-size configuration on 4 096 rays of the benchmark frame (SURVEY.md 8 d), without / with ClipSeg
+        "chunk_full_4k": dict(cfg="full", clipseg=False, patch=1, regime="scene", seed=0, rays="orbit", n=4096),
+        "chunk_full_clipseg_4k": dict(cfg="full", clipseg=True, patch=1, regime="scene", seed=2, rays="orbit", n=4096),
     }
 
 
@@ -252,7 +255,10 @@ def main():
     torch.set_num_threads(os.cpu_count() or 1)
     os.makedirs(GOLDEN, exist_ok=True)
     ref = load_reference()
+    only = set(sys.argv[1:])  # python -m oracle.make_golden [fixture names]: regenerate just those
     for name, spec in fixture_specs().items():
+        if only and name not in only:
+            continue
         cfg = make_cfg(spec)
         params = make_synthetic_params(cfg, spec["regime"], spec["seed"])
         model = build_reference_model(ref, cfg, params)

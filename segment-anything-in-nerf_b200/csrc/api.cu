@@ -71,7 +71,9 @@ struct snrf_ctx {
   BrickDev prop_bricks = {}, field_bricks = {};
   bool march_v1 = false;  // SNRF_MARCH=v1: the round-1 march kernel (A/B measurements only)
   float et_eps = 0.f;  // snrf_set_early_termination
-  float feat_cutoff = -1.f;  // snrf_set_feature_cutoff: < 0 = kernel B on every slot (default), >= 0 = bucketed kernel B'
+  // snrf_set_feature_cutoff: >= 0 = bucketed kernel B' (default 2^-24: slots below one fp32 ulp of the ray's weight sum
+  // are not evaluated), < 0 = kernel B on every slot
+  float feat_cutoff = 5.9604645e-8f;
   const float* jitter = nullptr;  // snrf_set_jitter: training-mode draws for the next render / sample call
   int64_t jitter_rays = 0;
   float anneal = 1.f;  // snrf_set_anneal
@@ -960,7 +962,9 @@ int snrf_render_frame(snrf_ctx* ctx, const float* origins, const float* dirs, co
     ctx->aux_ready = true;
   }
   const bool feats = (flags & (SNRF_WANT_SAM | SNRF_WANT_CLIPSEG)) != 0;
-  const bool dma = ctx->rep_mode == 1 && ctx->rep[0].local && ctx->rep[0].n > 0;
+  bool dma = false;  // copy-engine exchange: any output registered with at least one destination
+  for (int w = 0; w < 5; ++w) dma = dma || (ctx->rep_mode == 1 && ctx->rep[w].local && ctx->rep[w].n > 0);
+  const bool dma_sam = dma && ctx->rep[0].local && ctx->rep[0].n > 0;
   // auto: pipeline only when a kernel's own replicated stores are NVLink-bound; with copy engines the kernels run
   // back to back on one stream (cross-stream hops cost ~20 us per chunk and buy nothing when the exchange is off the SMs)
   const bool pipelined = feats && n_rays > chunk && (ctx->pipeline == 2 || (ctx->pipeline == 1 && ctx->rep[0].local && !dma));
@@ -998,7 +1002,7 @@ int snrf_render_frame(snrf_ctx* ctx, const float* origins, const float* dirs, co
       CK(cudaEventRecord(ctx->ev_out_done[slot], ctx->aux_out));
     }
     // copy-engine exchange: as soon as this chunk's feature rows exist, DMA them into every peer's frame buffer
-    if (dma && sam && (flags & SNRF_WANT_SAM) && !(flags & SNRF_PATCH)) {
+    if (dma_sam && sam && (flags & SNRF_WANT_SAM) && !(flags & SNRF_PATCH)) {
       const Replication& R = ctx->rep[0];
       float* src = sam + i * 256;
       const char* lo = reinterpret_cast<const char*>(R.local);
@@ -1010,7 +1014,7 @@ int snrf_render_frame(snrf_ctx* ctx, const float* origins, const float* dirs, co
         for (int q = 0; q < R.n; ++q) {
           cudaStream_t cp = ctx->copy_stream[q & 3];
           CK(cudaStreamWaitEvent(cp, ctx->ev_out[c & 1], 0));
-          CK(cudaMemcpyAsync(R.peer[q] + off, src, n * 256 * sizeof(float), cudaMemcpyDeviceToDevice, cp));
+          CK(cudaMemcpyAsync(R.peer[q] + off, src, n * 256 * sizeof(float), cudaMemcpyDefault, cp));
         }
       }
     }
@@ -1030,7 +1034,7 @@ int snrf_render_frame(snrf_ctx* ctx, const float* origins, const float* dirs, co
       for (int q = 0; q < R.n; ++q) {
         cudaStream_t cp = ctx->copy_stream[q & 3];
         CK(cudaStreamWaitEvent(cp, ctx->ev_join, 0));
-        CK(cudaMemcpyAsync(R.peer[q] + off, outs[w], n_rays * widths[w] * sizeof(float), cudaMemcpyDeviceToDevice, cp));
+        CK(cudaMemcpyAsync(R.peer[q] + off, outs[w], n_rays * widths[w] * sizeof(float), cudaMemcpyDefault, cp));
       }
     }
     for (int q = 0; q < 4; ++q) {  // the caller's stream resumes after every copy has been queued and finished

@@ -173,9 +173,10 @@ class Renderer:
         self._check(self.lib.snrf_set_anneal(self.h, float(anneal)))
 
     def set_feature_cutoff(self, cutoff: float) -> None:
-        """Opt-in bucketed feature kernel: only the leading slots of a ray whose sharpened weight is >= ``cutoff`` (in
-        buckets of 1 / 2 / 4 / 8 / 16) are evaluated.  ``< 0`` = off (default), ``0`` = drop exact zeros only,
-        ``2**-24`` = drop what is below one fp32 ulp of the accumulated feature.  See ``snrf_set_feature_cutoff``."""
+        """Bucketed feature kernel: only the leading slots of a ray whose sharpened weight is >= ``cutoff`` (in buckets
+        of 1 / 2 / 4 / 8 / 16) are evaluated.  Library default ``2**-24`` = drop what is below one fp32 ulp of the
+        accumulated feature; ``0`` = drop exact zeros only; ``< 0`` = every slot of every ray through the un-bucketed
+        kernel.  See ``snrf_set_feature_cutoff``."""
         self._check(self.lib.snrf_set_feature_cutoff(self.h, float(cutoff)))
 
     def feature_slot_stats(self, reset: bool = True):

@@ -25,3 +25,22 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+def pytest_sessionfinish(session, exitstatus):
+    """Write the fractions the parity comparisons observed (tests/helpers.py OBSERVED) next to the required ones."""
+    try:
+        import json
+
+        sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+        from helpers import OBSERVED
+    except Exception:  # pragma: no cover
+        return
+    if not OBSERVED:
+        return
+    out_dir = os.path.join(ROOT, "gpurun_out")
+    if not os.path.isdir(out_dir):
+        return
+    rows = {k: {**v, "margin": v["observed_min"] - v["required"]} for k, v in sorted(OBSERVED.items())}
+    with open(os.path.join(out_dir, "parity_observed.json"), "w") as f:
+        json.dump(rows, f, indent=1)

@@ -29,6 +29,23 @@ FRAC_SMOOTH = 0.999   # quantities that are continuous in the inputs
 FRAC_DISCRETE = 0.97  # quantities behind a discrete pick (median index, top-k set)
 
 
+# every comparison records the fraction it observed next to the one it required; tests/conftest.py writes the table out
+# at the end of a session (gpurun_out/parity_observed.json on the GPU box), so that the budgets can be judged and
+# tightened against what the hardware really delivers
+OBSERVED: Dict[str, Dict[str, float]] = {}
+
+
+def _record(what: str, got: float, need: float, max_err: float) -> None:
+    import os
+
+    test = os.environ.get("PYTEST_CURRENT_TEST", "").split(" ")[0].split("::")[-1]
+    e = OBSERVED.setdefault(f"{test} | {what}", {"observed_min": 1.0, "required": need, "max_err": 0.0, "n": 0})
+    e["observed_min"] = min(e["observed_min"], got)
+    e["max_err"] = max(e["max_err"], max_err)
+    e["required"] = need
+    e["n"] += 1
+
+
 def frac_close(a, b, rtol, atol) -> float:
     a = torch.as_tensor(a).detach().float().cpu()
     b = torch.as_tensor(b).detach().float().cpu()
@@ -48,6 +65,7 @@ def assert_mostly_close(a, b, tol: Dict[str, float], frac: float, what: str, per
         ok = ok.reshape(ok.shape[0], -1).all(dim=1)
     got = float(ok.float().mean())
     err = torch.nan_to_num((a - b).abs(), nan=0.0)
+    _record(what, got, frac, float(err.max()) if err.numel() else 0.0)
     assert got >= frac, (
         f"{what}: only {got:.5f} within rtol={tol['rtol']} atol={tol['atol']} (need {frac}); "
         f"max|err|={float(err.max()):.3e} median|err|={float(err.median()):.3e}"
@@ -71,6 +89,7 @@ def assert_features_close(a, b, what: str, row_frac: float = FRAC_DISCRETE, elem
     rel = torch.linalg.norm(torch.nan_to_num(a2 - b2), dim=-1) / torch.linalg.norm(torch.nan_to_num(b2), dim=-1).clamp_min(1e-6)
     ok = (rel <= rel_l2) | nan_rows
     got = float(ok.float().mean())
+    _record(what + f" (rays within relative L2 {rel_l2})", got, row_frac, float(rel.max()) if rel.numel() else 0.0)
     assert got >= row_frac, f"{what}: only {got:.5f} of rays within relative L2 {rel_l2} (need {row_frac}); median {float(rel.median()):.2e}"
     return got
 
@@ -85,7 +104,7 @@ def error_stats(a, b) -> str:
             f"ref_absmean={float(ref.mean()):.3e}")
 
 
-@functools.lru_cache(maxsize=4)
+@functools.lru_cache(maxsize=6)
 def model_pair(kind: str, regime: str, seed: int, clipseg: bool, patch: int):
     """(cfg, params, Oracle) for a config; the CUDA renderer is created by the caller (needs a GPU)."""
     from oracle.samnerf_oracle import Oracle

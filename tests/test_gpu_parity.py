@@ -28,6 +28,13 @@ def full():
     return cfg, params, orc, make_renderer(cfg, params)
 
 
+@pytest.fixture(scope="module")
+def full_clipseg():
+    """The shipped full-size configuration with the ClipSeg grids and head (BASELINE.json configs[3])."""
+    cfg, params, orc = model_pair("full", "scene", 2, True, 1)
+    return cfg, params, orc, make_renderer(cfg, params)
+
+
 def _positions(n, seed):
     g = torch.Generator().manual_seed(seed)
     inner = (torch.rand(n // 2, 3, generator=g) * 2 - 1) * 0.9
@@ -53,7 +60,7 @@ def test_density_fields(which, request):
     assert_mostly_close(rgb_gpu, rgb_ref, dict(rtol=0.0, atol=2e-3), FRAC_SMOOTH, "per-sample rgb")
 
 
-@pytest.mark.parametrize("which", ["tiny", "full"])
+@pytest.mark.parametrize("which", ["tiny", "full", "full_clipseg"])
 def test_feature_field(which, request):
     cfg, params, orc, r = request.getfixturevalue(which)
     x = _positions(2048, 3)
@@ -67,9 +74,12 @@ def test_feature_field(which, request):
 
 
 # ---- stage level: sampler, weights, compositing, top-k ------------------------------------------------------------
-@pytest.mark.parametrize("which,regime", [("tiny", "scene"), ("full", "scene"), ("tiny", "init")])
+@pytest.mark.parametrize("which,regime", [("tiny", "scene"), ("full", "scene"), ("tiny", "init"), ("full_clipseg", "scene")])
 def test_render_stages(which, regime):
-    cfg, params, orc = model_pair(which, regime, 11 if which == "tiny" else 0, which == "tiny", 1)
+    if which == "full_clipseg":
+        cfg, params, orc = model_pair("full", regime, 2, True, 1)
+    else:
+        cfg, params, orc = model_pair(which, regime, 11 if which == "tiny" else 0, which == "tiny", 1)
     r = make_renderer(cfg, params)
     o, d = test_rays(1024, seed=5)
     feats = ("sam", "clipseg") if cfg.use_clipseg_feature else ("sam",)
@@ -107,7 +117,8 @@ def test_engines_agree_with_oracle(engine):
 
 
 # ---- golden fixtures produced by the reference's own Python (oracle/make_golden.py) ----------------------------
-@pytest.mark.parametrize("name", ["chunk_tiny_scene", "chunk_tiny_init", "chunk_tiny_patch4", "chunk_full_scene"])
+@pytest.mark.parametrize("name", ["chunk_tiny_scene", "chunk_tiny_init", "chunk_tiny_patch4", "chunk_full_scene", "chunk_full_4k",
+                                  "chunk_full_clipseg_4k"])
 def test_golden_chunks(name):
     from oracle.make_golden import fixture_specs, make_cfg, params_checksum
     from samnerf_b200 import make_synthetic_params

@@ -194,14 +194,17 @@ def test_bucketed_feature_kernel_matches_kernel_b(full, cutoff, rel):
     cfg, r = full
     o, d = test_rays(9000, seed=14)
     o, d = o.cuda(), d.cuda()
-    exact = r.render(o, d, get_feature=("sam",))
-    r.set_feature_cutoff(cutoff)
     try:
+        r.set_feature_cutoff(-1.0)  # every slot of every ray (csrc/sam.cu)
+        exact = r.render(o, d, get_feature=("sam",))
+        r.set_feature_cutoff(cutoff)
         got = r.render(o, d, get_feature=("sam",))
         part = r.render(o[:1003], d[:1003], get_feature=("sam",))  # ragged: partial tiles in every bucket
         torch.cuda.synchronize()
-    finally:
         r.set_feature_cutoff(-1.0)
+        again = r.render(o, d, get_feature=("sam",))
+    finally:
+        r.set_feature_cutoff(2.0 ** -24)  # the library default
     for k in ("rgb", "depth", "accumulation"):
         assert torch.equal(got[k], exact[k]), k
     a, b = got["sam"], exact["sam"]
@@ -214,5 +217,4 @@ def test_bucketed_feature_kernel_matches_kernel_b(full, cutoff, rel):
     assert float((err <= rel).float().mean()) > 0.99, float((err <= rel).float().mean())
     assert float((err == 0).float().mean()) > 0.5  # most rays agree bit for bit
     assert torch.equal(part["sam"], got["sam"][:1003])
-    again = r.render(o, d, get_feature=("sam",))
     assert torch.equal(again["sam"], exact["sam"])

@@ -29,7 +29,8 @@ def _oracle_for(name):
     return Oracle(cfg, params), cfg, g
 
 
-@pytest.mark.parametrize("name", ["chunk_tiny_scene", "chunk_tiny_init", "chunk_tiny_patch4", "chunk_full_scene"])
+@pytest.mark.parametrize("name", ["chunk_tiny_scene", "chunk_tiny_init", "chunk_tiny_patch4", "chunk_full_scene", "chunk_full_4k",
+                                  "chunk_full_clipseg_4k"])
 def test_chunk_matches_reference(name):
     """Restated samplers / fields / renderers / top-k / MeanRenderer / conv head == the reference's code.
     Both sides are fp32 CPU torch with the same tcnn stand-in, so the tolerance is rounding-order only."""
