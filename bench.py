@@ -334,9 +334,10 @@ def run_native(args):
     o_dev, d_dev = o_host.to(dev), d_host.to(dev)
     # Rays per launch.  The reference's eval_num_rays_per_chunk (32768, samconfigs.py:79) caps the [N,S,C] intermediates
     # its PyTorch path materialises; this path has none (128 B + 512 B of scratch per ray), so a launch covers 131072 rays
-    # on one GPU (fewer launch tails; measured +8 %), and the tile is cut finer with N ranks so that the exchange of
-    # chunk c overlaps the compute of chunk c+1 (the chunk size is caller-tunable in the reference too, eval_utils.py:90-91)
-    chunk = args.chunk or (131072 if world == 1 else 32768 if world == 2 else 16384)
+    # on one GPU (fewer launch tails; measured +8 %), and the tile is cut as finely with N ranks (131072 / N) so that the
+    # exchange of chunk c overlaps the compute of chunk c+1 (the chunk size is caller-tunable in the reference too,
+    # eval_utils.py:90-91)
+    chunk = args.chunk or max(16384, 131072 // world)  # five launches per tile at every N
 
     names = {"rgb": 3, "depth": 1, "accumulation": 1, "prop_depth_0": 1}
     if "sam" in feats:

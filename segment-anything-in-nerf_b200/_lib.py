@@ -13,7 +13,7 @@ import sys
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SNRF_LIB_PATH") or os.path.join(_HERE, "libsnrf.so")
 CSRC = os.path.join(_HERE, "csrc")
-SOURCES = ["api.cu", "march.cu", "march_v1.cu", "sam.cu", "gemm.cu", "query.cu", "raygen.cu", "backward.cu", "sam_bucket.cu", "bricks.cu"]
+SOURCES = ["api.cu", "march.cu", "march_v1.cu", "sam.cu", "gemm.cu", "query.cu", "raygen.cu", "backward.cu", "sam_bucket.cu", "bricks.cu", "gemm_tma.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared", "--threads", "0",  # one compile job per source file

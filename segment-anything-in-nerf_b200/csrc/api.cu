@@ -102,8 +102,9 @@ struct snrf_ctx {
   // fused tile all-gather (snrf_set_replication): 0 sam, 1 rgb, 2 depth, 3 accumulation, 4 prop_depth
   Replication rep[5];
   int rep_mode = 0;  // 0: the kernels' own stores (multimem.st / peer pointers); 1: copy engines (cudaMemcpyAsync per peer)
-  cudaStream_t copy_stream[4] = {nullptr, nullptr, nullptr, nullptr};
-  cudaEvent_t ev_copy[4] = {nullptr, nullptr, nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+  // one copy stream per destination (kMaxPeers): the copy engines serve the peers of a chunk concurrently
+  cudaStream_t copy_stream[kMaxPeers] = {nullptr};
+  cudaEvent_t ev_copy[kMaxPeers] = {nullptr}, ev_out[2] = {nullptr, nullptr};
   // frame-level pipelining (snrf_render_frame)
   int pipeline = 1;  // 0 off, 1 auto (only when outputs are replicated to other ranks), 2 always
   bool aux_ready = false;
@@ -355,7 +356,7 @@ void snrf_ctx_destroy(snrf_ctx* ctx) {
   ctx->hbar[0][1].release(); ctx->hbar[1][0].release(); ctx->hbar[1][1].release();
   if (ctx->aux_feat) cudaStreamDestroy(ctx->aux_feat);
   if (ctx->aux_out) cudaStreamDestroy(ctx->aux_out);
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < kMaxPeers; ++i) {
     if (ctx->copy_stream[i]) cudaStreamDestroy(ctx->copy_stream[i]);
     if (ctx->ev_copy[i]) cudaEventDestroy(ctx->ev_copy[i]);
   }
@@ -758,6 +759,7 @@ struct ChunkStreams {
   int slot;        // which copy of the per-chunk scratch (sam_t / sam_w / hbar) to use
   int out_grid;    // CTA cap of the output-layer kernel (0 = one per SM)
   bool small_cta;  // 8-warp / 145 KB feature kernel that shares an SM with march CTAs
+  cudaEvent_t after_march;  // recorded right behind the march launch when not null (the per-ray outputs are complete there)
 };
 
 // offset-preserving aliases of an output pointer in the other ranks' frame buffers (snrf_set_replication)
@@ -821,6 +823,7 @@ static int render_chunk(snrf_ctx* ctx, const float* origins, const float* dirs, 
     M.dbg_rgb = dbg->rgb_samples;
   }
   TIMED_LAUNCH(0, cs.march, ctx->march_v1 ? launch_march_v1(M, ctx->sm_count, cs.march) : launch_march(M, ctx->sm_count, cs.march));
+  if (cs.after_march) CK(cudaEventRecord(cs.after_march, cs.march));
   if (dbg && dbg->sam_t) {
     CK(cudaMemcpyAsync(dbg->sam_t, M.sam_t, n_rays * 16 * 4, cudaMemcpyDeviceToDevice, cs.march));
     if (dbg->sam_w) CK(cudaMemcpyAsync(dbg->sam_w, M.sam_w, n_rays * 16 * 4, cudaMemcpyDeviceToDevice, cs.march));
@@ -936,7 +939,7 @@ int snrf_render(snrf_ctx* ctx, const float* origins, const float* dirs, const fl
   if (n_rays < 0) return fail(ctx, SNRF_E_INVALID, "negative ray count");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   CK(cudaSetDevice(ctx->device));
-  const ChunkStreams cs = {s, s, s, 0, 0, false};
+  const ChunkStreams cs = {s, s, s, 0, 0, false, nullptr};
   return render_chunk(ctx, origins, dirs, nears, fars, n_rays, flags, opts, rgb, depth, acc, prop_depth, sam, clipseg, dbg, cs);
 }
 
@@ -953,7 +956,7 @@ int snrf_render_frame(snrf_ctx* ctx, const float* origins, const float* dirs, co
     CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
     CK(cudaStreamCreateWithPriority(&ctx->aux_feat, cudaStreamNonBlocking, hi));
     CK(cudaStreamCreateWithPriority(&ctx->aux_out, cudaStreamNonBlocking, hi));
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < kMaxPeers; ++i) {
       CK(cudaStreamCreateWithFlags(&ctx->copy_stream[i], cudaStreamNonBlocking));
       CK(cudaEventCreateWithFlags(&ctx->ev_copy[i], cudaEventDisableTiming));
     }
@@ -986,8 +989,11 @@ int snrf_render_frame(snrf_ctx* ctx, const float* origins, const float* dirs, co
   for (int64_t i = 0; i < n_rays; i += chunk, ++c) {
     const int64_t n = n_rays - i < chunk ? n_rays - i : chunk;
     const int slot = pipelined ? static_cast<int>(c & 1) : 0;
+    // copy-engine exchange: rgb / depth / accumulation / proposal depth of the whole tile are complete behind the LAST
+    // chunk's march kernel, so their copies start there and overlap that chunk's feature kernels
+    const bool last_chunk = i + chunk >= n_rays;
     ChunkStreams cs = {s, pipelined ? ctx->aux_feat : s, pipelined ? ctx->aux_out : s, slot, out_grid,
-                       pipelined && getenv("SNRF_CORESIDENT") != nullptr};
+                       pipelined && getenv("SNRF_CORESIDENT") != nullptr, (dma && last_chunk) ? ctx->ev_join : nullptr};
     if (pipelined && c >= 2) {
       CK(cudaStreamWaitEvent(s, ctx->ev_feat_done[slot], 0));             // sam_t / sam_w of this slot are free again
       CK(cudaStreamWaitEvent(ctx->aux_feat, ctx->ev_out_done[slot], 0));  // hbar of this slot is free again
@@ -1012,7 +1018,7 @@ int snrf_render_frame(snrf_ctx* ctx, const float* origins, const float* dirs, co
         cudaStream_t so = pipelined ? ctx->aux_out : s;
         CK(cudaEventRecord(ctx->ev_out[c & 1], so));
         for (int q = 0; q < R.n; ++q) {
-          cudaStream_t cp = ctx->copy_stream[q & 3];
+          cudaStream_t cp = ctx->copy_stream[q % kMaxPeers];
           CK(cudaStreamWaitEvent(cp, ctx->ev_out[c & 1], 0));
           CK(cudaMemcpyAsync(R.peer[q] + off, src, n * 256 * sizeof(float), cudaMemcpyDefault, cp));
         }
@@ -1020,10 +1026,10 @@ int snrf_render_frame(snrf_ctx* ctx, const float* origins, const float* dirs, co
     }
   }
   if (dma) {
-    // the small per-ray outputs (24 B/ray) go once per frame, after the last march
+    // the small per-ray outputs (24 B/ray) go once per frame, behind the last march kernel
     float* outs[4] = {rgb, depth, acc, prop_depth};
     const int64_t widths[4] = {3, 1, 1, 1};
-    CK(cudaEventRecord(ctx->ev_join, s));
+    if (n_rays == 0) CK(cudaEventRecord(ctx->ev_join, s));  // otherwise recorded behind the last march (see above)
     for (int w = 0; w < 4; ++w) {
       const Replication& R = ctx->rep[w + 1];
       if (!outs[w] || !R.local) continue;
@@ -1032,12 +1038,12 @@ int snrf_render_frame(snrf_ctx* ctx, const float* origins, const float* dirs, co
       if (p < lo || p + n_rays * widths[w] * sizeof(float) > lo + R.bytes) continue;
       const int64_t off = (p - lo) / static_cast<int64_t>(sizeof(float));
       for (int q = 0; q < R.n; ++q) {
-        cudaStream_t cp = ctx->copy_stream[q & 3];
+        cudaStream_t cp = ctx->copy_stream[q % kMaxPeers];
         CK(cudaStreamWaitEvent(cp, ctx->ev_join, 0));
         CK(cudaMemcpyAsync(R.peer[q] + off, outs[w], n_rays * widths[w] * sizeof(float), cudaMemcpyDefault, cp));
       }
     }
-    for (int q = 0; q < 4; ++q) {  // the caller's stream resumes after every copy has been queued and finished
+    for (int q = 0; q < kMaxPeers; ++q) {  // the caller's stream resumes after every copy has been queued and finished
       CK(cudaEventRecord(ctx->ev_copy[q], ctx->copy_stream[q]));
       CK(cudaStreamWaitEvent(s, ctx->ev_copy[q], 0));
     }

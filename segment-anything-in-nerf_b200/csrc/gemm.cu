@@ -9,6 +9,8 @@
 //
 // Persistent CTAs of 16 warps, one 128-row tile at a time, operands in shared memory in the core-matrix layout
 // (common.cuh); accumulator in TMEM (tcgen05 engine, M=128 x N x K=16 x 16 per tap) or registers (legacy engine).
+#include <stdlib.h>
+
 #include "kernels.cuh"
 
 namespace snrf {
@@ -296,6 +298,12 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const GemmParams P
 }  // namespace
 
 cudaError_t launch_tapgemm(const GemmParams& P, bool tcgen05, int sm_count, cudaStream_t stream) {
+  // the plain output layer runs on the TMA-fed kernel (gemm_tma.cu); SNRF_TAPGEMM=v1 keeps it on this file's kernel (A/B runs)
+  static const bool force_v1 = [] { const char* e = getenv("SNRF_TAPGEMM"); return e && e[0] == 'v' && e[1] == '1'; }();
+  if (tcgen05 && !force_v1) {
+    const cudaError_t e = launch_tapgemm_tma(P, sm_count, stream);
+    if (e != cudaErrorNotSupported) return e;
+  }
   // function attributes are per device: remember which devices of this process have been configured
   static bool configured_dev[64] = {false};
   int dev_id = 0;

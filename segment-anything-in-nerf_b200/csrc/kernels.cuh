@@ -161,6 +161,9 @@ struct GemmParams {
   int n_peers;
 };
 cudaError_t launch_tapgemm(const GemmParams& P, bool tcgen05, int sm_count, cudaStream_t stream);
+// TMA-fed, warp-specialised version for the plain output layer (taps = 1, fp32 rows, no fused replication): gemm_tma.cu.
+// cudaErrorNotSupported = this launch is not its case; launch_tapgemm falls through to the kernel above.
+cudaError_t launch_tapgemm_tma(const GemmParams& P, int sm_count, cudaStream_t stream);
 
 // ---- stand-alone field queries (back Field.density_fn / SAMField.get_outputs) --------------------
 struct QueryParams {

@@ -26,7 +26,7 @@ TOL = {
     "encoding": dict(rtol=0.0, atol=1e-3),
 }
 FRAC_SMOOTH = 0.999   # quantities that are continuous in the inputs
-FRAC_DISCRETE = 0.97  # quantities behind a discrete pick (median index, top-k set)
+FRAC_DISCRETE = 0.99  # quantities behind a discrete pick (median index, top-k set); observed on B200: >= 0.992 (profiles/r02_parity_observed.json)
 
 
 # every comparison records the fraction it observed next to the one it required; tests/conftest.py writes the table out

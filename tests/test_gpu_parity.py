@@ -134,15 +134,17 @@ def test_golden_chunks(name):
                    patch=cfg.patch_size > 1)
     assert_mostly_close(out["rgb"], z["rgb"], TOL["rgb"], 0.99, "rgb", per_row=True)
     assert_mostly_close(out["accumulation"], z["accumulation"], TOL["accumulation"], 0.99, "accumulation")
-    assert_mostly_close(out["depth"], z["depth"], TOL["depth"], 0.95, "depth")
-    assert_mostly_close(out["prop_depth_0"], z["prop_depth_0"], TOL["depth"], 0.95, "prop depth")
+    # budgets for the discrete picks were 0.95 in round 1; the observed fractions on B200 are >= 0.992 everywhere
+    # (profiles/r02_parity_observed.json), so they are held to FRAC_DISCRETE = 0.99 now
+    assert_mostly_close(out["depth"], z["depth"], TOL["depth"], FRAC_DISCRETE, "depth")
+    assert_mostly_close(out["prop_depth_0"], z["prop_depth_0"], TOL["depth"], FRAC_DISCRETE, "prop depth")
     if cfg.patch_size == 1:
-        assert_features_close(out["sam"], z["sam"], "sam", row_frac=0.95)
-    else:  # 16 patch-aggregated rows: one flipped ray moves a whole row, so allow 2 of 16
-        assert_features_close(out["sam"], z["sam"], "sam", row_frac=0.85, elem_frac=0.9, rel_l2=3e-2,
+        assert_features_close(out["sam"], z["sam"], "sam", row_frac=FRAC_DISCRETE)
+    else:  # 16 patch-aggregated rows: one flipped ray moves a whole row, so allow 1 of 16 (observed: 0)
+        assert_features_close(out["sam"], z["sam"], "sam", row_frac=0.93, elem_frac=0.93, rel_l2=3e-2,
                               tol=dict(rtol=3e-2, atol=3e-3))
     if "clipseg" in z.files:
-        assert_features_close(out["clipseg"], z["clipseg"], "clipseg", row_frac=0.95)
+        assert_features_close(out["clipseg"], z["clipseg"], "clipseg", row_frac=FRAC_DISCRETE)
 
 
 def test_golden_image_through_model_shim():
@@ -163,11 +165,11 @@ def test_golden_image_through_model_shim():
     out = m.get_outputs_for_camera_ray_bundle(bundle)
     assert out["rgb"].shape == (24, 32, 3) and out["sam"].shape == (48, 64, 256) and out["clipseg"].shape == (32, 32, 192)
     assert_mostly_close(out["rgb"], z["rgb"], TOL["rgb"], 0.99, "rgb", per_row=False)
-    assert_mostly_close(out["depth"], z["depth"], TOL["depth"], 0.95, "depth")
+    assert_mostly_close(out["depth"], z["depth"], TOL["depth"], FRAC_DISCRETE, "depth")
     st = int(z["_sam_stride"])
-    assert_features_close(out["sam"][::st, ::st], z["sam"], "patch-aggregated sam", row_frac=0.95, elem_frac=0.97,
+    assert_features_close(out["sam"][::st, ::st], z["sam"], "patch-aggregated sam", row_frac=0.97, elem_frac=0.97,
                           rel_l2=3e-2, tol=dict(rtol=3e-2, atol=3e-3))
-    assert_features_close(out["clipseg"], z["clipseg"], "clipseg", row_frac=0.95)
+    assert_features_close(out["clipseg"], z["clipseg"], "clipseg", row_frac=FRAC_DISCRETE)
 
 
 # ---- patch aggregation kernel on its own -----------------------------------------------------------------------
