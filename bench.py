@@ -324,6 +324,17 @@ def run_native(args):
     if args.early_termination > 0:
         r.set_early_termination(args.early_termination)  # opt-in, not the reference's exact arithmetic: see config
     r.set_feature_cutoff(args.feature_cutoff)
+    # Feature rows: fp32 on one GPU (the dtype of the reference's outputs["sam"]); with N > 1 the rows are exchanged AND
+    # stored as fp16 on every rank (--feature-dtype auto): tinycudann's own per-sample output precision (sam_field.py:51-61),
+    # one rounding of the fp32 result (2^-11 relative; the stated feature tolerance is 2e-2).  It halves the 585 MB each of
+    # 8 ranks has to receive per frame, which at 770 GB/s per direction would otherwise take 0.76 of the 0.83 ms a rank has.
+    if args.feature_dtype == "auto":
+        args.feature_dtype = "f16" if world > 1 else "f32"
+    fdt = torch.float16 if args.feature_dtype == "f16" else torch.float32
+    r.set_feature_dtype(fdt)
+    if args.march_first == -1:
+        args.march_first = 1 if world > 2 else 0
+    r.set_march_first(bool(args.march_first))
     o_all, d_all = frame_rays(conf)
     n_all = o_all.shape[0]
     assert H % world == 0
@@ -342,6 +353,12 @@ def run_native(args):
     names = {"rgb": 3, "depth": 1, "accumulation": 1, "prop_depth_0": 1}
     if "sam" in feats:
         names["sam"] = cfg.sam_out
+    dtypes = {k: (fdt if k == "sam" else torch.float32) for k in names}
+    esz = {k: (2 if dtypes[k] == torch.float16 else 4) for k in names}
+    offs, tot = {}, 0
+    for k, c in names.items():  # byte offsets of the outputs inside one frame-sized allocation (256-byte aligned)
+        offs[k] = tot
+        tot += (n_all * c * esz[k] + 255) // 256 * 256
     # With N > 1 the rendered tiles are exchanged into every rank's frame buffer over NVLink, overlapped with the next
     # chunk's compute; a symmetric-memory barrier ends the frame.  Fallback / comparison: NCCL all-gather (--gather nccl).
     gather_mode, symm, full = "single", None, {}
@@ -353,15 +370,14 @@ def run_native(args):
             try:
                 import torch.distributed._symmetric_memory as symm_mem
 
-                big = symm_mem.empty(n_all * sum(names.values()), dtype=torch.float32, device=dev)
+                big = symm_mem.empty(tot, dtype=torch.uint8, device=dev)
                 symm = symm_mem.rendezvous(big, dist.group.WORLD.group_name)
                 has_mc = bool(int(getattr(symm, "multicast_ptr", 0) or 0)) and args.gather == "mc"
-                off = 0
                 for k, c in names.items():
-                    full[k] = big[off:off + n_all * c].view(n_all, c)
-                    off += n_all * c
+                    full[k] = big[offs[k]:offs[k] + n_all * c * esz[k]].view(dtypes[k]).view(n_all, c)
                 gather_mode = ("fused multimem.st (NVSwitch multicast)" if has_mc else
                                "copy engines (cudaMemcpyAsync to peer buffers per chunk)" if args.gather == "dma" else
+                               "push kernel (peer stores from 32 CTAs on a side stream, csrc/exchange.cu)" if args.gather == "push" else
                                "fused peer stores (NVLink P2P)")
             except Exception as e:  # no symmetric memory on this box: say so and use NCCL
                 if rank == 0:
@@ -369,19 +385,17 @@ def run_native(args):
                 symm, gather_mode, full = None, "nccl", {}
     for k, c in names.items():
         if k not in full:
-            full[k] = torch.empty(n_all, c, device=dev)
+            full[k] = torch.empty(n_all, c, device=dev, dtype=dtypes[k])
     mine = {k: v[lo:lo + n_loc] for k, v in full.items()}
 
     def point_replication_at_peers():
         if symm is None:
             return
         mc = int(getattr(symm, "multicast_ptr", 0) or 0) if args.gather == "mc" else 0
-        r.set_replication_mode("dma" if args.gather == "dma" else "stores")
-        off = 0
+        r.set_replication_mode(args.gather if args.gather in ("dma", "push") else "stores")
         for k, c in names.items():
-            peers = [int(symm.buffer_ptrs[p]) + off * 4 for p in range(world) if p != rank]
-            r.set_replication(k, full[k], () if mc else peers, mc + off * 4 if mc else 0)
-            off += n_all * c
+            peers = [int(symm.buffer_ptrs[p]) + offs[k] for p in range(world) if p != rank]
+            r.set_replication(k, full[k], () if mc else peers, mc + offs[k] if mc else 0)
 
     point_replication_at_peers()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
@@ -475,11 +489,11 @@ def run_native(args):
     # "peer": each chunk's feature rows leave for host memory as soon as its output layer has finished, overlapped with
     # the next chunk's render; the caller's stream resumes when the last copy has landed.  Every rank feeds and drains
     # its own tile over its own PCIe link (no NVLink exchange here: the frame is assembled in host memory).
-    out_host = {k: torch.empty(n_loc, c).pin_memory() for k, c in names.items()}
+    out_host = {k: torch.empty(n_loc, c, dtype=dtypes[k]).pin_memory() for k, c in names.items()}
     o_stage, d_stage = torch.empty_like(o_dev), torch.empty_like(d_dev)
     r.set_replication_mode("dma")
     for k, c in names.items():
-        r.set_replication(k, full[k], [out_host[k].data_ptr() - lo * c * 4], 0)  # offset-preserving alias of this tile
+        r.set_replication(k, full[k], [out_host[k].data_ptr() - lo * c * esz[k]], 0)  # offset-preserving alias of this tile
     e2e_chunk = args.chunk or 32768
 
     def frame_e2e():
@@ -506,7 +520,7 @@ def run_native(args):
         dist.all_reduce(t2, op=dist.ReduceOp.MAX)
     e2e_value = n_all * e2e_steps / (float(t2.item()) * 1e-3) / 1e6
     h2d = 2 * n_all * 3 * 4
-    d2h = n_all * sum(names.values()) * 4
+    d2h = n_all * sum(c * esz[k] for k, c in names.items())
     if not e2e_ok:
         raise SystemExit("end-to-end path: the host copy differs from the device frame")
 
@@ -520,6 +534,8 @@ def run_native(args):
                 continue
             rays_per_launch = n_loc * args.steps / cnt
             bpr = BYTES_PER_RAY[k]
+            if k == "tapgemm" and args.feature_dtype == "f16":
+                bpr = 512 + 512  # fp16 hidden sums in, fp16 rows out
             extra = {}
             if k == "feature" and slot_stats is not None:
                 slots_per_ray = slot_stats[1] / max(n_loc, 1)
@@ -550,6 +566,11 @@ def run_native(args):
                        "early_termination": args.early_termination or None,
                        "feature_cutoff": args.feature_cutoff if args.feature_cutoff >= 0 else None,
                        "bricks": {"budget_gib": brick_gb, "proposal_levels": brick_levels[0], "field_levels": brick_levels[1]},
+                       "feature_dtype": {"rows": args.feature_dtype,
+                                         "note": None if args.feature_dtype == "f32" else
+                                         "feature rows are exchanged and stored as fp16 on every rank: one rounding of the fp32 result "
+                                         "(2^-11 relative, tinycudann's own output precision; stated feature tolerance 2e-2); N = 1 writes fp32"},
+                       "march_first": bool(args.march_first),
                        "chunk": chunk, "e2e_chunk": e2e_chunk,
                        "pipeline": "chunks pipelined over 3 streams" if (args.pipeline == 2 or (args.pipeline == 1 and world > 1 and symm is not None and args.gather in ("mc", "peer"))) else "sequential"},
             "roofline": {"bound": "hbm", "kernel": names_long[top],
@@ -588,8 +609,12 @@ def main():
                     help="sam = BASELINE.json configs[2] (headline, default); rgb = configs[1]; clipseg_patch = configs[3]")
     ap.add_argument("--regime", choices=["scene", "init"], default="scene")
     ap.add_argument("--engine", choices=["tcgen05", "mma_sync"], default="tcgen05")
-    ap.add_argument("--gather", choices=["auto", "mc", "peer", "dma", "nccl"], default="auto",
-                    help="N > 1: how the tiles are exchanged (copy engines = auto, fused multicast / peer stores, or NCCL)")
+    ap.add_argument("--gather", choices=["auto", "mc", "peer", "dma", "push", "nccl"], default="auto",
+                    help="N > 1: how the tiles are exchanged (auto = copy engines; push kernel; fused multicast / peer stores; NCCL)")
+    ap.add_argument("--feature-dtype", choices=["auto", "f32", "f16"], default="auto",
+                    help="element type of the 256-d feature rows: auto = f32 on one GPU, f16 with N > 1 (wire and storage)")
+    ap.add_argument("--march-first", type=int, default=-1, choices=[-1, 0, 1],
+                    help="frame = one march launch over the tile, then the feature chunks (-1 = auto: on for N > 2)")
     ap.add_argument("--chunk", type=int, default=0, help="rays per launch (default: 131072 on one GPU, finer with N > 1)")
     ap.add_argument("--pipeline", type=int, default=1, choices=[0, 1, 2],
                     help="chunk pipelining over 3 streams: 0 off, 1 auto (only with replicated outputs, N > 1), 2 always")

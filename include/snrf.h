@@ -187,6 +187,17 @@ int snrf_ray_op(snrf_ctx* ctx, int mode, const float* a, const float* b, const f
 int snrf_render_frame(snrf_ctx* ctx, const float* origins, const float* dirs, const float* nears, const float* fars,
                       int64_t n_rays, int64_t chunk, uint32_t flags, const snrf_render_opts* opts, float* rgb,
                       float* depth, float* acc, float* prop_depth, float* sam, float* clipseg, void* stream);
+/* Element type of the feature rows the render calls write (sam [N,256], clipseg [N,192]; not the patch-aggregated rows):
+ * 0 = fp32 (default, the dtype of the reference's outputs["sam"]), 1 = fp16 - the precision tinycudann itself emits per
+ * sample (sam_field.py:51-61): the fp32 result of the output layer is rounded once (2^-11 relative, against a stated
+ * feature tolerance of 2e-2).  Halves the bytes of the tile exchange between GPUs and of the device-to-host copy; the
+ * `sam` / `clipseg` pointers of snrf_render / snrf_render_frame / snrf_render_camera are then read as __half*.
+ * Copy-engine and push exchange only (not with the fused multicast / peer stores). */
+int snrf_set_feature_dtype(snrf_ctx* ctx, int f16);
+/* Frame calls: 1 = one march launch over the whole tile first (the picked samples of every ray go to a scratch of 128 B
+ * per ray), then the feature kernels chunk by chunk - fewer, larger march launches when a tile is cut into small chunks
+ * for the exchange; 0 (default) = march and features alternate per chunk. */
+int snrf_set_march_first(snrf_ctx* ctx, int enable);
 /* chunk pipelining of snrf_render_frame: 0 = off (strictly sequential on the caller's stream), 1 = auto (default:
  * only when outputs are replicated to other ranks - on one GPU the stages cannot share an SM, so it gains nothing),
  * 2 = always */
@@ -206,7 +217,7 @@ int snrf_set_replication(snrf_ctx* ctx, int which, void* local_base, int64_t byt
 /* How snrf_render_frame moves replicated outputs: 0 (default) = the kernels' own stores (multimem.st through
  * mc_base, else st.global through the peer pointers); 1 = copy engines: kernels write locally and each chunk's rows
  * are pushed to every peer pointer with cudaMemcpyAsync on side streams, so the exchange costs no SM time at all. */
-int snrf_set_replication_mode(snrf_ctx* ctx, int mode);
+int snrf_set_replication_mode(snrf_ctx* ctx, int mode); /* 0 fused stores, 1 copy engines, 2 push kernel (csrc/exchange.cu) */
 
 /* ---- camera ray generation fused in front of the render -------------------------------
  * Replaces Cameras.generate_rays(camera_indices=i, keep_shape=True) for one camera

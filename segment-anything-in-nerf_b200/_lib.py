@@ -13,7 +13,7 @@ import sys
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SNRF_LIB_PATH") or os.path.join(_HERE, "libsnrf.so")
 CSRC = os.path.join(_HERE, "csrc")
-SOURCES = ["api.cu", "march.cu", "march_v1.cu", "sam.cu", "gemm.cu", "query.cu", "raygen.cu", "backward.cu", "sam_bucket.cu", "bricks.cu", "gemm_tma.cu"]
+SOURCES = ["api.cu", "march.cu", "march_v1.cu", "sam.cu", "gemm.cu", "query.cu", "raygen.cu", "backward.cu", "sam_bucket.cu", "bricks.cu", "gemm_tma.cu", "exchange.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared", "--threads", "0",  # one compile job per source file
@@ -84,6 +84,8 @@ SYMBOLS = {
     "snrf_set_pipeline": (_I, [_P, _I]),
     "snrf_set_replication": (_I, [_P, _I, _P, _L, _P, C.POINTER(C.c_void_p), _I]),
     "snrf_set_replication_mode": (_I, [_P, _I]),
+    "snrf_set_feature_dtype": (_I, [_P, _I]),
+    "snrf_set_march_first": (_I, [_P, _I]),
     "snrf_generate_rays": (_I, [_P, C.POINTER(Camera), _P, _I, _P, _I, _I, _P, _P, _P, _P, _P, _P]),
     "snrf_render_camera": (_I, [_P, C.POINTER(Camera), _P, _I, _P, _I, _L, _U, C.POINTER(RenderOpts), _P, _P, _P, _P,
                                 _P, _P, _P]),

@@ -167,16 +167,68 @@ def load_checkpoint(path: str, base: Optional[SAMNeRFConfig] = None) -> Tuple[SA
     return infer_config(params, base), params, int(loaded.get("step", 0))
 
 
+def model_state_dict(cfg: SAMNeRFConfig, params: Mapping[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    """Every key the reference's ``SAMModel.state_dict()`` carries for this path (tests/golden/state_dict_layout.json,
+    produced by the reference's own modules): the hot-path tensors of ``params`` plus the geometry buffers the fields
+    register (``aabb``, ``max_res``, ``num_levels``, ``log2_hashmap_size``: nerfacto_field.py:121-125,
+    density_fields.py:66-71) and the parameter-free tcnn encodings (``direction_encoding.params`` /
+    ``position_encoding.params``, empty tensors), so that ``load_state_dict(strict=True)`` on the reference model finds
+    all of them."""
+    sd = {k: v.detach().cpu() for k, v in params.items()}
+    aabb = torch.tensor([[-1.0, -1.0, -1.0], [1.0, 1.0, 1.0]])  # scene box of the nerfstudio dataparsers (scene_box.py)
+    for prefix, g in (("field", cfg.field_grid), ("proposal_networks.0", cfg.proposal_grid)):
+        sd.setdefault(f"{prefix}.aabb", aabb.clone())
+        sd[f"{prefix}.max_res"] = torch.tensor(g.max_resolution)
+        sd[f"{prefix}.num_levels"] = torch.tensor(g.n_levels)
+        sd[f"{prefix}.log2_hashmap_size"] = torch.tensor(g.log2_hashmap_size)
+    sd.setdefault("field.direction_encoding.params", torch.empty(0))
+    sd.setdefault("field.position_encoding.params", torch.empty(0))
+    return sd
+
+
 def save_checkpoint(path: str, params: Mapping[str, torch.Tensor], step: int,
+                    source: Optional[str] = None, cfg: Optional[SAMNeRFConfig] = None,
                     extra_pipeline_state: Optional[Mapping[str, torch.Tensor]] = None, ddp: bool = False) -> str:
-    """Write ``params`` in the trainer's container layout (trainer.py:389-400) so that the reference's
-    ``Trainer._load_checkpoint`` / ``eval_load_checkpoint`` find the hot-path tensors where they expect them.
-    ``path`` may be a directory (-> ``step-{step:09d}.ckpt`` inside it)."""
+    """Write ``params`` in the trainer's container layout (trainer.py:389-400).  ``path`` may be a directory
+    (-> ``step-{step:09d}.ckpt`` inside it).  Two modes:
+
+    * ``source`` = the reference checkpoint the run started from (file or directory): its WHOLE pipeline state dict,
+      optimizer states and grad-scaler state are kept and only the hot-path tensors are replaced (under the prefix
+      convention the source uses).  This is what ``Trainer._load_checkpoint`` needs to resume: it calls
+      ``load_pipeline(..., strict=True)`` and ``grad_scaler.load_state_dict`` (trainer.py:372-380), both of which raise
+      on missing entries.
+    * no ``source``: an EVAL-ONLY export.  With ``cfg`` the model part is complete (``model_state_dict``: strict
+      loading of the model succeeds), but tensors that live outside the model (camera optimizer, optimizer / scaler
+      state) cannot be invented, so ``optimizers`` / ``scalers`` are empty and a training resume from it is refused by
+      the reference.  ``eval_load_checkpoint`` (eval_utils.py:36-65, non-strict consumers such as the viewer and
+      ``ns-render``) reads it as is."""
     if os.path.isdir(path) or path.endswith(os.sep):
         os.makedirs(path, exist_ok=True)
         path = os.path.join(path, f"step-{step:09d}.ckpt")
+    if source is not None:
+        if os.path.isdir(source):
+            source = latest_checkpoint(source)
+        loaded = torch.load(source, map_location="cpu", weights_only=True)
+        if "pipeline" not in loaded:
+            raise KeyError(f"{source}: not a trainer checkpoint (keys {sorted(loaded)[:5]})")
+        pipe = dict(loaded["pipeline"])
+        by_bare = {strip_prefixes(k): k for k in pipe}
+        for k, v in params.items():
+            if k not in by_bare:
+                raise KeyError(f"{k} is not in the source checkpoint's pipeline state")
+            old = pipe[by_bare[k]]
+            if tuple(old.shape) != tuple(v.shape) and old.numel() != v.numel():
+                raise ValueError(f"{k}: {tuple(v.shape)} does not fit the source checkpoint's {tuple(old.shape)}")
+            pipe[by_bare[k]] = v.detach().cpu().reshape(old.shape).to(old.dtype)
+        for k, v in (extra_pipeline_state or {}).items():
+            pipe[k] = v
+        out = dict(loaded)
+        out.update(step=int(step), pipeline=pipe)
+        torch.save(out, path)
+        return path
     prefix = ("module." if ddp else "") + "_model."
-    pipe = {prefix + k: v.detach().cpu() for k, v in params.items()}
+    model = model_state_dict(cfg, params) if cfg is not None else {k: v.detach().cpu() for k, v in params.items()}
+    pipe = {prefix + k: v for k, v in model.items()}
     for k, v in (extra_pipeline_state or {}).items():
         pipe[k] = v
     torch.save({"step": int(step), "pipeline": pipe, "optimizers": {}, "scalers": {}}, path)

@@ -41,6 +41,8 @@ struct DevBuf {
   }
 };
 
+constexpr int kCopyStreams = 32;  // kMaxPeers destinations x up to 4 pieces
+
 struct Replication {
   float* local = nullptr;
   size_t bytes = 0;
@@ -101,10 +103,14 @@ struct snrf_ctx {
   int64_t k_count[3] = {0, 0, 0};
   // fused tile all-gather (snrf_set_replication): 0 sam, 1 rgb, 2 depth, 3 accumulation, 4 prop_depth
   Replication rep[5];
-  int rep_mode = 0;  // 0: the kernels' own stores (multimem.st / peer pointers); 1: copy engines (cudaMemcpyAsync per peer)
+  int rep_mode = 0;  // 0: the kernels' own stores (multimem.st / peer pointers); 1: copy engines (cudaMemcpyAsync per peer);
+                     // 2: a small push kernel (peer stores from a few CTAs on a side stream, see launch_push_rows)
+  int dma_split = 1;      // copy-engine mode: pieces per destination and chunk (more copies in flight; SNRF_DMA_SPLIT)
+  bool rows_f16 = false;  // snrf_set_feature_dtype: the sam / clipseg output rows are fp16 instead of fp32
+  bool march_first = false;  // snrf_set_march_first: frame calls march the whole tile in one launch, then the feature chunks
   // one copy stream per destination (kMaxPeers): the copy engines serve the peers of a chunk concurrently
-  cudaStream_t copy_stream[kMaxPeers] = {nullptr};
-  cudaEvent_t ev_copy[kMaxPeers] = {nullptr}, ev_out[2] = {nullptr, nullptr};
+  cudaStream_t copy_stream[kCopyStreams] = {nullptr};
+  cudaEvent_t ev_copy[kCopyStreams] = {nullptr}, ev_out[2] = {nullptr, nullptr};
   // frame-level pipelining (snrf_render_frame)
   int pipeline = 1;  // 0 off, 1 auto (only when outputs are replicated to other ranks), 2 always
   bool aux_ready = false;
@@ -356,7 +362,7 @@ void snrf_ctx_destroy(snrf_ctx* ctx) {
   ctx->hbar[0][1].release(); ctx->hbar[1][0].release(); ctx->hbar[1][1].release();
   if (ctx->aux_feat) cudaStreamDestroy(ctx->aux_feat);
   if (ctx->aux_out) cudaStreamDestroy(ctx->aux_out);
-  for (int i = 0; i < kMaxPeers; ++i) {
+  for (int i = 0; i < kCopyStreams; ++i) {
     if (ctx->copy_stream[i]) cudaStreamDestroy(ctx->copy_stream[i]);
     if (ctx->ev_copy[i]) cudaEventDestroy(ctx->ev_copy[i]);
   }
@@ -462,8 +468,22 @@ int snrf_set_replication(snrf_ctx* ctx, int which, void* local_base, int64_t byt
 }
 
 int snrf_set_replication_mode(snrf_ctx* ctx, int mode) {
-  if (!ctx || (mode != 0 && mode != 1)) return fail(ctx, SNRF_E_INVALID, "replication mode must be 0 (stores) or 1 (copy engines)");
+  if (!ctx || mode < 0 || mode > 2)
+    return fail(ctx, SNRF_E_INVALID, "replication mode must be 0 (fused stores), 1 (copy engines) or 2 (push kernel)");
   ctx->rep_mode = mode;
+  if (const char* e = getenv("SNRF_DMA_SPLIT")) ctx->dma_split = atoi(e) < 1 ? 1 : (atoi(e) > 4 ? 4 : atoi(e));
+  return SNRF_OK;
+}
+
+int snrf_set_feature_dtype(snrf_ctx* ctx, int f16) {
+  if (!ctx || (f16 != 0 && f16 != 1)) return fail(ctx, SNRF_E_INVALID, "feature dtype must be 0 (fp32) or 1 (fp16)");
+  ctx->rows_f16 = f16 != 0;
+  return SNRF_OK;
+}
+
+int snrf_set_march_first(snrf_ctx* ctx, int enable) {
+  if (!ctx) return SNRF_E_INVALID;
+  ctx->march_first = enable != 0;
   return SNRF_OK;
 }
 
@@ -760,30 +780,32 @@ struct ChunkStreams {
   int out_grid;    // CTA cap of the output-layer kernel (0 = one per SM)
   bool small_cta;  // 8-warp / 145 KB feature kernel that shares an SM with march CTAs
   cudaEvent_t after_march;  // recorded right behind the march launch when not null (the per-ray outputs are complete there)
+  int stage;           // 0: march + features; 1: march only (picks go to the scratch); 2: features only (picks come from it)
+  int64_t scratch_off; // first ray of this call inside the sam_t / sam_w scratch (stage 1 / 2: the scratch spans the tile)
 };
 
 // offset-preserving aliases of an output pointer in the other ranks' frame buffers (snrf_set_replication)
-static void replicate(const snrf_ctx* ctx, int which, const float* out, int64_t n_floats, float** mc, float** peers,
+static void replicate(const snrf_ctx* ctx, int which, const void* out, int64_t n_bytes, float** mc, float** peers,
                       int* n_peers) {
   *mc = nullptr;
   *n_peers = 0;
   const Replication& R = ctx->rep[which];
-  if (ctx->rep_mode == 1) return;  // copy-engine mode: kernels write locally, snrf_render_frame pushes the rows
+  if (ctx->rep_mode != 0) return;  // copy-engine / push modes: kernels write locally, snrf_render_frame moves the rows
   const char* lo = reinterpret_cast<const char*>(R.local);
   const char* p = reinterpret_cast<const char*>(out);
-  if (!R.local || !out || p < lo || p + n_floats * sizeof(float) > lo + R.bytes) return;
-  const int64_t off = (p - lo) / static_cast<int64_t>(sizeof(float));
+  if (!R.local || !out || p < lo || p + n_bytes > lo + R.bytes) return;
+  const int64_t off = p - lo;
   if (R.mc) {
-    *mc = R.mc + off;
+    *mc = reinterpret_cast<float*>(reinterpret_cast<char*>(R.mc) + off);
   } else {
     *n_peers = R.n;
-    for (int i = 0; i < R.n; ++i) peers[i] = R.peer[i] + off;
+    for (int i = 0; i < R.n; ++i) peers[i] = reinterpret_cast<float*>(reinterpret_cast<char*>(R.peer[i]) + off);
   }
 }
 
 static int render_chunk(snrf_ctx* ctx, const float* origins, const float* dirs, const float* nears, const float* fars,
                         int64_t n_rays, uint32_t flags, const snrf_render_opts* opts, float* rgb, float* depth, float* acc,
-                        float* prop_depth, float* sam, float* clipseg, const snrf_debug_out* dbg, const ChunkStreams& cs) {
+                        float* prop_depth, void* sam, void* clipseg, const snrf_debug_out* dbg, const ChunkStreams& cs) {
   if (n_rays == 0) return SNRF_OK;  // empty chunk: nothing to read or write, pointers may be null
   if (!origins || !dirs || !opts || !rgb || !depth) return fail(ctx, SNRF_E_INVALID, "null argument");
   if (!ctx->have_base || !ctx->have_head) return fail(ctx, SNRF_E_STATE, "nerfacto field parameters not uploaded");
@@ -804,16 +826,16 @@ static int render_chunk(snrf_ctx* ctx, const float* origins, const float* dirs, 
   M.depth = depth;
   M.acc = acc;
   M.prop_depth = prop_depth;
-  replicate(ctx, 1, rgb, n_rays * 3, &M.rep[0].mc, M.rep[0].peer, &M.rep[0].n);
-  replicate(ctx, 2, depth, n_rays, &M.rep[1].mc, M.rep[1].peer, &M.rep[1].n);
-  replicate(ctx, 3, acc, n_rays, &M.rep[2].mc, M.rep[2].peer, &M.rep[2].n);
-  replicate(ctx, 4, prop_depth, n_rays, &M.rep[3].mc, M.rep[3].peer, &M.rep[3].n);
+  replicate(ctx, 1, rgb, n_rays * 12, &M.rep[0].mc, M.rep[0].peer, &M.rep[0].n);
+  replicate(ctx, 2, depth, n_rays * 4, &M.rep[1].mc, M.rep[1].peer, &M.rep[1].n);
+  replicate(ctx, 3, acc, n_rays * 4, &M.rep[2].mc, M.rep[2].peer, &M.rep[2].n);
+  replicate(ctx, 4, prop_depth, n_rays * 4, &M.rep[3].mc, M.rep[3].peer, &M.rep[3].n);
   const bool feats = want_sam || want_clip;
   if (feats || (dbg && dbg->sam_t)) {
-    CK(ctx->sam_t[slot].ensure(n_rays * 16 * 4));
-    CK(ctx->sam_w[slot].ensure(n_rays * 16 * 4));
-    M.sam_t = ctx->sam_t[slot].as<float>();
-    M.sam_w = ctx->sam_w[slot].as<float>();
+    CK(ctx->sam_t[slot].ensure((cs.scratch_off + n_rays) * 16 * 4));
+    CK(ctx->sam_w[slot].ensure((cs.scratch_off + n_rays) * 16 * 4));
+    M.sam_t = ctx->sam_t[slot].as<float>() + cs.scratch_off * 16;
+    M.sam_w = ctx->sam_w[slot].as<float>() + cs.scratch_off * 16;
   }
   if (dbg) {
     M.dbg_w0 = dbg->prop_weights;
@@ -822,8 +844,10 @@ static int render_chunk(snrf_ctx* ctx, const float* origins, const float* dirs, 
     M.dbg_density = dbg->density;
     M.dbg_rgb = dbg->rgb_samples;
   }
-  TIMED_LAUNCH(0, cs.march, ctx->march_v1 ? launch_march_v1(M, ctx->sm_count, cs.march) : launch_march(M, ctx->sm_count, cs.march));
+  if (cs.stage != 2)
+    TIMED_LAUNCH(0, cs.march, ctx->march_v1 ? launch_march_v1(M, ctx->sm_count, cs.march) : launch_march(M, ctx->sm_count, cs.march));
   if (cs.after_march) CK(cudaEventRecord(cs.after_march, cs.march));
+  if (cs.stage == 1) return SNRF_OK;
   if (dbg && dbg->sam_t) {
     CK(cudaMemcpyAsync(dbg->sam_t, M.sam_t, n_rays * 16 * 4, cudaMemcpyDeviceToDevice, cs.march));
     if (dbg->sam_w) CK(cudaMemcpyAsync(dbg->sam_w, M.sam_w, n_rays * 16 * 4, cudaMemcpyDeviceToDevice, cs.march));
@@ -902,11 +926,17 @@ static int render_chunk(snrf_ctx* ctx, const float* origins, const float* dirs, 
       CK(ctx->feat_f16.ensure(n_rays * 256 * 2));
       G.out_f16 = ctx->feat_f16.as<__half>();
       G.out_mode = 1;
+    } else if (ctx->rows_f16 && !patch) {
+      // fp16 output rows (snrf_set_feature_dtype): tcnn's own output precision; only the copy-engine / push exchange
+      if (ctx->rep_mode == 0 && which == 0 && ctx->rep[0].local && (ctx->rep[0].mc || ctx->rep[0].n > 0))
+        return fail(ctx, SNRF_E_INVALID, "fp16 feature rows cannot be combined with the fused multicast / peer stores");
+      G.out_f16 = reinterpret_cast<__half*>(which == 0 ? sam : clipseg);
+      G.out_mode = 1;
     } else {
-      G.out_f32 = which == 0 ? sam : clipseg;
+      G.out_f32 = reinterpret_cast<float*>(which == 0 ? sam : clipseg);
       G.out_mode = 0;
       // fused tile all-gather: mirror the rows into the other ranks' frame buffers at the same offset
-      if (which == 0) replicate(ctx, 0, sam, n_rays * 256, &G.out_mc, G.out_peer, &G.n_peers);
+      if (which == 0) replicate(ctx, 0, sam, n_rays * 256 * 4, &G.out_mc, G.out_peer, &G.n_peers);
     }
     TIMED_LAUNCH(2, cs.out, launch_tapgemm(G, ctx->engine == 1, out_sms, cs.out));
     if (to_patch) {
@@ -924,7 +954,7 @@ static int render_chunk(snrf_ctx* ctx, const float* origins, const float* dirs, 
       C.w = ctx->conv_w[1].as<__half>();
       C.bias = ctx->conv_b[1].as<float>();
       C.out_f16 = nullptr;
-      C.out_f32 = sam;
+      C.out_f32 = reinterpret_cast<float*>(sam);  // patch-aggregated rows are always fp32
       C.relu = 0; C.out_mode = 2;
       LAUNCH(launch_tapgemm(C, ctx->engine == 1, ctx->sm_count, cs.out));
     }
@@ -939,7 +969,7 @@ int snrf_render(snrf_ctx* ctx, const float* origins, const float* dirs, const fl
   if (n_rays < 0) return fail(ctx, SNRF_E_INVALID, "negative ray count");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   CK(cudaSetDevice(ctx->device));
-  const ChunkStreams cs = {s, s, s, 0, 0, false, nullptr};
+  const ChunkStreams cs = {s, s, s, 0, 0, false, nullptr, 0, 0};
   return render_chunk(ctx, origins, dirs, nears, fars, n_rays, flags, opts, rgb, depth, acc, prop_depth, sam, clipseg, dbg, cs);
 }
 
@@ -956,8 +986,8 @@ int snrf_render_frame(snrf_ctx* ctx, const float* origins, const float* dirs, co
     CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
     CK(cudaStreamCreateWithPriority(&ctx->aux_feat, cudaStreamNonBlocking, hi));
     CK(cudaStreamCreateWithPriority(&ctx->aux_out, cudaStreamNonBlocking, hi));
-    for (int i = 0; i < kMaxPeers; ++i) {
-      CK(cudaStreamCreateWithFlags(&ctx->copy_stream[i], cudaStreamNonBlocking));
+    for (int i = 0; i < kCopyStreams; ++i) {
+      CK(cudaStreamCreateWithPriority(&ctx->copy_stream[i], cudaStreamNonBlocking, hi));
       CK(cudaEventCreateWithFlags(&ctx->ev_copy[i], cudaEventDisableTiming));
     }
     CK(cudaEventCreateWithFlags(&ctx->ev_out[0], cudaEventDisableTiming));
@@ -965,13 +995,15 @@ int snrf_render_frame(snrf_ctx* ctx, const float* origins, const float* dirs, co
     ctx->aux_ready = true;
   }
   const bool feats = (flags & (SNRF_WANT_SAM | SNRF_WANT_CLIPSEG)) != 0;
-  bool dma = false;  // copy-engine exchange: any output registered with at least one destination
-  for (int w = 0; w < 5; ++w) dma = dma || (ctx->rep_mode == 1 && ctx->rep[w].local && ctx->rep[w].n > 0);
-  const bool dma_sam = dma && ctx->rep[0].local && ctx->rep[0].n > 0;
+  // rows leave through copy engines (mode 1) or the push kernel (mode 2): any output registered with a destination
+  bool moved = false;
+  for (int w = 0; w < 5; ++w) moved = moved || (ctx->rep_mode != 0 && ctx->rep[w].local && ctx->rep[w].n > 0);
+  const bool move_sam = moved && ctx->rep[0].local && ctx->rep[0].n > 0;
   // auto: pipeline only when a kernel's own replicated stores are NVLink-bound; with copy engines the kernels run
   // back to back on one stream (cross-stream hops cost ~20 us per chunk and buy nothing when the exchange is off the SMs)
-  const bool pipelined = feats && n_rays > chunk && (ctx->pipeline == 2 || (ctx->pipeline == 1 && ctx->rep[0].local && !dma));
+  const bool pipelined = feats && n_rays > chunk && (ctx->pipeline == 2 || (ctx->pipeline == 1 && ctx->rep[0].local && !moved));
   const int p2 = (flags & SNRF_PATCH) ? 16 : 1;
+  const size_t esz = ctx->rows_f16 && !(flags & SNRF_PATCH) ? 2 : 4;  // bytes per feature element (patch rows stay fp32)
   // the aux streams start after everything already queued on the caller's stream
   if (pipelined) {
     CK(cudaEventRecord(ctx->ev_join, s));
@@ -981,51 +1013,78 @@ int snrf_render_frame(snrf_ctx* ctx, const float* origins, const float* dirs, co
   // with replicated outputs the output-layer kernel is throttled by NVLink, not by the SMs: keep its footprint small
   // (multicast: one store reaches every rank, a handful of SMs saturate the link; peer pointers: n_peers stores)
   int out_grid = 0;
-  if (pipelined && ctx->rep[0].local && !dma) {
+  if (pipelined && ctx->rep[0].local && !moved) {
     out_grid = 32;
     if (const char* e = getenv("SNRF_OUT_GRID")) out_grid = atoi(e);
   }
+  // march-first (snrf_set_march_first): one march launch over the whole tile - the picks of every ray go to the scratch -
+  // then the feature kernels chunk by chunk.  Fewer, larger march launches; the bulk rows still leave chunk by chunk.
+  const bool march_first = ctx->march_first && feats && !pipelined && n_rays > chunk;
+  if (march_first) {
+    ChunkStreams cs = {s, s, s, 0, 0, false, moved ? ctx->ev_join : nullptr, 1, 0};
+    int rc = render_chunk(ctx, origins, dirs, nears, fars, n_rays, flags, opts, rgb, depth, acc, prop_depth, sam, clipseg, nullptr, cs);
+    if (rc) return rc;
+  }
+  uint32_t used = 0;  // copy streams that carry work of this frame
   int64_t c = 0;
   for (int64_t i = 0; i < n_rays; i += chunk, ++c) {
     const int64_t n = n_rays - i < chunk ? n_rays - i : chunk;
     const int slot = pipelined ? static_cast<int>(c & 1) : 0;
-    // copy-engine exchange: rgb / depth / accumulation / proposal depth of the whole tile are complete behind the LAST
-    // chunk's march kernel, so their copies start there and overlap that chunk's feature kernels
+    // rgb / depth / accumulation / proposal depth of the whole tile are complete behind the LAST chunk's march kernel,
+    // so their copies start there and overlap that chunk's feature kernels
     const bool last_chunk = i + chunk >= n_rays;
     ChunkStreams cs = {s, pipelined ? ctx->aux_feat : s, pipelined ? ctx->aux_out : s, slot, out_grid,
-                       pipelined && getenv("SNRF_CORESIDENT") != nullptr, (dma && last_chunk) ? ctx->ev_join : nullptr};
+                       pipelined && getenv("SNRF_CORESIDENT") != nullptr,
+                       (moved && last_chunk && !march_first) ? ctx->ev_join : nullptr, march_first ? 2 : 0, march_first ? i : 0};
     if (pipelined && c >= 2) {
       CK(cudaStreamWaitEvent(s, ctx->ev_feat_done[slot], 0));             // sam_t / sam_w of this slot are free again
       CK(cudaStreamWaitEvent(ctx->aux_feat, ctx->ev_out_done[slot], 0));  // hbar of this slot is free again
     }
+    char* sam_c = sam ? reinterpret_cast<char*>(sam) + (i / p2) * 256 * esz : nullptr;
+    char* clip_c = clipseg ? reinterpret_cast<char*>(clipseg) + i * 192 * esz : nullptr;
     int rc = render_chunk(ctx, origins + 3 * i, dirs + 3 * i, nears ? nears + i : nullptr, fars ? fars + i : nullptr, n,
                           flags, opts, rgb + 3 * i, depth + i, acc ? acc + i : nullptr,
-                          prop_depth ? prop_depth + i : nullptr, sam ? sam + (i / p2) * 256 : nullptr,
-                          clipseg ? clipseg + i * 192 : nullptr, nullptr, cs);
+                          prop_depth ? prop_depth + i : nullptr, sam_c, clip_c, nullptr, cs);
     if (rc) return rc;
     if (pipelined) {
       CK(cudaEventRecord(ctx->ev_feat_done[slot], ctx->aux_feat));
       CK(cudaEventRecord(ctx->ev_out_done[slot], ctx->aux_out));
     }
-    // copy-engine exchange: as soon as this chunk's feature rows exist, DMA them into every peer's frame buffer
-    if (dma_sam && sam && (flags & SNRF_WANT_SAM) && !(flags & SNRF_PATCH)) {
+    // exchange: as soon as this chunk's feature rows exist, move them into every destination's frame buffer
+    if (move_sam && sam && (flags & SNRF_WANT_SAM) && !(flags & SNRF_PATCH)) {
       const Replication& R = ctx->rep[0];
-      float* src = sam + i * 256;
       const char* lo = reinterpret_cast<const char*>(R.local);
-      const char* p = reinterpret_cast<const char*>(src);
-      if (p >= lo && p + n * 256 * sizeof(float) <= lo + R.bytes) {
-        const int64_t off = (p - lo) / static_cast<int64_t>(sizeof(float));
+      const size_t bytes = static_cast<size_t>(n) * 256 * esz;
+      if (sam_c >= lo && sam_c + bytes <= lo + R.bytes) {
+        const int64_t off = sam_c - lo;
         cudaStream_t so = pipelined ? ctx->aux_out : s;
         CK(cudaEventRecord(ctx->ev_out[c & 1], so));
-        for (int q = 0; q < R.n; ++q) {
-          cudaStream_t cp = ctx->copy_stream[q % kMaxPeers];
+        if (ctx->rep_mode == 2) {
+          cudaStream_t cp = ctx->copy_stream[0];
+          used |= 1u;
           CK(cudaStreamWaitEvent(cp, ctx->ev_out[c & 1], 0));
-          CK(cudaMemcpyAsync(R.peer[q] + off, src, n * 256 * sizeof(float), cudaMemcpyDefault, cp));
+          void* dst[kMaxPeers] = {nullptr};
+          for (int q = 0; q < R.n; ++q) dst[q] = reinterpret_cast<char*>(R.peer[q]) + off;
+          LAUNCH(launch_push_rows(sam_c, dst, R.n, bytes, cp));
+        } else {
+          const int pieces = ctx->dma_split;
+          const size_t piece = ((bytes / pieces) + 255) & ~static_cast<size_t>(255);
+          for (int q = 0; q < R.n; ++q)
+            for (int k = 0; k < pieces; ++k) {
+              const size_t b0 = k * piece;
+              if (b0 >= bytes) break;
+              const size_t nb = bytes - b0 < piece ? bytes - b0 : piece;
+              const int si = (q * pieces + k) % kCopyStreams;
+              cudaStream_t cp = ctx->copy_stream[si];
+              used |= 1u << si;
+              CK(cudaStreamWaitEvent(cp, ctx->ev_out[c & 1], 0));
+              CK(cudaMemcpyAsync(reinterpret_cast<char*>(R.peer[q]) + off + b0, sam_c + b0, nb, cudaMemcpyDefault, cp));
+            }
         }
       }
     }
   }
-  if (dma) {
+  if (moved) {
     // the small per-ray outputs (24 B/ray) go once per frame, behind the last march kernel
     float* outs[4] = {rgb, depth, acc, prop_depth};
     const int64_t widths[4] = {3, 1, 1, 1};
@@ -1038,12 +1097,15 @@ int snrf_render_frame(snrf_ctx* ctx, const float* origins, const float* dirs, co
       if (p < lo || p + n_rays * widths[w] * sizeof(float) > lo + R.bytes) continue;
       const int64_t off = (p - lo) / static_cast<int64_t>(sizeof(float));
       for (int q = 0; q < R.n; ++q) {
-        cudaStream_t cp = ctx->copy_stream[q % kMaxPeers];
+        const int si = (kCopyStreams - 1 - q) % kCopyStreams;
+        cudaStream_t cp = ctx->copy_stream[si];
+        used |= 1u << si;
         CK(cudaStreamWaitEvent(cp, ctx->ev_join, 0));
         CK(cudaMemcpyAsync(R.peer[q] + off, outs[w], n_rays * widths[w] * sizeof(float), cudaMemcpyDefault, cp));
       }
     }
-    for (int q = 0; q < kMaxPeers; ++q) {  // the caller's stream resumes after every copy has been queued and finished
+    for (int q = 0; q < kCopyStreams; ++q) {  // the caller's stream resumes after every copy has been queued and finished
+      if (!((used >> q) & 1u)) continue;
       CK(cudaEventRecord(ctx->ev_copy[q], ctx->copy_stream[q]));
       CK(cudaStreamWaitEvent(s, ctx->ev_copy[q], 0));
     }

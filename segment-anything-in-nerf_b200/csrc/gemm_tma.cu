@@ -36,12 +36,6 @@ constexpr uint32_t kOffA = 0, kOffStore = kStages * kStageBytes, kOffW = kOffSto
 constexpr uint32_t kSmemBytes = kOffBar + 256 + 1024;  // + slack for the 1024-byte alignment of the swizzled tiles
 constexpr int kThreads = 192;
 
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
-}
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int x, int y, uint32_t bar) {
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::"r"(dst),
                "l"(map), "r"(x), "r"(y), "r"(bar)
@@ -50,11 +44,6 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int x, int y) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];\n" ::"l"(map), "r"(src), "r"(x),
                "r"(y)
-               : "memory");
-}
-__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst), "l"(src),
-               "r"(bytes), "r"(bar)
                : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
@@ -90,6 +79,9 @@ struct TmaGemmParams {
   int relu;
 };
 
+// F16 = false: fp32 output rows (boxes of 128 x 32 floats); F16 = true: fp16 output rows (boxes of 128 x 64 halfs, two
+// 32-column TMEM chunks per box) - the fp16 feature rows of snrf_set_feature_dtype and the input rows of the conv head
+template <bool F16>
 __global__ void __launch_bounds__(kThreads, 1)
 tapgemm_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_out, const TmaGemmParams P) {
   extern __shared__ unsigned char smem_raw[];
@@ -188,34 +180,46 @@ tapgemm_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       const int acc = t & 1;
       mbar_wait(t_full(acc), (t >> 1) & 1u);
       tc_fence_after();
-      for (int c = 0; c < n_chunks; ++c, ++n_store) {
+      for (int c = 0; c < n_chunks; ++c) {
         const int sb = n_store & 1;
-        if (issuer) bulk_wait_read<1>();  // the store issued two chunks ago has finished reading this staging buffer
-        epi_bar();
+        const bool opens = !F16 || (c & 1) == 0;               // first chunk of a staging box
+        const bool closes = !F16 || (c & 1) == 1 || c == n_chunks - 1;  // last chunk of a staging box
+        if (opens) {
+          if (issuer) bulk_wait_read<1>();  // the store issued two boxes ago has finished reading this staging buffer
+          epi_bar();
+        }
         float v[32];
         tmem_ld32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * 256 + c * 32, v);
         if (c == n_chunks - 1) {  // accumulator fully read: hand it back to the MMA warp
           tc_fence_before();
           mbar_arrive(t_empty(acc));
         }
-        unsigned char* st = gen + kOffStore + sb * kStoreBytes + row * 128;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          float4 o;
-          o.x = v[4 * q + 0] + s_bias[c * 32 + 4 * q + 0];
-          o.y = v[4 * q + 1] + s_bias[c * 32 + 4 * q + 1];
-          o.z = v[4 * q + 2] + s_bias[c * 32 + 4 * q + 2];
-          o.w = v[4 * q + 3] + s_bias[c * 32 + 4 * q + 3];
-          if (P.relu) {
-            o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
-          }
-          *reinterpret_cast<float4*>(st + ((q ^ (row & 7)) << 4)) = o;  // 128-byte swizzle: chunk ^= row % 8
+        for (int i = 0; i < 32; ++i) {
+          v[i] += s_bias[c * 32 + i];
+          if (P.relu) v[i] = fmaxf(v[i], 0.f);
         }
-        fence_async_smem();
-        epi_bar();
-        if (issuer) {
-          tma_store_2d(&map_out, base + kOffStore + sb * kStoreBytes, c * 32, static_cast<int>(tile * 128));
-          bulk_commit();
+        unsigned char* st = gen + kOffStore + sb * kStoreBytes + row * 128;
+        if (F16) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {  // 8 halfs per 16-byte piece; this chunk fills pieces (c & 1) * 4 .. + 3 of the row
+            const uint4 o = make_uint4(f2_to_h2(v[8 * q + 0], v[8 * q + 1]), f2_to_h2(v[8 * q + 2], v[8 * q + 3]),
+                                       f2_to_h2(v[8 * q + 4], v[8 * q + 5]), f2_to_h2(v[8 * q + 6], v[8 * q + 7]));
+            *reinterpret_cast<uint4*>(st + ((((c & 1) * 4 + q) ^ (row & 7)) << 4)) = o;
+          }
+        } else {
+#pragma unroll
+          for (int q = 0; q < 8; ++q)  // 128-byte swizzle: 16-byte piece index ^= row % 8
+            *reinterpret_cast<float4*>(st + ((q ^ (row & 7)) << 4)) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        }
+        if (closes) {
+          fence_async_smem();
+          epi_bar();
+          if (issuer) {
+            tma_store_2d(&map_out, base + kOffStore + sb * kStoreBytes, F16 ? (c >> 1) * 64 : c * 32, static_cast<int>(tile * 128));
+            bulk_commit();
+          }
+          ++n_store;
         }
       }
     }
@@ -258,19 +262,26 @@ bool make_map(CUtensorMap* map, CUtensorMapDataType type, size_t elem, void* ptr
 
 // Returns cudaErrorNotSupported when this launch cannot take the TMA path (the caller then uses gemm.cu).
 cudaError_t launch_tapgemm_tma(const GemmParams& P, int sm_count, cudaStream_t stream) {
-  if (P.taps != 1 || P.out_mode != 0 || P.out_mc || P.n_peers > 0 || (P.n != 256 && P.n != 192)) return cudaErrorNotSupported;
+  if (P.taps != 1 || (P.out_mode != 0 && P.out_mode != 1) || P.out_mc || P.n_peers > 0 || (P.n != 256 && P.n != 192))
+    return cudaErrorNotSupported;
   if (P.m <= 0) return cudaSuccess;
-  if ((reinterpret_cast<uintptr_t>(P.a) | reinterpret_cast<uintptr_t>(P.out_f32) | reinterpret_cast<uintptr_t>(P.w)) & 15u)
+  const bool f16 = P.out_mode == 1;
+  void* out = f16 ? static_cast<void*>(P.out_f16) : static_cast<void*>(P.out_f32);
+  if ((reinterpret_cast<uintptr_t>(P.a) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(P.w)) & 15u)
     return cudaErrorNotSupported;  // TMA wants 16-byte aligned global addresses
   CUtensorMap map_a, map_out;
-  if (!make_map(&map_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(P.a), kK, static_cast<uint64_t>(P.m), 64, 128) ||
-      !make_map(&map_out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, P.out_f32, static_cast<uint64_t>(P.n), static_cast<uint64_t>(P.m), 32, 128))
+  if (!make_map(&map_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(P.a), kK, static_cast<uint64_t>(P.m), 64, 128))
+    return cudaErrorNotSupported;
+  if (f16 ? !make_map(&map_out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, out, static_cast<uint64_t>(P.n), static_cast<uint64_t>(P.m), 64, 128)
+          : !make_map(&map_out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, out, static_cast<uint64_t>(P.n), static_cast<uint64_t>(P.m), 32, 128))
     return cudaErrorNotSupported;
   static bool configured_dev[64] = {false};
   int dev_id = 0;
   if (cudaGetDevice(&dev_id) != cudaSuccess || dev_id < 0 || dev_id >= 64) return cudaErrorInvalidDevice;
   if (!configured_dev[dev_id]) {
-    cudaError_t e = cudaFuncSetAttribute(tapgemm_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(tapgemm_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(tapgemm_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
     if (e != cudaSuccess) return e;
     configured_dev[dev_id] = true;
   }
@@ -282,7 +293,10 @@ cudaError_t launch_tapgemm_tma(const GemmParams& P, int sm_count, cudaStream_t s
   T.relu = P.relu;
   const int64_t n_tiles = (P.m + 127) / 128;
   const int grid = static_cast<int>(n_tiles < sm_count ? n_tiles : sm_count);
-  tapgemm_tma_kernel<<<grid, kThreads, kSmemBytes, stream>>>(map_a, map_out, T);
+  if (f16)
+    tapgemm_tma_kernel<true><<<grid, kThreads, kSmemBytes, stream>>>(map_a, map_out, T);
+  else
+    tapgemm_tma_kernel<false><<<grid, kThreads, kSmemBytes, stream>>>(map_a, map_out, T);
   return cudaGetLastError();
 }
 

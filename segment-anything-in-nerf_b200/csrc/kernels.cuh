@@ -165,6 +165,9 @@ cudaError_t launch_tapgemm(const GemmParams& P, bool tcgen05, int sm_count, cuda
 // cudaErrorNotSupported = this launch is not its case; launch_tapgemm falls through to the kernel above.
 cudaError_t launch_tapgemm_tma(const GemmParams& P, int sm_count, cudaStream_t stream);
 
+// ---- tile exchange by peer stores from a small kernel (exchange.cu) --------------------------------
+cudaError_t launch_push_rows(const void* src, void* const* dst, int n_dst, size_t bytes, cudaStream_t stream);
+
 // ---- stand-alone field queries (back Field.density_fn / SAMField.get_outputs) --------------------
 struct QueryParams {
   const float* xyz;  // [N,3] world positions

@@ -107,20 +107,24 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 2 : 1) sam_kernel(const Sam
   unsigned char* s_w1 = smem;
   unsigned char* s_a = smem + kW1Bytes;
   float* s_sw = reinterpret_cast<float*>(smem + kW1Bytes + NBUF * kATileBytes);  // [2][128]
-  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_sw + 256);                  // [2]
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 2);
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_sw + 256);                  // [2] MMA done, [1] W1 landed
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 3);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const unsigned FULL = 0xffffffffu;
 
-  // W1 is already in core-matrix layout in HBM: straight 16-byte copy
-  for (uint32_t i = tid; i < kW1Bytes / 16; i += kThreads)
-    reinterpret_cast<uint4*>(s_w1)[i] = ldg_u128(reinterpret_cast<const uint4*>(P.w1) + i);
+  // W1 is already in core-matrix layout in HBM.  tcgen05 engine: one bulk copy by the TMA unit (cp.async.bulk, 96 KB),
+  // issued below and awaited only in front of the first MMA, so that it overlaps the first tile's gather; the legacy
+  // engine stages it with plain 16-byte copies
+  if (!TC)
+    for (uint32_t i = tid; i < kW1Bytes / 16; i += kThreads)
+      reinterpret_cast<uint4*>(s_w1)[i] = ldg_u128(reinterpret_cast<const uint4*>(P.w1) + i);
   uint32_t tmem_base = 0;
   if (TC) {
     if (tid == 0) {
       mbar_init(smem_u32(&s_bar[0]), 1);
       mbar_init(smem_u32(&s_bar[1]), 1);
+      mbar_init(smem_u32(&s_bar[2]), 1);
       asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     if (warp == 0) tmem_alloc(smem_u32(s_tmem), 256 * NBUF);
@@ -128,9 +132,14 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 2 : 1) sam_kernel(const Sam
     tc_fence_before();
   }
   __syncthreads();
+  bool w1_ready = !TC;
   if (TC) {
     tc_fence_after();
     tmem_base = *s_tmem;
+    if (tid == 0) {
+      mbar_expect_tx(smem_u32(&s_bar[2]), kW1Bytes);
+      bulk_load_1d(smem_u32(s_w1), P.w1, kW1Bytes, smem_u32(&s_bar[2]));
+    }
   }
 
   const int64_t n_tiles = (P.n_rays + kRaysPerTile - 1) / kRaysPerTile;
@@ -191,6 +200,10 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 2 : 1) sam_kernel(const Sam
 
     if (TC) {
       if (tid == 0) {
+        if (!w1_ready) {
+          mbar_wait(smem_u32(&s_bar[2]), 0);
+          w1_ready = true;
+        }
         tc_fence_after();
         const uint32_t a_addr = smem_u32(a_tile), b_addr = smem_u32(s_w1);
         const uint32_t idesc = umma_idesc_f16(128, 256);

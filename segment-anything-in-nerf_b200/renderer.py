@@ -86,6 +86,7 @@ class Renderer:
         u = torch.cat([base + 1.0 / (2 * nb), base]).contiguous()  # eval positions, then the training-mode base (:314-322)
         self._check(self.lib.snrf_set_pdf_u(self.h, u.data_ptr(), 2 * nb))
         self.have_sam = self.have_clipseg = self.have_conv = False
+        self.feature_dtype = torch.float32
         # opt-in knobs from the environment, so that a whole test / bench run can be put through them unchanged
         # (e.g. SNRF_FEATURE_CUTOFF=5.96e-8 pytest -m gpu runs every parity test through the bucketed feature kernel)
         import os
@@ -137,8 +138,22 @@ class Renderer:
             C.c_void_p(multicast_ptr) if multicast_ptr else None, arr, len(peer_ptrs)))
 
     def set_replication_mode(self, mode: str) -> None:
-        """``stores``: the kernels' own multimem.st / peer stores (default); ``dma``: copy engines push each chunk."""
-        self._check(self.lib.snrf_set_replication_mode(self.h, {"stores": 0, "dma": 1}[mode]))
+        """``stores``: the kernels' own multimem.st / peer stores (default); ``dma``: copy engines move each chunk;
+        ``push``: a small kernel on a side stream stores each chunk into the peers' buffers (csrc/exchange.cu)."""
+        self._check(self.lib.snrf_set_replication_mode(self.h, {"stores": 0, "dma": 1, "push": 2}[mode]))
+
+    def set_feature_dtype(self, dtype) -> None:
+        """Element type of the ``sam`` / ``clipseg`` rows the render calls write: ``torch.float32`` (default, as the
+        reference) or ``torch.float16`` (tinycudann's own output precision; halves the bytes of the tile exchange and
+        of the device-to-host copy).  See ``snrf_set_feature_dtype``."""
+        dtype = {"f32": torch.float32, "f16": torch.float16}.get(dtype, dtype)
+        assert dtype in (torch.float32, torch.float16), dtype
+        self._check(self.lib.snrf_set_feature_dtype(self.h, int(dtype == torch.float16)))
+        self.feature_dtype = dtype
+
+    def set_march_first(self, enable: bool) -> None:
+        """Frame calls march the whole tile in one launch, then run the feature kernels per chunk (``snrf_set_march_first``)."""
+        self._check(self.lib.snrf_set_march_first(self.h, int(bool(enable))))
 
     def set_pipeline(self, mode: int) -> None:
         """Chunk pipelining of ``render_frame`` over the library's internal streams: 0 off, 1 auto (default: only
@@ -289,11 +304,11 @@ class Renderer:
         dev = self.device
         given = out if out is not None else {}
 
-        def buf(name, *shape):
+        def buf(name, *shape, dtype=torch.float32):
             t = given.get(name)
             if t is None:
-                return torch.empty(*shape, device=dev)
-            assert t.is_cuda and t.is_contiguous() and t.dtype == torch.float32 and tuple(t.shape) == shape, name
+                return torch.empty(*shape, device=dev, dtype=dtype)
+            assert t.is_cuda and t.is_contiguous() and t.dtype == dtype and tuple(t.shape) == shape, (name, t.dtype, dtype)
             return t
 
         out = {"rgb": buf("rgb", n, 3), "depth": buf("depth", n, 1)}
@@ -308,10 +323,10 @@ class Renderer:
                 flags |= L.PATCH
                 out["sam"] = buf("sam", n // (cfg.patch_size**2), cfg.sam_out)
             else:
-                out["sam"] = buf("sam", n, cfg.sam_out)
+                out["sam"] = buf("sam", n, cfg.sam_out, dtype=self.feature_dtype)
         if cfg.distill_sam and cfg.use_clipseg_feature and "clipseg" in get_feature:
             flags |= L.WANT_CLIPSEG
-            out["clipseg"] = buf("clipseg", n, cfg.clipseg_out)
+            out["clipseg"] = buf("clipseg", n, cfg.clipseg_out, dtype=torch.float32 if patch else self.feature_dtype)
         dbg = None
         if debug:
             k = cfg.num_sam_samples
@@ -363,16 +378,17 @@ class Renderer:
                 out["accumulation"] = torch.empty(n, 1, device=dev)
                 out["prop_depth_0"] = torch.empty(n, 1, device=dev)
             if cfg.distill_sam and "sam" in get_feature:
-                out["sam"] = torch.empty(n, cfg.sam_out, device=dev)
+                out["sam"] = torch.empty(n, cfg.sam_out, device=dev, dtype=self.feature_dtype)
             if cfg.distill_sam and cfg.use_clipseg_feature and "clipseg" in get_feature:
-                out["clipseg"] = torch.empty(n, cfg.clipseg_out, device=dev)
+                out["clipseg"] = torch.empty(n, cfg.clipseg_out, device=dev, dtype=self.feature_dtype)
         flags = 0
         if "sam" in out:
             flags |= L.WANT_SAM
         if "clipseg" in out:
             flags |= L.WANT_CLIPSEG
         for k, v in out.items():
-            assert v.is_cuda and v.is_contiguous() and v.dtype == torch.float32 and v.shape[0] == n, k
+            want = self.feature_dtype if k in ("sam", "clipseg") else torch.float32
+            assert v.is_cuda and v.is_contiguous() and v.dtype == want and v.shape[0] == n, (k, v.dtype, want)
         opts = self._opts(None)
         self._check(self.lib.snrf_render_frame(
             self.h, o.data_ptr(), d.data_ptr(), None, None, n, chunk, flags, C.byref(opts), out["rgb"].data_ptr(),
@@ -415,16 +431,18 @@ class Renderer:
             if not fast:
                 out["accumulation"] = torch.empty(n, 1, device=dev)
                 out["prop_depth_0"] = torch.empty(n, 1, device=dev)
+            fdt = torch.float32 if patch else self.feature_dtype
             if cfg.distill_sam and "sam" in get_feature:
-                out["sam"] = torch.empty(n // (cfg.patch_size**2) if patch else n, cfg.sam_out, device=dev)
+                out["sam"] = torch.empty(n // (cfg.patch_size**2) if patch else n, cfg.sam_out, device=dev, dtype=fdt)
             if cfg.distill_sam and cfg.use_clipseg_feature and "clipseg" in get_feature:
-                out["clipseg"] = torch.empty(n, cfg.clipseg_out, device=dev)
+                out["clipseg"] = torch.empty(n, cfg.clipseg_out, device=dev, dtype=fdt)
         if "sam" in out:
             flags |= L.WANT_SAM | (L.PATCH if patch else 0)
         if "clipseg" in out:
             flags |= L.WANT_CLIPSEG
         for k, v in out.items():
-            assert v.is_cuda and v.is_contiguous() and v.dtype == torch.float32, k
+            want = (torch.float32 if patch else self.feature_dtype) if k in ("sam", "clipseg") else torch.float32
+            assert v.is_cuda and v.is_contiguous() and v.dtype == want, (k, v.dtype, want)
         opts = self._opts(None)
         st = cam.as_struct()
         self._check(self.lib.snrf_render_camera(

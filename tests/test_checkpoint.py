@@ -156,3 +156,64 @@ def test_model_from_checkpoint(tmp_path, monkeypatch):
     assert m2.step == 1300
     assert torch.allclose(m2.renderer.p["sam_field.sam_net.params"], params["sam_field.sam_net.params"] + 0.25)
     assert torch.equal(m2.renderer.p["field.mlp_base.params"], params["field.mlp_base.params"])
+
+
+def _strict_load(target_keys_shapes, state):
+    """What ``nn.Module.load_state_dict(strict=True)`` enforces (Trainer._load_checkpoint -> load_pipeline(strict=True),
+    trainer.py:372-376, base_pipeline.py:366-375): no missing key, no unexpected key, equal shapes."""
+    missing = sorted(set(target_keys_shapes) - set(state))
+    unexpected = sorted(set(state) - set(target_keys_shapes))
+    assert not missing and not unexpected, (missing, unexpected)
+    for k, shp in target_keys_shapes.items():
+        assert list(state[k].shape) == list(shp), (k, tuple(state[k].shape), shp)
+
+
+@pytest.mark.parametrize("name,cfg", [("tiny_distill_clipseg_p4", SAMNeRFConfig.tiny(clipseg=True, patch_size=4)),
+                                      ("full_distill_p4", None)])
+def test_saved_checkpoint_passes_the_reference_trainers_strict_load(tmp_path, name, cfg):
+    """Resume path: starting from a reference checkpoint (every key of the reference's own modules, the camera
+    optimizer, Adam state, grad-scaler state), ``save_checkpoint(source=...)`` must hand back a file the reference's
+    strict loader accepts, with the hot-path tensors replaced and everything else untouched."""
+    layout = _layout(name)
+    if cfg is None:  # full size: keep the test light - meta-sized fake tensors are enough for key / shape logic
+        pytest.importorskip("torch")
+        small = {k: v for k, v in layout.items() if int(np.prod(v)) < 1_000_000}
+        layout = small
+    gen = torch.Generator().manual_seed(5)
+    pipe = {k: torch.randn(*shp, generator=gen) if shp else torch.tensor(7) for k, shp in layout.items()}
+    opt = {"fields": {"state": {0: {"step": torch.tensor(3.0), "exp_avg": torch.randn(5, generator=gen)}}, "param_groups": [{"lr": 1e-2}]}}
+    scaler = {"scale": 65536.0, "growth_factor": 2.0, "backoff_factor": 0.5, "growth_interval": 2000, "_growth_tracker": 0}
+    src = tmp_path / "step-000000100.ckpt"
+    torch.save({"step": 100, "pipeline": pipe, "optimizers": opt, "scalers": scaler}, src)
+
+    hot = {ck.strip_prefixes(k): v for k, v in pipe.items() if ck.strip_prefixes(k) in ck.HOT_PATH_KEYS}
+    assert hot, "layout has no hot-path tensors?"
+    trained = {k: v + 1.0 for k, v in hot.items()}
+    out = ck.save_checkpoint(str(tmp_path / "out") + os.sep, trained, step=200, source=str(src))
+    got = torch.load(out, map_location="cpu", weights_only=True)
+    assert got["step"] == 200
+    _strict_load(layout, got["pipeline"])
+    for k, v in pipe.items():
+        bare = ck.strip_prefixes(k)
+        want = trained[bare] if bare in trained else v
+        assert torch.equal(got["pipeline"][k], want), k
+    # optimizer and scaler state survive: GradScaler.load_state_dict({}) raises in the reference (mixed precision is on
+    # in both shipped configs), and Adam moments must not be lost on resume
+    assert got["scalers"] == scaler and torch.equal(got["optimizers"]["fields"]["state"][0]["exp_avg"], opt["fields"]["state"][0]["exp_avg"])
+    with pytest.raises(KeyError, match="not in the source"):
+        ck.save_checkpoint(str(tmp_path / "out") + os.sep, {"sam_field.bogus.params": torch.zeros(3)}, step=201, source=str(src))
+
+
+def test_eval_export_has_every_model_key_of_the_reference(tmp_path):
+    """Without a source checkpoint: the model part of the export is complete (strict load of the MODEL passes: the
+    geometry buffers and the parameter-free encodings are synthesised from the config); what lives outside the model
+    cannot be invented, and the file says so by carrying empty optimizer / scaler dicts (eval-only)."""
+    cfg = SAMNeRFConfig.tiny(clipseg=True, patch_size=4)
+    layout = {k: v for k, v in _layout("tiny_distill_clipseg_p4").items() if k.startswith("_model.")}
+    params = make_synthetic_params(cfg, "init", 2)
+    out = ck.save_checkpoint(str(tmp_path) + os.sep, params, step=9, cfg=cfg)
+    got = torch.load(out, map_location="cpu", weights_only=True)
+    _strict_load(layout, got["pipeline"])
+    assert got["optimizers"] == {} and got["scalers"] == {}
+    cfg2, params2, step = ck.load_checkpoint(out, base=SAMNeRFConfig.tiny())
+    assert step == 9 and cfg2 == cfg and all(torch.equal(params2[k], params[k]) for k in params)

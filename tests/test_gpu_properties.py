@@ -82,6 +82,31 @@ def test_bricks_are_a_pure_relayout(full):
             assert torch.equal(outs[0.0][k], outs[gb][k]), f"{k}: bricks ({gb} GB -> {levels[gb]} levels) change the result"
 
 
+def test_fp16_rows_and_march_first_are_the_same_frame(full):
+    """snrf_set_feature_dtype(fp16): the rows are the fp32 rows rounded once to fp16, bit for bit (TMA-fed output layer
+    with the fp16 epilogue); snrf_set_march_first: one march launch over the tile + feature chunks == alternating chunks."""
+    cfg, r = full
+    o, d = test_rays(7001, seed=12)  # ragged: 7 chunks of 1024 less a few rays
+    o, d = o.cuda(), d.cuda()
+    base = r.render_frame(o, d, get_feature=("sam",), chunk=1024)
+    try:
+        r.set_march_first(True)
+        mf = r.render_frame(o, d, get_feature=("sam",), chunk=1024)
+        r.set_feature_dtype(torch.float16)
+        h = r.render_frame(o, d, get_feature=("sam",), chunk=1024)
+        hc = r.render(o[:515], d[:515], get_feature=("sam",))
+        torch.cuda.synchronize()
+    finally:
+        r.set_march_first(False)
+        r.set_feature_dtype(torch.float32)
+    for k in ("rgb", "depth", "accumulation", "prop_depth_0", "sam"):
+        assert torch.equal(torch.nan_to_num(base[k]), torch.nan_to_num(mf[k])), f"{k}: march-first changes the frame"
+    assert h["sam"].dtype == torch.float16 and hc["sam"].dtype == torch.float16
+    assert torch.equal(torch.nan_to_num(h["sam"]), torch.nan_to_num(base["sam"].half())), "fp16 rows != fp32 rows rounded once"
+    assert torch.equal(torch.nan_to_num(hc["sam"]), torch.nan_to_num(base["sam"][:515].half()))
+    assert torch.equal(h["rgb"], base["rgb"])
+
+
 def test_edge_cases(full):
     cfg, r = full
     o, d = test_rays(64, seed=4)

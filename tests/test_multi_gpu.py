@@ -28,20 +28,33 @@ o, d = test_rays(H * W, seed=3)
 names = {"rgb": 3, "depth": 1, "accumulation": 1, "prop_depth_0": 1, "sam": 256}
 single = r.render_frame(o.to(dev), d.to(dev), get_feature=("sam",), chunk=1024)      # whole frame on this GPU
 mode = os.environ["SNRF_GATHER"]
-big = symm_mem.empty(H * W * sum(names.values()), dtype=torch.float32, device=dev)
-big.fill_(-7.0)
+f16 = mode.endswith("_f16")          # fp16 feature rows (snrf_set_feature_dtype), exchanged and stored as such
+march_first = "_mf" in mode          # one march launch over the tile, then the feature chunks
+mode = mode.split("_")[0]
+if f16:
+    r.set_feature_dtype(torch.float16)
+    single = r.render_frame(o.to(dev), d.to(dev), get_feature=("sam",), chunk=1024)
+    ref32 = r.feature_dtype
+esz = {k: (2 if (f16 and k == "sam") else 4) for k in names}
+offs, tot = {}, 0
+for k, c in names.items():
+    offs[k] = tot
+    tot += (H * W * c * esz[k] + 255) // 256 * 256
+big = symm_mem.empty(tot, dtype=torch.uint8, device=dev)
+big.fill_(0x5A)
 hdl = symm_mem.rendezvous(big, dist.group.WORLD.group_name)
 mc = int(hdl.multicast_ptr or 0) if mode == "mc" else 0
-if mode == "dma":
-    r.set_replication_mode("dma")
+if mode in ("dma", "push"):
+    r.set_replication_mode(mode)
+r.set_march_first(march_first)
 if mode == "mc" and not mc:
     print("SKIP no multicast"); dist.destroy_process_group(); sys.exit(0)
-full, off = {}, 0
+full = {}
 for k, c in names.items():
-    full[k] = big[off:off + H * W * c].view(H * W, c)
-    peers = [int(hdl.buffer_ptrs[p]) + off * 4 for p in range(world) if p != rank]
-    r.set_replication(k, full[k], () if mc else peers, mc + off * 4 if mc else 0)
-    off += H * W * c
+    dt = torch.float16 if esz[k] == 2 else torch.float32
+    full[k] = big[offs[k]:offs[k] + H * W * c * esz[k]].view(dt).view(H * W, c)
+    peers = [int(hdl.buffer_ptrs[p]) + offs[k] for p in range(world) if p != rank]
+    r.set_replication(k, full[k], () if mc else peers, mc + offs[k] if mc else 0)
 lo, hi = ray_block(rank, world, H, W)
 hdl.barrier()
 r.render_frame(o[lo:hi].to(dev), d[lo:hi].to(dev), get_feature=("sam",), chunk=1024, out={k: v[lo:hi] for k, v in full.items()})
@@ -54,7 +67,7 @@ dist.destroy_process_group()
 '''
 
 
-@pytest.mark.parametrize("mode", ["peer", "mc", "dma"])
+@pytest.mark.parametrize("mode", ["peer", "mc", "dma", "push", "dma_f16", "push_mf_f16"])
 def test_fused_tile_all_gather(mode, tmp_path):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
