@@ -333,7 +333,7 @@ def run_native(args):
     fdt = torch.float16 if args.feature_dtype == "f16" else torch.float32
     r.set_feature_dtype(fdt)
     if args.march_first == -1:
-        args.march_first = 1 if world > 2 else 0
+        args.march_first = 0  # measured: equal at N = 8 (514 vs 513 Mrays/s), worse at N = 4 (310 vs 326)
     r.set_march_first(bool(args.march_first))
     o_all, d_all = frame_rays(conf)
     n_all = o_all.shape[0]
@@ -363,7 +363,8 @@ def run_native(args):
     # chunk's compute; a symmetric-memory barrier ends the frame.  Fallback / comparison: NCCL all-gather (--gather nccl).
     gather_mode, symm, full = "single", None, {}
     if args.gather == "auto":
-        args.gather = "dma"
+        # measured on 8 B200 (profiles/r02_multi_gpu.txt): push kernel 514 Mrays/s, copy engines 466, NCCL 306
+        args.gather = "push"
     if world > 1:
         gather_mode = "nccl"
         if args.gather != "nccl":
@@ -610,11 +611,11 @@ def main():
     ap.add_argument("--regime", choices=["scene", "init"], default="scene")
     ap.add_argument("--engine", choices=["tcgen05", "mma_sync"], default="tcgen05")
     ap.add_argument("--gather", choices=["auto", "mc", "peer", "dma", "push", "nccl"], default="auto",
-                    help="N > 1: how the tiles are exchanged (auto = copy engines; push kernel; fused multicast / peer stores; NCCL)")
+                    help="N > 1: how the tiles are exchanged (auto = push kernel; copy engines; fused multicast / peer stores; NCCL)")
     ap.add_argument("--feature-dtype", choices=["auto", "f32", "f16"], default="auto",
                     help="element type of the 256-d feature rows: auto = f32 on one GPU, f16 with N > 1 (wire and storage)")
     ap.add_argument("--march-first", type=int, default=-1, choices=[-1, 0, 1],
-                    help="frame = one march launch over the tile, then the feature chunks (-1 = auto: on for N > 2)")
+                    help="frame = one march launch over the tile, then the feature chunks (-1 = auto: off)")
     ap.add_argument("--chunk", type=int, default=0, help="rays per launch (default: 131072 on one GPU, finer with N > 1)")
     ap.add_argument("--pipeline", type=int, default=1, choices=[0, 1, 2],
                     help="chunk pipelining over 3 streams: 0 off, 1 auto (only with replicated outputs, N > 1), 2 always")

@@ -158,33 +158,56 @@ class NearFarCollider:
 # ------------------------------------------------------------------------------------------------
 # fields
 # ------------------------------------------------------------------------------------------------
-class _Field:
+class _TcnnParams(torch.nn.Module):
+    """Parameter holder standing in for a tinycudann module (``tcnn.Encoding`` / ``tcnn.Network`` /
+    ``tcnn.NetworkWithInputEncoding``): ONE flat fp32 ``params`` tensor - network weights first, then the grid - which
+    is all such a module contributes to a ``state_dict`` (sam_field.py:51-109, nerfacto_field.py:144-175,228-240,
+    density_fields.py:92-100).  The arithmetic lives in libsnrf, which keeps its own packed fp16 copy."""
+
+    def __init__(self, n: int, device=None):
+        super().__init__()
+        self.params = torch.nn.Parameter(torch.zeros(int(n), device=device))
+
+
+_AABB = ((-1.0, -1.0, -1.0), (1.0, 1.0, 1.0))  # scene box of the nerfstudio dataparsers (scene_box.py)
+
+
+class _Field(torch.nn.Module):
+    """Common part of the field shims: ``nn.Module``s whose parameters / buffers carry the reference's names, so that
+    ``state_dict()`` / ``load_state_dict(strict=True)`` interoperate with the reference's checkpoints."""
+
     def __init__(self, renderer: Renderer):
+        super().__init__()
         self.renderer = renderer
 
-    #: set by SAMModel: callable returning the dict of trainable flat parameters while the model is in training
-    #: mode (else None) - the hook through which the component shims become differentiable
-    trainable: Optional[Callable] = None
+    def _grid_buffers(self, g) -> None:
+        """The geometry the reference's fields register as buffers (nerfacto_field.py:121-125, density_fields.py:66-71)."""
+        dev = self.renderer.device if self.renderer is not None else None
+        self.register_buffer("aabb", torch.tensor(_AABB, device=dev))
+        self.register_buffer("max_res", torch.tensor(g.max_resolution, device=dev))
+        self.register_buffer("num_levels", torch.tensor(g.n_levels, device=dev))
+        self.register_buffer("log2_hashmap_size", torch.tensor(g.log2_hashmap_size, device=dev))
 
-    def _params(self):
-        p = self.trainable() if self.trainable is not None else None
-        return p if p and torch.is_grad_enabled() else None
+    def _differentiable(self) -> bool:
+        return self.training and torch.is_grad_enabled()
 
     def density_fn(self, positions: torch.Tensor) -> torch.Tensor:
         """base_field.py:38-56."""
         return self._density(positions)[0]
 
-    def __call__(self, ray_samples: RaySamples, compute_normals: bool = False):
-        return self.forward(ray_samples, compute_normals)
-
 
 class HashMLPDensityField(_Field):
     """density_fields.py:39-125 (the proposal network)."""
 
+    def __init__(self, renderer: Renderer, cfg: Optional[SAMNeRFConfig] = None):
+        super().__init__(renderer)
+        cfg = cfg or renderer.cfg
+        self.mlp_base = _TcnnParams(cfg.proposal_mlp_params + cfg.proposal_grid.n_params, renderer.device)
+        self._grid_buffers(cfg.proposal_grid)
+
     def _density(self, positions):
-        p = self._params()
-        if p and "proposal_networks.0.mlp_base.params" in p:
-            return _ProposalDensityFn.apply(p["proposal_networks.0.mlp_base.params"], self.renderer, positions.detach()), None
+        if self._differentiable():
+            return _ProposalDensityFn.apply(self.mlp_base.params, self.renderer, positions.detach()), None
         return self.renderer.query_density("proposal", positions)
 
     def get_density(self, ray_samples: RaySamples):
@@ -201,6 +224,17 @@ class HashMLPDensityField(_Field):
 class TCNNNerfactoField(_Field):
     """nerfacto_field.py:67-351 with appearance embedding off (samconfigs.py:80,134)."""
 
+    def __init__(self, renderer: Renderer, cfg: Optional[SAMNeRFConfig] = None):
+        super().__init__(renderer)
+        cfg = cfg or renderer.cfg
+        dev = renderer.device
+        self.mlp_base = _TcnnParams(cfg.field_mlp_params + cfg.field_grid.n_params, dev)
+        self.mlp_head = _TcnnParams(cfg.head_mlp_params, dev)
+        # parameter-free tcnn encodings: they still show up in the reference's state_dict, as empty tensors
+        self.direction_encoding = _TcnnParams(0, dev)
+        self.position_encoding = _TcnnParams(0, dev)
+        self._grid_buffers(cfg.field_grid)
+
     def _density(self, positions):
         return self.renderer.query_density("field", positions)
 
@@ -215,12 +249,11 @@ class TCNNNerfactoField(_Field):
         return {FieldHeadNames.RGB: rgb}
 
     def forward(self, ray_samples: RaySamples, compute_normals: bool = False):
-        p = self._params()
-        if p and "field.mlp_base.params" in p:
+        if self._differentiable():
             # training: density and colour in one differentiable call (tinycudann's autograd in the reference)
             if ray_samples.camera_indices is None:
                 raise AttributeError("Camera indices are not provided.")  # nerfacto_field.py:273-275
-            density, rgb = _NerfactoFieldFn.apply(p["field.mlp_base.params"], p["field.mlp_head.params"], self.renderer,
+            density, rgb = _NerfactoFieldFn.apply(self.mlp_base.params, self.mlp_head.params, self.renderer,
                                                   ray_samples.frustums.get_positions().detach(),
                                                   ray_samples.frustums.directions.detach())
             return {FieldHeadNames.RGB: rgb, FieldHeadNames.DENSITY: density}
@@ -231,7 +264,29 @@ class TCNNNerfactoField(_Field):
 
 
 class SAMField(_Field):
-    """sam_field.py:25-140.  ``get_feautre`` keeps the reference's spelling of the keyword."""
+    """sam_field.py:25-140.  Constructor arguments in the reference's order (sam_field.py:26-35); ``renderer`` is the one
+    addition.  ``get_feautre`` keeps the reference's spelling of the keyword."""
+
+    def __init__(self, grid_layers, grid_sizes, grid_resolutions, hidden_layers=2, spatial_distortion=None,
+                 use_dino_features: bool = False, use_clipseg_features: bool = False, renderer: Optional[Renderer] = None):
+        super().__init__(renderer)
+        assert len(grid_layers) == len(grid_sizes) and len(grid_resolutions) == len(grid_layers)  # sam_field.py:37
+        if renderer is None:
+            raise RuntimeError("SAMField needs renderer=Renderer(...): the arithmetic lives in libsnrf (no PyTorch fallback)")
+        if hidden_layers != 1 or use_dino_features:
+            raise ValueError("libsnrf builds the shipped configuration: hidden_layers = 1, no DINO head (samconfigs.py:81-83)")
+        from .config import GridConfig
+
+        self.spatial_distortion = spatial_distortion  # L2 scene contraction inside the kernels (sam_field.py:32)
+        self.use_dino_features, self.use_clipseg_features = use_dino_features, use_clipseg_features
+        dev = renderer.device
+        grids = [GridConfig(int(l), 8, int(t), int(r[0]), int(r[1])) for l, t, r in zip(grid_layers, grid_sizes, grid_resolutions)]
+        width = sum(g.n_levels * g.n_features for g in grids)
+        self.clip_encs = torch.nn.ModuleList([_TcnnParams(g.n_params, dev) for g in grids])
+        self.sam_net = _TcnnParams(256 * width + 256 * 256, dev)
+        if use_clipseg_features:
+            self.clipseg_encs = torch.nn.ModuleList([_TcnnParams(g.n_params, dev) for g in grids])
+            self.clipseg_net = _TcnnParams(256 * width + 192 * 256, dev)
 
     def get_outputs(self, ray_samples: RaySamples, get_feautre=("sam", "dino", "clipseg")):
         pos = ray_samples.frustums.get_positions().detach()
@@ -241,6 +296,9 @@ class SAMField(_Field):
         if "clipseg" in get_feautre and self.renderer.cfg.use_clipseg_feature:
             _, out["clipseg"] = self.renderer.query_features("clipseg", pos)
         return out
+
+    def forward(self, ray_samples: RaySamples, get_feautre=("sam", "dino", "clipseg")):
+        return self.get_outputs(ray_samples, get_feautre=get_feautre)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -525,46 +583,88 @@ class _FeatureBranchFn(torch.autograd.Function):
 # ------------------------------------------------------------------------------------------------
 # the model
 # ------------------------------------------------------------------------------------------------
-class SAMModel:
-    """samnerf/sam_model.py:179-418, inference side.
+class SAMModel(torch.nn.Module):
+    """samnerf/sam_model.py:179-418, inference side (+ the training shim of SURVEY 8 f-1).
+
+    An ``nn.Module`` whose parameter tree is the reference's (``SAMModel(NerfactoModel)``, sam_model.py:179-224;
+    nerfacto.py:149-225): ``proposal_networks.0.mlp_base.params``, ``field.mlp_base.params``, ``field.mlp_head.params``,
+    ``sam_field.{clip_encs.i,sam_net,clipseg_encs.i,clipseg_net}.params``, ``conv_head.{0,2}.{weight,bias}`` plus the
+    geometry buffers - so ``state_dict()`` / ``load_state_dict(strict=True)`` exchange checkpoints with the reference
+    (tests/golden/state_dict_layout.json holds the reference modules' own key list).  The tensors are fp32 masters on the
+    device; libsnrf keeps packed fp16 copies that are re-uploaded whenever a master's version counter moves.
 
     ``get_outputs`` / ``forward`` run one fused ``snrf_render`` call per chunk; the component objects
     (``proposal_sampler``, ``field``, ``sam_field``, renderers) expose the same pieces individually.
     Prompt lifting / projection (sam_model.py:426-475) is done here as in the reference; the 2-D mask decoders that
     consume the prompts and the rendered feature map (sam_model.py:485-548) are out of scope.
-    """
+    Constructed in eval mode (a bare ``nn.Module`` starts in training mode; the reference's pipelines call ``eval()`` /
+    ``train()`` explicitly, and so may callers of this class)."""
 
     def __init__(self, config: SAMNeRFConfig, device: int = 0, engine: str = "tcgen05"):
+        super().__init__()
         self.config = config
         self.renderer = Renderer(config, device=device, engine=engine)
-        self.training = False
         r = self.renderer
         self.collider = NearFarCollider(near_plane=0.05, far_plane=config.far_plane)
-        self.proposal_networks = [HashMLPDensityField(r)]
+        self.proposal_networks = torch.nn.ModuleList([HashMLPDensityField(r, config)])
         self.density_fns = [n.density_fn for n in self.proposal_networks]
         from .training import proposal_update_schedule
 
         self.proposal_sampler = ProposalNetworkSampler(
             r, update_sched=proposal_update_schedule(config.proposal_warmup, config.proposal_update_every))
-        self.field = TCNNNerfactoField(r)
-        self.sam_field = SAMField(r) if config.distill_sam else None
+        self.field = TCNNNerfactoField(r, config)
+        if config.distill_sam:
+            gs = config.sam_grids
+            self.sam_field = SAMField(
+                tuple(g.n_levels for g in gs), tuple(g.log2_hashmap_size for g in gs),
+                tuple((g.base_resolution, g.max_resolution) for g in gs), hidden_layers=1,
+                use_dino_features=False, use_clipseg_features=config.use_clipseg_feature, renderer=r)
+            k = config.kernel_size  # sam_model.py:202-208: parameter holders; the convolutions run in libsnrf
+            self.conv_head = torch.nn.Sequential(
+                torch.nn.Conv2d(256, 256, k, stride=1, padding=(k - 1) // 2), torch.nn.ReLU(inplace=True),
+                torch.nn.Conv2d(256, 256, k, stride=1, padding=(k - 1) // 2)).to(r.device)
+        else:
+            self.sam_field = None
         self.renderer_rgb = RGBRenderer(r, background_color="last_sample")
         self.renderer_accumulation = AccumulationRenderer(r)
         self.renderer_depth = DepthRenderer(r)
         self.renderer_mean = MeanRenderer(r)
-        self.params: Dict[str, torch.nn.Parameter] = {}
-        hook = lambda: self.params if self.training else None  # noqa: E731
-        for f in (self.proposal_networks[0], self.field):
-            f.trainable = hook
+        self.prompts = None
+        self._uploaded: Dict[str, int] = {name: p._version for name, p in self.params.items()}
+        self.train(False)
+
+    @property
+    def params(self) -> Dict[str, torch.nn.Parameter]:
+        """The hot-path parameters under the reference's names (the empty tcnn encodings are left out; the conv head
+        only when the patch head is in use, as before)."""
+        from .checkpoint import HOT_PATH_KEYS
+
+        use_conv = self.config.distill_sam and self.config.patch_size > 1
+        return {n: p for n, p in self.named_parameters()
+                if n in HOT_PATH_KEYS and p.numel() > 0 and (use_conv or not n.startswith("conv_head."))}
 
     def load_state_dict(self, state_dict: Dict[str, torch.Tensor], strict: bool = False):
         """Accepts the reference's pipeline keys (with or without the ``module.`` / ``_model.`` prefixes,
-        base_pipeline.py:109-115,366-375); tensors off the hot path are ignored."""
-        from .checkpoint import params_from_state_dict
+        base_pipeline.py:109-115,366-375).  ``strict=True`` is ``nn.Module``'s own check against this model's key set -
+        what the reference's trainer enforces; the default ignores tensors off the hot path (camera optimiser, ...)."""
+        from .checkpoint import params_from_state_dict, strip_prefixes
 
-        self._loaded = params_from_state_dict(state_dict)
-        self.renderer.load_params(self._loaded)
-        self.params = {}  # trainable copies are (re)built by train()
+        params_from_state_dict(state_dict)  # raises KeyError when a required hot-path tensor is missing
+        own = super().state_dict()
+        mapped = {}
+        for k, v in state_dict.items():
+            name = strip_prefixes(k)
+            if name in own and torch.is_tensor(v):
+                v = v.detach()
+                mapped[name] = v.reshape(own[name].shape) if v.numel() == own[name].numel() else v
+            elif strict:
+                mapped[name] = v
+        if not strict:  # tensors this configuration does not use (e.g. an unused conv head) keep their initial values
+            mapped = {k: v for k, v in mapped.items() if k in own}
+        res = super().load_state_dict(mapped, strict=strict)
+        self.renderer.load_params({n: p.detach() for n, p in self.named_parameters() if p.numel() > 0 and n in mapped})
+        self._uploaded = {name: p._version for name, p in self.params.items()}
+        return res
 
     @classmethod
     def from_checkpoint(cls, path: str, device: int = 0, engine: str = "tcgen05", base: Optional[SAMNeRFConfig] = None):
@@ -580,42 +680,22 @@ class SAMModel:
 
     # ---- training -------------------------------------------------------------------
     def train(self, mode: bool = True):
-        """Training mode: every flat hot-path tensor becomes an fp32 ``nn.Parameter`` on the device whose gradient
-        comes from libsnrf's backward kernels (``snrf_field_backward``, ``snrf_feature_backward``,
-        ``snrf_patch_aggregate_backward``, ``snrf_ray_op_backward``).
+        """Training mode: the gradients of the flat fp32 parameters come from libsnrf's backward kernels
+        (``snrf_field_backward``, ``snrf_feature_backward``, ``snrf_patch_aggregate_backward``, ``snrf_ray_op_backward``).
         The collider switches to its training near plane (scene_colliders.py:185) and the sampler to stratified
-        single-jitter sampling (ray_samplers.py:104-112,314-322)."""
-        self.training = bool(mode)
-        self.collider.training = self.training
-        self.proposal_sampler.training = self.training
-        if not self.training:
-            self._sync_params()
-            return self
-        loaded = getattr(self, "_loaded", None)
-        if loaded is None:
-            raise RuntimeError("load_state_dict() before train(): the fp32 master copies come from there")
-        dev = self.renderer.device
-        if not getattr(self, "params", None):
-            self.params, self._uploaded = {}, {}
-            names = list(Renderer.DENSITY_PARAMS)
-            if self.config.distill_sam:
-                names += [n for which in ("sam", "clipseg") for n in Renderer.FEATURE_PARAMS[which]]
-            for name in names:
-                if name in loaded:
-                    self.params[name] = torch.nn.Parameter(loaded[name].to(dev, torch.float32).reshape(-1).clone())
-                    self._uploaded[name] = self.params[name]._version
-            if self.config.distill_sam and self.config.patch_size > 1 and "conv_head.0.weight" in loaded:
-                for name in Renderer.CONV_PARAMS:
-                    self.params[name] = torch.nn.Parameter(loaded[name].to(dev, torch.float32).clone())
-                    self._uploaded[name] = self.params[name]._version
+        single-jitter sampling (ray_samplers.py:104-112,314-322).  Leaving training mode pushes every parameter an
+        optimiser has changed into the library's packed copies."""
+        super().train(mode)
+        if hasattr(self, "collider"):
+            self.collider.training = bool(mode)
+            self.proposal_sampler.training = bool(mode)
+            if not mode and hasattr(self, "_uploaded"):
+                self._sync_params()
         return self
-
-    def eval(self):
-        return self.train(False)
 
     def get_param_groups(self) -> Dict[str, List[torch.nn.Parameter]]:
         """nerfacto.py:236-240 + sam_model.py:330-335."""
-        p = getattr(self, "params", {})
+        p = self.params
         groups = {
             "proposal_networks": [v for k, v in p.items() if k.startswith("proposal_networks.")],
             "fields": [v for k, v in p.items() if k.startswith("field.")],
@@ -626,13 +706,6 @@ class SAMModel:
             if conv:
                 groups["conv"] = conv
         return groups
-
-    def state_dict(self) -> Dict[str, torch.Tensor]:
-        """Hot-path tensors under the reference's names (trained values where training has happened)."""
-        sd = dict(getattr(self, "_loaded", {}))
-        for name, p in getattr(self, "params", {}).items():
-            sd[name] = p.detach().cpu().clone()
-        return sd
 
     # nerfacto.py:316-344 + sam_model.py:316-328
     def get_metrics_dict(self, outputs, batch) -> Dict[str, torch.Tensor]:
@@ -670,7 +743,7 @@ class SAMModel:
         world = dist.get_world_size(group)
         if world == 1:
             return
-        for p in getattr(self, "params", {}).values():
+        for p in self.params.values():
             if p.grad is not None:
                 dist.all_reduce(p.grad, op=dist.ReduceOp.SUM, group=group)
                 p.grad.div_(world)
@@ -690,8 +763,9 @@ class SAMModel:
         """Push parameters an optimiser step has changed (tensor version counters) back into the library's packed
         fp16 copies - the re-upload SURVEY 8 b asks for."""
         r = self.renderer
+        params = self.params
         for name in Renderer.DENSITY_PARAMS:
-            p = getattr(self, "params", {}).get(name)
+            p = params.get(name)
             if p is not None and p._version != self._uploaded[name]:
                 r.upload_density_params(name, p)
                 self._uploaded[name] = p._version
@@ -699,13 +773,13 @@ class SAMModel:
             names = Renderer.FEATURE_PARAMS[which]
             changed = {}
             for slot, name in zip(("net", "grid0", "grid1"), names):
-                p = getattr(self, "params", {}).get(name)
+                p = params.get(name)
                 if p is not None and p._version != self._uploaded[name]:
                     changed[slot] = p
                     self._uploaded[name] = p._version
             if changed:
                 r.upload_feature_params(which, **changed)
-        conv = [getattr(self, "params", {}).get(n) for n in Renderer.CONV_PARAMS]
+        conv = [params.get(n) for n in Renderer.CONV_PARAMS]
         if conv[0] is not None and any(p._version != self._uploaded[n] for p, n in zip(conv, Renderer.CONV_PARAMS)):
             r.upload_conv_head(*conv)
             for p, n in zip(conv, Renderer.CONV_PARAMS):
@@ -731,7 +805,8 @@ class SAMModel:
                 out["accumulation"] = self.renderer_accumulation(weights=weights)
                 out["prop_depth_0"] = self.renderer_depth(weights=weights_list[0], ray_samples=ray_samples_list[0])
         out["weights_list"], out["ray_samples_list"] = weights_list, ray_samples_list
-        feats = [f for f in get_feature if Renderer.FEATURE_PARAMS[f][0] in self.params]
+        params = self.params
+        feats = [f for f in get_feature if Renderer.FEATURE_PARAMS[f][0] in params]
         if feats:
             # top-k + sharpen on the (detached) weights of this very pass (sam_model.py:244-255)
             sam_t, sam_w = r.pick_samples(weights, ray_samples.frustums.starts, ray_samples.frustums.ends)
@@ -739,9 +814,9 @@ class SAMModel:
             d = r._prep(ray_bundle.directions, 3)
             for which in feats:
                 names = Renderer.FEATURE_PARAMS[which]
-                feat = _FeatureBranchFn.apply(*[self.params[n] for n in names], r, which, o, d, sam_t, sam_w)
+                feat = _FeatureBranchFn.apply(*[params[n] for n in names], r, which, o, d, sam_t, sam_w)
                 if which == "sam" and cfg.patch_size > 1:  # sam_model.py:260-265
-                    feat = _PatchAggregateFn.apply(feat, *[self.params[n] for n in Renderer.CONV_PARAMS], r)
+                    feat = _PatchAggregateFn.apply(feat, *[params[n] for n in Renderer.CONV_PARAMS], r)
                 out[which] = feat
         return out
 
@@ -750,8 +825,6 @@ class SAMModel:
         if self.collider is not None:
             ray_bundle = self.collider(ray_bundle)
         return self.get_outputs(ray_bundle, **kwargs)
-
-    __call__ = forward
 
     # sam_model.py:226-278
     def get_outputs(self, ray_bundle: RayBundle, get_rgbsigma=True, get_feature=("sam", "dino", "clipseg"), fast=False):
