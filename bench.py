@@ -319,7 +319,7 @@ def run_native(args):
     params = make_synthetic_params(cfg, args.regime, 0)
     r = Renderer(cfg, device=local, engine=args.engine)
     r.load_params(params)
-    brick_gb = args.brick_gb if args.brick_gb >= 0 else 4.0
+    brick_gb = args.brick_gb if args.brick_gb >= 0 else 10.0
     brick_levels = r.set_brick_budget(brick_gb)
     if args.early_termination > 0:
         r.set_early_termination(args.early_termination)  # opt-in, not the reference's exact arithmetic: see config
@@ -627,8 +627,8 @@ def main():
                          ">= this (library default 2^-24 = below one fp32 ulp of the sum; 0 = drop exact zeros); "
                          "< 0 = every sample of every ray through the un-bucketed kernel")
     ap.add_argument("--brick-gb", type=float, default=-1.0,
-                    help="HBM budget (GiB) for the cell-major brick copies of the leading grid levels (library default 4; "
-                         "0 = off; a pure re-layout, results are bit-identical)")
+                    help="HBM budget (GiB) for the cell-major brick copies of the leading grid levels (bench default 10 = 12 of "
+                         "the 16 nerfacto levels, 9.3 GB; library default 4; 0 = off; a pure re-layout, results are bit-identical)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
