@@ -909,11 +909,14 @@ class SAMModel(torch.nn.Module):
             outputs["prompt_points"] = P.prompts_in_image(self.prompts, intrin, c2w, w, h)
 
     @torch.no_grad()
-    def get_outputs_for_camera(self, camera: Camera, fast: bool = False) -> Dict[str, torch.Tensor]:
+    def get_outputs_for_camera(self, camera: Camera, points=None, fast: bool = False) -> Dict[str, torch.Tensor]:
         """``get_outputs_for_camera_ray_bundle(cameras.generate_rays(i, keep_shape=True))`` without the ray bundle
         (SURVEY.md 8 f-2): the three loops of sam_model.py:354-406 each become one ``snrf_render_camera`` call that
         generates its rays on the device - LOOP A every pixel, LOOP B the ``fh*p x fw*p`` strided sub-grid in
-        patch-major order through the conv head, LOOP C the 32 x 32 ClipSeg grid."""
+        patch-major order through the conv head, LOOP C the 32 x 32 ClipSeg grid.  ``points`` are the viewer's clicks
+        (pixel ``[x, y]`` rows, as for ``get_outputs_for_camera_ray_bundle``); the intrinsics and pose the prompt
+        bookkeeping needs come from the camera itself.  ``points=None`` leaves remembered prompts alone (the viewer
+        interleaves both calls), an empty list clears them as in the reference."""
         cfg, r = self.config, self.renderer
         h, w = camera.height, camera.width
         outputs = {k: v.view(h, w, -1) for k, v in r.render_camera(camera, get_feature=(), fast=fast).items()}
@@ -927,5 +930,9 @@ class SAMModel(torch.nn.Module):
                 hi = torch.linspace(0, h - 1, 32, dtype=torch.long)
                 wi = torch.linspace(0, w - 1, 32, dtype=torch.long)
                 outputs["clipseg"] = r.render_camera(camera, rows=hi, cols=wi, get_feature=("clipseg",))["clipseg"].view(32, 32, -1)
-        self._handle_prompts(outputs, None, None, None)
+        if points is None:  # keep what get_outputs_for_camera_ray_bundle has remembered; re-project it into this view
+            points = [[0, 0]] * int(self.prompts.shape[0]) if getattr(self, "prompts", None) is not None else None
+        intrin = torch.tensor([[camera.fx, 0.0, camera.cx], [0.0, camera.fy, camera.cy], [0.0, 0.0, 1.0]])
+        self._handle_prompts(outputs, points, intrin if points is not None else None,
+                             camera.camera_to_world if points is not None else None)
         return outputs

@@ -193,6 +193,19 @@ def test_gpu_model_from_camera_equals_model_from_ray_bundle():
     assert set(got) == set(want)
     for k in want:
         assert torch.equal(got[k], want[k]), k
+    # clicks: both entry points lift / remember / re-project the same prompts, and the camera path neither drops what the
+    # ray-bundle path remembered nor needs the caller to hand it intrinsics (they are the camera's)
+    intrin = torch.tensor([[32.0, 0.0, 16.0], [0.0, 32.0, 12.0], [0.0, 0.0, 1.0]])
+    clicks = [[10, 8], [20, 15]]
+    a = m.get_outputs_for_camera_ray_bundle(bundle, points=clicks, intrin=intrin, c2w=cam.camera_to_world)
+    remembered = m.prompts.clone()
+    b = m.get_outputs_for_camera(cam)              # interleaved frame without new clicks: prompts stay
+    assert torch.equal(m.prompts, remembered) and torch.equal(b["prompt_points"], a["prompt_points"])
+    m.prompts = None
+    c = m.get_outputs_for_camera(cam, points=clicks)
+    assert torch.allclose(m.prompts, remembered) and torch.equal(c["prompt_points"], a["prompt_points"])
+    m.get_outputs_for_camera(cam, points=[])       # an empty click list clears them, as in the reference
+    assert m.prompts is None
 
 
 @pytest.mark.gpu
