@@ -72,6 +72,12 @@ struct snrf_ctx {
   DevBuf prop_brick_store, field_brick_store;
   BrickDev prop_bricks = {}, field_bricks = {};
   bool march_v1 = false;  // SNRF_MARCH=v1: the round-1 march kernel (A/B measurements only)
+  // Two alternative structures of the march kernel, both parity-green on hardware and both measured SLOWER than the fused
+  // mma.sync kernel on the headline frame (gpurun calls 14 / 15: 4.09 ms fused, 4.47 tcgen05 MLPs, 4.38 split), kept as
+  // opt-in variants for A/B measurements: SNRF_MARCH_TC=1, SNRF_MARCH_SPLIT=1 (see the notes in march.cu).
+  bool march_tc = false;
+  bool march_split = false;
+  DevBuf edges;             // [N,33] bin edges between the two halves
   float et_eps = 0.f;  // snrf_set_early_termination
   // snrf_set_feature_cutoff: >= 0 = bucketed kernel B' (default 2^-24: slots below one fp32 ulp of the ray's weight sum
   // are not evaluated), < 0 = kernel B on every slot
@@ -86,7 +92,7 @@ struct snrf_ctx {
   GridDev prop_grid;
   bool have_prop = false;
   // nerfacto field
-  DevBuf field_table, base_w1_rm, base_w2_rm, head_w1_rm, head_w2_rm, head_w3_rm, wfrag, head_perm;
+  DevBuf field_table, base_w1_rm, base_w2_rm, head_w1_rm, head_w2_rm, head_w3_rm, wfrag, head_perm, wcore;
   GridDev field_grid;
   bool have_base = false, have_head = false;
   // feature nets: 0 = sam, 1 = clipseg
@@ -314,6 +320,8 @@ int snrf_ctx_create(int device, snrf_ctx** out) {
   ctx->device = device;
   ctx->sm_count = prop.multiProcessorCount;
   if (const char* e = getenv("SNRF_MARCH")) ctx->march_v1 = strcmp(e, "v1") == 0;
+  if (const char* e = getenv("SNRF_MARCH_TC")) ctx->march_tc = atoi(e) != 0;
+  if (const char* e = getenv("SNRF_MARCH_SPLIT")) ctx->march_split = atoi(e) != 0;
   if (const char* e = getenv("SNRF_BRICK_GB")) ctx->brick_budget = static_cast<int64_t>(atof(e) * (1ll << 30));
   if (prop.major != 10) {
     // this library is compiled for sm_100a only; refuse loudly instead of failing at the first launch
@@ -351,7 +359,7 @@ void snrf_ctx_destroy(snrf_ctx* ctx) {
                     &ctx->q_h1,       &ctx->q_h2,       &ctx->q_sel,      &ctx->q_x,        &ctx->conv_w[0],
                     &ctx->conv_w[1],  &ctx->conv_b[0],  &ctx->conv_b[1]};
   for (DevBuf* b : bufs) b->release();
-  ctx->sam_t[1].release(); ctx->sam_w[1].release();
+  ctx->sam_t[1].release(); ctx->sam_w[1].release(); ctx->wcore.release(); ctx->edges.release();
   ctx->cam_rows.release(); ctx->cam_cols.release(); ctx->cam_o.release(); ctx->cam_d.release();
   ctx->cam_near.release(); ctx->cam_far.release();
   ctx->conv_w_rm[0].release(); ctx->conv_w_rm[1].release();
@@ -575,6 +583,10 @@ int snrf_upload_field_base(snrf_ctx* ctx, const float* params, int64_t n, const 
   uint2* wf = ctx->wfrag.as<uint2>();
   LAUNCH(launch_pack_frag(src, 32, nullptr, wf + kFragBase1 * 32, 8, 2, s));
   LAUNCH(launch_pack_frag(src + 64 * 32, 64, nullptr, wf + kFragBase2 * 32, 2, 4, s));
+  // the same two layers as tcgen05 B operands (march_kernel<.., TC>; byte plan in march.cu)
+  CK(ctx->wcore.ensure(kMarchCoreBytes));
+  LAUNCH(launch_pack_core(src, ctx->wcore.as<__half>(), 64, 32, s));
+  LAUNCH(launch_pack_core(src + 64 * 32, ctx->wcore.as<__half>() + 64 * 32, 16, 64, s));
   CK(cudaStreamSynchronize(s));
   tmp.release();
   ctx->field_grid = to_dev(grid, ctx->field_table.as<__half>());
@@ -610,6 +622,11 @@ int snrf_upload_field_head(snrf_ctx* ctx, const float* params, int64_t n, void* 
   LAUNCH(launch_pack_frag(src, 32, ctx->head_perm.as<int>(), wf + kFragHead1 * 32, 8, 2, s));
   LAUNCH(launch_pack_frag(src + 64 * 32, 64, nullptr, wf + kFragHead2 * 32, 8, 4, s));
   LAUNCH(launch_pack_frag(src + 64 * 32 + 64 * 64, 64, nullptr, wf + kFragHead3 * 32, 1, 4, s));
+  CK(ctx->wcore.ensure(kMarchCoreBytes));
+  __half* wc = ctx->wcore.as<__half>() + 64 * 32 + 16 * 64;
+  LAUNCH(launch_pack_core(src, wc, 64, 32, s, ctx->head_perm.as<int>()));
+  LAUNCH(launch_pack_core(src + 64 * 32, wc + 64 * 32, 64, 64, s));
+  LAUNCH(launch_pack_core(src + 64 * 32 + 64 * 64, wc + 64 * 32 + 64 * 64, 16, 64, s));
   CK(cudaStreamSynchronize(s));
   tmp.release();
   ctx->have_head = true;
@@ -721,6 +738,13 @@ static int fill_march(snrf_ctx* ctx, MarchParams& M, const float* origins, const
   M.prop_bricks = ctx->prop_bricks;
   M.field_bricks = ctx->field_bricks;
   M.wfrag = ctx->wfrag.as<uint2>();
+  M.wcore = ctx->have_base && ctx->have_head ? ctx->wcore.as<uint4>() : nullptr;
+  M.use_tc = ctx->march_tc ? 1 : 0;
+  if (ctx->march_split && !ctx->march_tc) {  // all march launches of a context are ordered on one stream: one buffer
+    CK(ctx->edges.ensure(static_cast<size_t>(n) * 33 * sizeof(float)));
+    M.edges = ctx->edges.as<float>();
+    M.split = 1;
+  }
   M.pdf_u = ctx->pdf_u.as<float>();
   M.hist_padding = o->hist_padding;
   M.bg_mode = o->bg_mode == SNRF_BG_FIXED ? kBgFixed : kBgLastSample;
@@ -879,7 +903,7 @@ static int render_chunk(snrf_ctx* ctx, const float* origins, const float* dirs, 
     if (ctx->feat_cutoff >= 0.f && ctx->engine == 1 && !S.dbg_feat) {
       // bucketed variant (sam_bucket.cu): pre-pass + one launch per bucket, all on the feature stream
       CK(ctx->bucket_lists[slot].ensure(static_cast<size_t>(kFeatBuckets) * n_rays * sizeof(int)));
-      CK(ctx->bucket_counts[slot].ensure(kFeatBuckets * sizeof(int)));
+      CK(ctx->bucket_counts[slot].ensure((kFeatBuckets + 1) * sizeof(int)));
       SamBucketParams Bk;
       memset(&Bk, 0, sizeof(Bk));
       Bk.origins = origins; Bk.dirs = dirs; Bk.sam_t = M.sam_t; Bk.sam_w = M.sam_w;

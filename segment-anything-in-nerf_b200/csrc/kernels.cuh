@@ -14,6 +14,8 @@ constexpr int kFragHead3 = 72;   // head MLP  64 -> 8  : 1 x 4   (only rgb = out
 constexpr int kFragProp1 = 76;   // proposal MLP 16 -> 16 : 2 x 1   (input columns 10..15 are tcnn's zero padding)
 constexpr int kFragProp2 = 78;   // proposal MLP 16 -> 8  : 1 x 1   (only output 0, the density, is used)
 constexpr int kMarchFragTiles = 79;
+// the five field layers once more in the core-matrix layout (tcgen05 B operands of march_kernel<.., TC>; plan in march.cu)
+constexpr uint32_t kMarchCoreBytes = (64 * 32 + 16 * 64 + 64 * 32 + 64 * 64 + 16 * 64) * 2;  // 20480
 
 constexpr uint32_t kFlagSamplesOnly = 1u;  // stop after the PDF resample (backs ProposalNetworkSampler)
 constexpr int kBgLastSample = 0;           // RGBRenderer background "last_sample" (renderers.py:102-103)
@@ -60,6 +62,10 @@ struct MarchParams {
   BrickDev prop_bricks;  // cell-major copies of the leading levels (n = 0: none)
   BrickDev field_bricks;
   const uint2* wfrag;    // kMarchFragTiles x 32 fragment words
+  const uint4* wcore;    // kMarchCoreBytes of core-matrix weights, or null: the mma.sync kernel is the only choice
+  int use_tc;            // run the field MLPs on tcgen05 (march_kernel<.., TC>) where an instantiation exists
+  float* edges;          // [N,33] scratch for the bin edges between the two halves of a split march, or null
+  int split;             // run the sampling half and the field half as two launches (needs `edges`)
   const float* pdf_u;    // [33] eval-mode PDF sample positions
   float hist_padding;
   int bg_mode;
@@ -113,7 +119,7 @@ struct SamBucketParams {
   const __half* w1;    // core-matrix layout, as SamParams
   __half* hbar;        // [N,256]
   const int* lists;    // [kFeatBuckets][n_rays] ray indices per bucket
-  const int* counts;   // [kFeatBuckets] entries per bucket (device memory, written by the pre-pass)
+  int* counts;         // [kFeatBuckets] entries per bucket (device memory, written by the pre-pass) + [1] tile counter
   int64_t n_rays;
 };
 // Pre-pass, one thread per ray: significant slots = 1 + index of the last slot whose weight is not below the
@@ -190,7 +196,7 @@ cudaError_t launch_half_to_float(const __half* in, int ld_in, float* out, int ld
 cudaError_t launch_ray_ops(int mode, const float* a, const float* b, const float* c, float* out, int64_t n, int S, int C,
                            int bg_mode, const float* bg, cudaStream_t stream);
 cudaError_t launch_f32_to_f16(const float* in, __half* out, int64_t n, cudaStream_t stream);
-cudaError_t launch_pack_core(const float* w, __half* out, int rows, int cols, cudaStream_t stream);
+cudaError_t launch_pack_core(const float* w, __half* out, int rows, int cols, cudaStream_t stream, const int* perm = nullptr);
 cudaError_t launch_pack_frag(const float* w, int k_w, const int* perm, uint2* out, int n_tiles, int k_steps,
                              cudaStream_t stream);
 cudaError_t launch_pack_prop(const float* w1, int k_w, const float* w2, float* o1, float* o2, cudaStream_t stream);

@@ -255,14 +255,15 @@ cudaError_t launch_f32_to_f16(const float* in, __half* out, int64_t n, cudaStrea
 }
 
 // row-major fp32 W[rows, cols] -> fp16 core-matrix layout (common.cuh::core_offset)
-__global__ void pack_core_kernel(const float* w, __half* out, int rows, int cols) {
+// (column k of the packed operand reads source column perm[k]; perm == null: identity)
+__global__ void pack_core_kernel(const float* w, __half* out, int rows, int cols, const int* perm) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * cols) return;
   const int r = i / cols, k = i % cols;
-  out[core_offset(r, k, cols) / 2] = __float2half_rn(w[i]);
+  out[core_offset(r, k, cols) / 2] = __float2half_rn(w[r * cols + (perm ? perm[k] : k)]);
 }
-cudaError_t launch_pack_core(const float* w, __half* out, int rows, int cols, cudaStream_t stream) {
-  pack_core_kernel<<<(rows * cols + 255) / 256, 256, 0, stream>>>(w, out, rows, cols);
+cudaError_t launch_pack_core(const float* w, __half* out, int rows, int cols, cudaStream_t stream, const int* perm) {
+  pack_core_kernel<<<(rows * cols + 255) / 256, 256, 0, stream>>>(w, out, rows, cols, perm);
   return cudaGetLastError();
 }
 

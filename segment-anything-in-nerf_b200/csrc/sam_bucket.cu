@@ -13,10 +13,9 @@
 // fp32 ulp of the accumulated sum, which is then rounded to fp16 anyway.  Rays whose weights are NaN (0/0,
 // sam_model.py:248) count as fully significant and produce the same NaN row as kernel B.
 //
-// NOT YET RUN ON HARDWARE (written after the round-1 GPU budget was spent): opt-in through snrf_set_feature_cutoff;
-// kernel B stays the default path.  The gather, MMA issue, TMEM epilogue and barrier protocol are copied from the
-// GPU-verified kernel B; what is new is the row -> (ray, slot) mapping through the bucket list, the per-lane ray
-// loads, and the generalised reduction width.
+// Default feature path since round 2 (snrf_set_feature_cutoff(ctx, < 0) selects kernel B): the whole GPU parity suite
+// runs through it.  The gather, MMA issue, TMEM epilogue and barrier protocol are kernel B's; what is new is the
+// row -> (ray, slot) mapping through the bucket list, the per-lane ray loads and the generalised reduction width.
 #include "kernels.cuh"
 
 namespace snrf {
@@ -143,8 +142,10 @@ __device__ __forceinline__ void epilogue_tile(const SamBucketParams& P, uint32_t
 // ceil(count[b] / (128 >> b)) tiles of 128 >> b rays x 1 << b slots) and strided over the CTAs, so W1 is staged and
 // TMEM allocated once per CTA and the buckets balance against each other.  The gather is the same code for every
 // bucket (row -> (ray, slot) is a shift and a mask); only the epilogue's reduction width is a compile-time variant.
+// 120 registers, not the 128 a 512-thread CTA could have: the 4096 left over are where a CTA of the push kernel
+// (exchange.cu) lives while this kernel occupies the SM.
 template <uint32_t M0, uint32_t M1>
-__global__ void __launch_bounds__(kThreads, 1) sam_bucket_kernel(const SamBucketParams P) {
+__global__ void __maxnreg__(120) sam_bucket_kernel(const SamBucketParams P) {
   extern __shared__ __align__(128) unsigned char smem[];
   unsigned char* s_w1 = smem;
   unsigned char* s_a = smem + kW1Bytes;
@@ -200,11 +201,19 @@ __global__ void __launch_bounds__(kThreads, 1) sam_bucket_kernel(const SamBucket
   const int s16 = lane >> 1, xb = lane & 1;
   const int row = g * 16 + s16;  // tile row this lane pair gathers
 
+  // Tiles are handed out by a device-wide counter (P.counts[kFeatBuckets], zeroed with the bucket sizes): a CTA whose SM
+  // is shared with another kernel - the push kernel of the tile exchange runs beside this one - simply takes fewer
+  // tiles instead of becoming the tail of the launch.  Thread 0 fetches the next index while the current tile is being
+  // gathered; the __syncthreads in the loop body publishes it.
+  __shared__ int s_next[2];
+  if (tid == 0) s_next[0] = atomicAdd(P.counts + kFeatBuckets, 1);
+  __syncthreads();
   int prev_b = 0, prev_count = 0;
   int64_t prev_tile = -1;
   int it = 0;
-  for (int64_t t = blockIdx.x; t < t5; t += gridDim.x, ++it) {
+  for (int64_t t = s_next[0]; t < t5; t = s_next[it & 1]) {
     const int buf = it & 1;
+    if (tid == 0) s_next[buf ^ 1] = atomicAdd(P.counts + kFeatBuckets, 1);
     unsigned char* a_tile = s_a + buf * kATileBytes;
     int64_t first;
     int count;
@@ -250,16 +259,48 @@ __global__ void __launch_bounds__(kThreads, 1) sam_bucket_kernel(const SamBucket
     prev_b = b;
     prev_count = count;
     prev_tile = tile;
+    ++it;
   }
   if (it > 0) run_epilogue(prev_b, prev_count, prev_tile, (it - 1) & 1, static_cast<uint32_t>(((it - 1) >> 1) & 1));
+  if (tid == 0 && !w1_ready) mbar_wait(smem_u32(&s_bar[2]), 0);  // a CTA that got no tile still owns an in-flight W1 copy
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
-__global__ void bucket_assign_kernel(const float* sam_w, float eps, int* counts, int* lists, int64_t n,
-                                     unsigned long long* totals) {
+// One thread per ray, same rule as bucket_assign_one (kernels.cuh, the host-checkable statement of it); the list
+// positions are handed out per CTA: the 256 rays of a CTA count themselves per bucket in shared memory, one thread per
+// bucket reserves the CTA's range with a single global atomic, and the rays then take consecutive positions inside it.
+// (One global atomic per ray on five addresses made this pre-pass 51 us per 131072 rays - 4 % of a frame.)  Rays of a
+// CTA stay neighbours in the lists, so the tiles built from them keep the spatial locality of the chunk.
+__global__ void __launch_bounds__(256) bucket_assign_kernel(const float* __restrict__ sam_w, float eps, int* counts,
+                                                            int* lists, int64_t n, unsigned long long* totals) {
+  __shared__ int s_count[kFeatBuckets], s_base[kFeatBuckets];
+  if (threadIdx.x < kFeatBuckets) s_count[threadIdx.x] = 0;
+  __syncthreads();
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i < n) bucket_assign_one(sam_w, eps, counts, lists, n, i, totals);
+  int b = -1, pos = 0;
+  if (i < n) {
+    const float4* row = reinterpret_cast<const float4*>(sam_w + i * 16);
+    int k = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 w = __ldg(row + q);
+      if (!(w.x < eps) && w.x != 0.f) k = 4 * q + 1;
+      if (!(w.y < eps) && w.y != 0.f) k = 4 * q + 2;
+      if (!(w.z < eps) && w.z != 0.f) k = 4 * q + 3;
+      if (!(w.w < eps) && w.w != 0.f) k = 4 * q + 4;
+    }
+    b = k <= 1 ? 0 : k <= 2 ? 1 : k <= 4 ? 2 : k <= 8 ? 3 : 4;
+    pos = atomicAdd(s_count + b, 1);
+  }
+  __syncthreads();
+  if (threadIdx.x < kFeatBuckets) {
+    const int c = s_count[threadIdx.x];
+    s_base[threadIdx.x] = c ? atomicAdd(counts + threadIdx.x, c) : 0;
+    if (totals && c) atomicAdd(totals + threadIdx.x, static_cast<unsigned long long>(c));
+  }
+  __syncthreads();
+  if (b >= 0) lists[static_cast<int64_t>(b) * n + s_base[b] + pos] = static_cast<int>(i);
 }
 
 constexpr uint32_t kEnc0MaskStd = 0xE00u, kEnc1MaskStd = 0xFFFu;  // as in sam.cu
@@ -284,7 +325,7 @@ cudaError_t launch_one(const SamBucketParams& P, int grid, cudaStream_t stream) 
 cudaError_t launch_bucket_assign(const float* sam_w, float eps, int* counts, int* lists, int64_t n,
                                  unsigned long long* totals, cudaStream_t stream) {
   if (n <= 0) return cudaSuccess;
-  cudaError_t e = cudaMemsetAsync(counts, 0, kFeatBuckets * sizeof(int), stream);
+  cudaError_t e = cudaMemsetAsync(counts, 0, (kFeatBuckets + 1) * sizeof(int), stream);  // + the tile counter of the main kernel
   if (e != cudaSuccess) return e;
   bucket_assign_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(sam_w, eps, counts, lists, n, totals);
   return cudaGetLastError();
