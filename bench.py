@@ -336,7 +336,9 @@ def run_native(args):
     fdt = torch.float16 if args.feature_dtype == "f16" else torch.float32
     r.set_feature_dtype(fdt)
     if args.march_first == -1:
-        args.march_first = 0  # measured: equal at N = 8 (514 vs 513 Mrays/s), worse at N = 4 (310 vs 326)
+        # measured (gpurun call 17, N = 8): 573 Mrays/s march-first vs 560 chunk-interleaved; at N = 4 (call 12) and
+        # N = 2 the interleaved frame is the faster one (326 vs 310 at N = 4)
+        args.march_first = 1 if world >= 8 else 0
     r.set_march_first(bool(args.march_first))
     o_all, d_all = frame_rays(conf)
     n_all = o_all.shape[0]
@@ -381,7 +383,7 @@ def run_native(args):
                     full[k] = big[offs[k]:offs[k] + n_all * c * esz[k]].view(dtypes[k]).view(n_all, c)
                 gather_mode = ("fused multimem.st (NVSwitch multicast)" if has_mc else
                                "copy engines (cudaMemcpyAsync to peer buffers per chunk)" if args.gather == "dma" else
-                               "push kernel (peer stores from 32 CTAs on a side stream, csrc/exchange.cu)" if args.gather == "push" else
+                               "push kernel (peer stores from 64 CTAs of 128 threads on a side stream, csrc/exchange.cu)" if args.gather == "push" else
                                "fused peer stores (NVLink P2P)")
             except Exception as e:  # no symmetric memory on this box: say so and use NCCL
                 if rank == 0:

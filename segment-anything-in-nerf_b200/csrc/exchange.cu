@@ -8,6 +8,7 @@
 // those persistent CTAs to retire, and the exchange of chunk c overlaps the march / feature kernels of chunk c + 1.
 // (The first version used 256-thread CTAs at 26 registers = 8192 allocated: it did not fit beside either kernel.)
 #include <stdlib.h>
+#include <string.h>
 
 #include "kernels.cuh"
 
@@ -42,6 +43,63 @@ __global__ void __launch_bounds__(kPushThreads, 16) push_rows_kernel(const uint4
   }
 }
 
+// The same exchange driven by the TMA unit (opt-in: SNRF_PUSH=tma): one thread per CTA streams 8 KB slices of the rows
+// global -> shared with cp.async.bulk, and from shared memory to every destination with cp.async.bulk stores (three
+// stages: the load of slice i + 1 is in flight while the stores of slices i and i - 1 drain).  The idea: no LSU
+// instruction touches the data, so a link that pushes back stalls the TMA queue of that CTA and not the load / store
+// pipe of the march or feature warps resident on the same SM (with plain stores the co-resident kernels lose 0.16 ms
+// per frame at N = 8).  Measured at N = 2 (gpurun call 18, bit-identity tests green): 193.8 Mrays/s against 218.1 with
+// the store kernel - its 24 KB of shared memory per CTA push the SM into the next shared-memory carve-out, and the march
+// kernel's gathers live on the L1 that is left (the same effect that makes 4 march CTAs per SM slower than 3).  Kept
+// for the comparison; the store kernel is the default.
+constexpr int kTmaStages = 3;
+constexpr uint32_t kTmaSlice = 8192;
+constexpr uint32_t kTmaSmem = kTmaStages * kTmaSlice + kTmaStages * 8;
+
+__device__ __forceinline__ void bulk_store_1d(void* dst, uint32_t src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(dst), "r"(src_smem), "r"(bytes) : "memory");
+}
+
+struct PushDstBytes {
+  char* p[kMaxPeers];
+};
+
+__global__ void __launch_bounds__(32) push_rows_tma_kernel(const char* __restrict__ src, PushDstBytes dst, int n_dst, size_t bytes) {
+  extern __shared__ __align__(128) unsigned char sm[];
+  if (threadIdx.x != 0) return;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sm + kTmaStages * kTmaSlice);
+  for (int s = 0; s < kTmaStages; ++s) mbar_init(smem_u32(&bar[s]), 1);
+  asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  const size_t n_slices = (bytes + kTmaSlice - 1) / kTmaSlice;
+  // this CTA's slices: blockIdx.x, blockIdx.x + gridDim.x, ...
+  const size_t mine = blockIdx.x < n_slices ? (n_slices - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  auto slice_off = [&](size_t i) { return (blockIdx.x + i * gridDim.x) * static_cast<size_t>(kTmaSlice); };
+  auto slice_len = [&](size_t i) {
+    const size_t off = slice_off(i);
+    return static_cast<uint32_t>(bytes - off < kTmaSlice ? bytes - off : kTmaSlice);
+  };
+  auto load = [&](size_t i) {
+    const int st = static_cast<int>(i % kTmaStages);
+    mbar_expect_tx(smem_u32(&bar[st]), slice_len(i));
+    bulk_load_1d(smem_u32(sm + st * kTmaSlice), src + slice_off(i), slice_len(i), smem_u32(&bar[st]));
+  };
+  if (mine > 0) load(0);
+  for (size_t i = 0; i < mine; ++i) {
+    const int st = static_cast<int>(i % kTmaStages);
+    if (i + 1 < mine) {
+      // slice i + 1 goes into the stage slice i - 2 was stored from: all but the newest store group must have been read
+      if (i >= 2) asm volatile("cp.async.bulk.wait_group.read 1;\n" ::: "memory");
+      load(i + 1);
+    }
+    mbar_wait(smem_u32(&bar[st]), static_cast<uint32_t>((i / kTmaStages) & 1));
+    const size_t off = slice_off(i);
+    const uint32_t len = slice_len(i);
+    for (int d = 0; d < n_dst; ++d) bulk_store_1d(dst.p[d] + off, smem_u32(sm + st * kTmaSlice), len);
+    asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+  }
+  asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");  // the writes are complete when the kernel is
+}
+
 }  // namespace
 
 cudaError_t launch_push_rows(const void* src, void* const* dst, int n_dst, size_t bytes, cudaStream_t stream) {
@@ -51,6 +109,14 @@ cudaError_t launch_push_rows(const void* src, void* const* dst, int n_dst, size_
   for (int d = 0; d < kMaxPeers; ++d) {
     D.p[d] = d < n_dst ? reinterpret_cast<uint4*>(dst[d]) : nullptr;
     if (d < n_dst && (reinterpret_cast<uintptr_t>(dst[d]) & 15u)) return cudaErrorInvalidValue;
+  }
+  static const bool tma = [] { const char* e = getenv("SNRF_PUSH"); return e && strcmp(e, "tma") == 0; }();
+  if (tma) {
+    static const int tgrid = [] { const char* e = getenv("SNRF_PUSH_GRID"); return e ? atoi(e) : 48; }();
+    PushDstBytes B;
+    for (int d = 0; d < kMaxPeers; ++d) B.p[d] = d < n_dst ? static_cast<char*>(dst[d]) : nullptr;
+    push_rows_tma_kernel<<<tgrid > 0 ? tgrid : 48, 32, kTmaSmem, stream>>>(static_cast<const char*>(src), B, n_dst, bytes);
+    return cudaGetLastError();
   }
   static const int grid = [] { const char* e = getenv("SNRF_PUSH_GRID"); return e ? atoi(e) : 64; }();
   push_rows_kernel<<<grid > 0 ? grid : 64, kPushThreads, 0, stream>>>(reinterpret_cast<const uint4*>(src), D, n_dst, bytes / 16);

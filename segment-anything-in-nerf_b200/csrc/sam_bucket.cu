@@ -27,7 +27,15 @@ constexpr int kHid = 256;   // hidden width
 constexpr uint32_t kSBO = kIn * 16;
 constexpr uint32_t kW1Bytes = kHid * kIn * 2;    // 98304
 constexpr uint32_t kATileBytes = 128 * kIn * 2;  // 49152
-constexpr uint32_t kSmemBytes = kW1Bytes + 2 * kATileBytes + 2 * 128 * 4 + 64;
+// One A tile, not two: the gathers of this kernel (and of the march kernel) live on the L1 that the shared-memory
+// carve-out leaves, and 145 KB instead of 193 KB moves the carve-out down a step.  The accumulator stays double
+// buffered in TMEM, so the epilogue of tile i - 1 still overlaps the MMAs of tile i; what is lost is only the overlap of
+// the 12 MMAs of tile i (< 1 us) with the first gathers of tile i + 1 (-DSNRF_SAMB_A_TILES=2 restores it).
+#ifndef SNRF_SAMB_A_TILES
+#define SNRF_SAMB_A_TILES 1
+#endif
+constexpr uint32_t kATiles = SNRF_SAMB_A_TILES;
+constexpr uint32_t kSmemBytes = kW1Bytes + kATiles * kATileBytes + 2 * 128 * 4 + 64;
 constexpr int kThreads = 512;
 
 // 12 levels x 4 (y,z) corners x 16 B for the sample this lane pair owns (identical to sam.cu's gather_f8)
@@ -149,7 +157,7 @@ __global__ void __maxnreg__(120) sam_bucket_kernel(const SamBucketParams P) {
   extern __shared__ __align__(128) unsigned char smem[];
   unsigned char* s_w1 = smem;
   unsigned char* s_a = smem + kW1Bytes;
-  float* s_sw = reinterpret_cast<float*>(smem + kW1Bytes + 2 * kATileBytes);  // [2][128]
+  float* s_sw = reinterpret_cast<float*>(smem + kW1Bytes + kATiles * kATileBytes);  // [2][128]
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_sw + 256);                // [2] MMA done, [1] W1 landed
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 3);
 
@@ -214,7 +222,10 @@ __global__ void __maxnreg__(120) sam_bucket_kernel(const SamBucketParams P) {
   for (int64_t t = s_next[0]; t < t5; t = s_next[it & 1]) {
     const int buf = it & 1;
     if (tid == 0) s_next[buf ^ 1] = atomicAdd(P.counts + kFeatBuckets, 1);
-    unsigned char* a_tile = s_a + buf * kATileBytes;
+    unsigned char* a_tile = s_a + (kATiles == 2 ? buf : 0) * kATileBytes;
+    // single A tile: the MMAs of the previous tile must have read it before this tile's rows are written (they were
+    // issued before the previous iteration's epilogue ran, so this wait is normally over before it starts)
+    if (kATiles == 1 && it > 0) mbar_wait(smem_u32(&s_bar[buf ^ 1]), static_cast<uint32_t>(((it - 1) >> 1) & 1));
     int64_t first;
     int count;
     const int b = bucket_of(t, first, count);  // LOG of this tile: 1 << b slots per ray, 128 >> b rays
