@@ -384,6 +384,7 @@ def run_native(args):
                 gather_mode = ("fused multimem.st (NVSwitch multicast)" if has_mc else
                                "copy engines (cudaMemcpyAsync to peer buffers per chunk)" if args.gather == "dma" else
                                "push kernel (peer stores from 64 CTAs of 128 threads on a side stream, csrc/exchange.cu)" if args.gather == "push" else
+                               "push kernel through the NVSwitch multicast alias (multimem.st from 64 CTAs of 128 threads on a side stream)" if args.gather == "pushmc" else
                                "fused peer stores (NVLink P2P)")
             except Exception as e:  # no symmetric memory on this box: say so and use NCCL
                 if rank == 0:
@@ -397,11 +398,14 @@ def run_native(args):
     def point_replication_at_peers():
         if symm is None:
             return
-        mc = int(getattr(symm, "multicast_ptr", 0) or 0) if args.gather == "mc" else 0
-        r.set_replication_mode(args.gather if args.gather in ("dma", "push") else "stores")
+        mc = int(getattr(symm, "multicast_ptr", 0) or 0) if args.gather in ("mc", "pushmc") else 0
+        r.set_replication_mode("push" if args.gather == "pushmc" else args.gather if args.gather in ("dma", "push") else "stores")
         for k, c in names.items():
             peers = [int(symm.buffer_ptrs[p]) + offs[k] for p in range(world) if p != rank]
-            r.set_replication(k, full[k], () if mc else peers, mc + offs[k] if mc else 0)
+            if args.gather == "pushmc":  # feature rows through the multicast alias, the small outputs through peer copies
+                r.set_replication(k, full[k], peers, mc + offs[k] if (mc and k == "sam") else 0)
+            else:
+                r.set_replication(k, full[k], () if mc else peers, mc + offs[k] if mc else 0)
 
     point_replication_at_peers()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
@@ -615,7 +619,7 @@ def main():
                     help="sam = BASELINE.json configs[2] (headline, default); rgb = configs[1]; clipseg_patch = configs[3]")
     ap.add_argument("--regime", choices=["scene", "init"], default="scene")
     ap.add_argument("--engine", choices=["tcgen05", "mma_sync"], default="tcgen05")
-    ap.add_argument("--gather", choices=["auto", "mc", "peer", "dma", "push", "nccl"], default="auto",
+    ap.add_argument("--gather", choices=["auto", "mc", "peer", "dma", "push", "pushmc", "nccl"], default="auto",
                     help="N > 1: how the tiles are exchanged (auto = push kernel; copy engines; fused multicast / peer stores; NCCL)")
     ap.add_argument("--feature-dtype", choices=["auto", "f32", "f16"], default="auto",
                     help="element type of the 256-d feature rows: auto = f32 on one GPU, f16 with N > 1 (wire and storage)")

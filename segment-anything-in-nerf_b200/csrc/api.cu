@@ -1087,9 +1087,13 @@ int snrf_render_frame(snrf_ctx* ctx, const float* origins, const float* dirs, co
           cudaStream_t cp = ctx->copy_stream[0];
           used |= 1u;
           CK(cudaStreamWaitEvent(cp, ctx->ev_out[c & 1], 0));
-          void* dst[kMaxPeers] = {nullptr};
-          for (int q = 0; q < R.n; ++q) dst[q] = reinterpret_cast<char*>(R.peer[q]) + off;
-          LAUNCH(launch_push_rows(sam_c, dst, R.n, bytes, cp));
+          if (R.mc) {  // one multicast store reaches every rank
+            LAUNCH(launch_push_rows_mc(sam_c, reinterpret_cast<char*>(R.mc) + off, bytes, cp));
+          } else {
+            void* dst[kMaxPeers] = {nullptr};
+            for (int q = 0; q < R.n; ++q) dst[q] = reinterpret_cast<char*>(R.peer[q]) + off;
+            LAUNCH(launch_push_rows(sam_c, dst, R.n, bytes, cp));
+          }
         } else {
           const int pieces = ctx->dma_split;
           const size_t piece = ((bytes / pieces) + 255) & ~static_cast<size_t>(255);

@@ -100,7 +100,29 @@ __global__ void __launch_bounds__(32) push_rows_tma_kernel(const char* __restric
   asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");  // the writes are complete when the kernel is
 }
 
+// Push through the NVSwitch multicast alias of the frame buffer: ONE multimem.st per 16 bytes reaches every rank (the
+// switch replicates it), so the SM issues a seventh of the store instructions of the peer-pointer kernel at N = 8 and the
+// rank's NVLink egress carries the rows once instead of seven times.  The ingress of every rank is unchanged.
+__global__ void __launch_bounds__(kPushThreads, 16) push_rows_mc_kernel(const uint4* __restrict__ src, uint4* mc, size_t n16) {
+  const size_t stride = static_cast<size_t>(gridDim.x) * kPushThreads;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * kPushThreads + threadIdx.x; i < n16; i += stride) {
+    const uint4 v = __ldcs(src + i);
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};\n" ::"l"(mc + i), "f"(__uint_as_float(v.x)),
+                 "f"(__uint_as_float(v.y)), "f"(__uint_as_float(v.z)), "f"(__uint_as_float(v.w))
+                 : "memory");
+  }
+}
+
 }  // namespace
+
+cudaError_t launch_push_rows_mc(const void* src, void* mc_dst, size_t bytes, cudaStream_t stream) {
+  if (bytes == 0) return cudaSuccess;
+  if ((bytes & 15u) || (reinterpret_cast<uintptr_t>(src) & 15u) || (reinterpret_cast<uintptr_t>(mc_dst) & 15u)) return cudaErrorInvalidValue;
+  static const int grid = [] { const char* e = getenv("SNRF_PUSH_GRID"); return e ? atoi(e) : 64; }();
+  push_rows_mc_kernel<<<grid > 0 ? grid : 64, kPushThreads, 0, stream>>>(reinterpret_cast<const uint4*>(src),
+                                                                        reinterpret_cast<uint4*>(mc_dst), bytes / 16);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_push_rows(const void* src, void* const* dst, int n_dst, size_t bytes, cudaStream_t stream) {
   if (n_dst <= 0 || bytes == 0) return cudaSuccess;

@@ -173,6 +173,7 @@ cudaError_t launch_tapgemm_tma(const GemmParams& P, int sm_count, cudaStream_t s
 
 // ---- tile exchange by peer stores from a small kernel (exchange.cu) --------------------------------
 cudaError_t launch_push_rows(const void* src, void* const* dst, int n_dst, size_t bytes, cudaStream_t stream);
+cudaError_t launch_push_rows_mc(const void* src, void* mc_dst, size_t bytes, cudaStream_t stream);
 
 // ---- stand-alone field queries (back Field.density_fn / SAMField.get_outputs) --------------------
 struct QueryParams {
