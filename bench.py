@@ -336,9 +336,9 @@ def run_native(args):
     fdt = torch.float16 if args.feature_dtype == "f16" else torch.float32
     r.set_feature_dtype(fdt)
     if args.march_first == -1:
-        # measured (gpurun call 17, N = 8): 573 Mrays/s march-first vs 560 chunk-interleaved; at N = 4 (call 12) and
-        # N = 2 the interleaved frame is the faster one (326 vs 310 at N = 4)
-        args.march_first = 1 if world >= 8 else 0
+        # measured at N = 8 (gpurun calls 17 / 24): multicast push 596 Mrays/s chunk-interleaved vs 557 march-first;
+        # peer-pointer push 560 vs 573; at N = 4 (call 12) and N = 2 the interleaved frame is the faster one as well
+        args.march_first = 0
     r.set_march_first(bool(args.march_first))
     o_all, d_all = frame_rays(conf)
     n_all = o_all.shape[0]
@@ -368,8 +368,9 @@ def run_native(args):
     # chunk's compute; a symmetric-memory barrier ends the frame.  Fallback / comparison: NCCL all-gather (--gather nccl).
     gather_mode, symm, full = "single", None, {}
     if args.gather == "auto":
-        # measured on 8 B200 (profiles/r02_multi_gpu.txt): push kernel 514 Mrays/s, copy engines 466, NCCL 306
-        args.gather = "push"
+        # measured on 8 B200 (profiles/r02_multi_gpu.txt): push through the multicast alias 596 Mrays/s, push through peer
+        # pointers 573, copy engines 496, NCCL 306 (older commit).  Without a multicast alias pushmc is the peer-pointer push.
+        args.gather = "pushmc"
     if world > 1:
         gather_mode = "nccl"
         if args.gather != "nccl":
