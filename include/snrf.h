@@ -66,8 +66,8 @@ int snrf_set_early_termination(snrf_ctx* ctx, float eps);
 /* HBM budget (bytes) for "bricks": cell-major copies of the leading levels of the proposal and nerfacto grids, in which
  * the 8 corner entries of a cell are 32 contiguous bytes (one sector, one 256-bit load per sample and level instead of
  * 8 scattered gathers; csrc/bricks.cu).  Pure re-layout: rendered values are bit-identical with any budget.  The
- * longest prefix of levels that fits is used (nerfacto 16..2048 x 16 levels: 11 levels = 3.5 GB, 12 = 9.3 GB,
- * 13 = 24.5 GB, 14 = 64.5 GB); rebuilt by every snrf_upload_proposal / snrf_upload_field_base.  Default 4 GiB
+ * longest prefix of levels that fits is used (nerfacto 16..2048 x 16 levels: 11 levels = 3.2 GiB, 12 = 8.5 GiB,
+ * 13 = 22.5 GiB, 14 = 59.3 GiB); rebuilt by every snrf_upload_proposal / snrf_upload_field_base.  Default 4 GiB
  * (environment SNRF_BRICK_GB overrides), 0 = off.  Optionally returns the number of bricked levels.  Synchronises. */
 int snrf_set_brick_budget(snrf_ctx* ctx, int64_t bytes, int* prop_levels, int* field_levels);
 /* Feature samples below the precision of their own sum.  cutoff >= 0: rays are bucketed by the number of leading slots
@@ -216,7 +216,11 @@ int snrf_set_replication(snrf_ctx* ctx, int which, void* local_base, int64_t byt
                          void* const* peer_bases_host, int n_peers);
 /* How snrf_render_frame moves replicated outputs: 0 (default) = the kernels' own stores (multimem.st through
  * mc_base, else st.global through the peer pointers); 1 = copy engines: kernels write locally and each chunk's rows
- * are pushed to every peer pointer with cudaMemcpyAsync on side streams, so the exchange costs no SM time at all. */
+ * are pushed to every peer pointer with cudaMemcpyAsync on side streams, so the exchange costs no SM time at all;
+ * 2 = push kernel (csrc/exchange.cu): kernels write locally and a small kernel on a high-priority side stream stores each
+ * chunk's feature rows into the other ranks' buffers - with ONE multimem.st per 16 bytes through mc_base when the "sam"
+ * descriptor has both mc_base and peer pointers, else with one store per peer pointer (the small per-ray outputs always
+ * go through copy engines once per frame).  Fastest measured mode at N = 8 (profiles/r02_multi_gpu.txt). */
 int snrf_set_replication_mode(snrf_ctx* ctx, int mode); /* 0 fused stores, 1 copy engines, 2 push kernel (csrc/exchange.cu) */
 
 /* ---- camera ray generation fused in front of the render -------------------------------
