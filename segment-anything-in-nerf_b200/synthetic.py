@@ -36,7 +36,7 @@ def make_synthetic_params(cfg: SAMNeRFConfig, regime: str = "scene", seed: int =
                 row is shifted negative (proposal -0.5, field -0.1): ``exp(MLP)`` then spans ~7 orders of
                 magnitude, space is mostly empty, rays terminate at ray-dependent depths from 0.1 to beyond the
                 contraction radius, accumulation stays ~1 and the sharpened top-k weights concentrate on 1-3
-                samples - the statistics of a trained scene (checked in tests/test_synthetic.py).
+                samples - the statistics of a trained scene (checked in tests/test_host.py::test_scene_regime_is_scene_like).
     """
     assert regime in REGIMES, regime
     gen = torch.Generator(device="cpu")
