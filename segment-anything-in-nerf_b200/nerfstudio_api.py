@@ -907,6 +907,35 @@ class SAMModel(torch.nn.Module):
         if getattr(self, "prompts", None) is not None:
             h, w = outputs["rgb"].shape[:2]
             outputs["prompt_points"] = P.prompts_in_image(self.prompts, intrin, c2w, w, h)
+            self._decode_mask(outputs)
+
+    def attach_mask_decoder(self, predictor) -> None:
+        """Give the model SAM's prompt encoder + mask decoder (``mask_decoder.SamMaskPredictor``, or a SAM checkpoint path /
+        state dict for ``SamMaskPredictor.from_sam_checkpoint``): the whole-image entry points then turn the remembered
+        prompts into ``outputs["masked_rgb"]`` like the reference (sam_model.py:485-486,514-527).  Kept out of the module
+        tree, like the reference's ``self.predictor``: the decoder is not part of the NeRF's ``state_dict()``."""
+        from .mask_decoder import SamMaskPredictor
+
+        if predictor is not None and not isinstance(predictor, SamMaskPredictor):
+            predictor = SamMaskPredictor.from_sam_checkpoint(predictor, device=self.renderer.device)
+        self.__dict__["predictor"] = predictor
+
+    def _decode_mask(self, outputs: Dict[str, torch.Tensor]) -> None:
+        """``predictor.set_feature(outputs["sam"])`` + ``generate_masked_img(predictor, prompts, 1s, rgb)`` for the prompts
+        that fall inside this view (sam_model.py:485-486,514-527).  Without an attached decoder, without a rendered SAM
+        map or without a prompt in view ``masked_rgb`` stays the plain rgb.  (The reference then draws the visible prompts
+        as red key points with torchvision - ``show_prompts``, sam_model.py:39-92 - which is viewer decoration and not
+        reproduced; ``prompts.visible`` gives the same selection.)"""
+        from .mask_decoder import generate_masked_img
+
+        pred = self.__dict__.get("predictor")
+        pts = outputs.get("prompt_points")
+        if pred is None or "sam" not in outputs or pts is None or len(pts) == 0:
+            return
+        h, w = outputs["rgb"].shape[:2]
+        pred.set_feature(outputs["sam"], (h, w))
+        rgb = outputs["rgb"].to(pred.device)
+        outputs["masked_rgb"] = generate_masked_img(pred, pts.cpu().numpy(), [1] * len(pts), rgb).to(outputs["rgb"].device)
 
     @torch.no_grad()
     def get_outputs_for_camera(self, camera: Camera, points=None, fast: bool = False) -> Dict[str, torch.Tensor]:
