@@ -160,3 +160,39 @@ def test_model_turns_prompts_into_a_masked_image(monkeypatch):
     m.attach_mask_decoder(None)
     again = m.get_outputs_for_camera_ray_bundle(bundle, points=np.array([[3, 2], [9, 5]]), intrin=intrin, c2w=c2w)
     assert again["masked_rgb"] is again["rgb"]
+
+
+@pytest.mark.gpu
+def test_gpu_rendered_map_through_the_decoder():
+    """The whole downstream chain on the device: camera -> rendered rgb / depth / SAM map (libsnrf) -> clicks lifted and
+    re-projected -> prompt encoder + mask decoder on the same GPU -> ``masked_rgb``; the decoder gives the same logits on
+    the GPU as on the CPU for the rendered map (library kernels, TF32 convolutions by torch's default: stated tolerance 5e-3 of
+    the largest logit)."""
+    from helpers import model_pair
+    from samnerf_b200.nerfstudio_api import SAMModel
+    from samnerf_b200.renderer import Camera
+    from samnerf_b200.synthetic import look_at
+
+    cfg, params, _ = model_pair("tiny", "scene", 6, False, 4)
+    m = SAMModel(cfg)
+    m.load_state_dict(params)
+    torch.manual_seed(0)
+    cpu_pred = SamMaskPredictor().eval()
+    m.attach_mask_decoder({k: v.clone() for k, v in cpu_pred.state_dict().items()})  # the checkpoint route, onto the GPU
+    assert m.__dict__["predictor"].device.type == "cuda"
+    cam = Camera(32.0, 32.0, 16.0, 12.0, 32, 24, look_at((1.1, 0.6, 0.45))[:3, :4])
+    out = m.get_outputs_for_camera(cam, points=[[10, 8], [20, 15]])
+    torch.cuda.synchronize()
+    assert out["masked_rgb"].shape == out["rgb"].shape and out["masked_rgb"].is_cuda and torch.isfinite(out["masked_rgb"]).all()
+    pts = out["prompt_points"].cpu().numpy()
+    gpu_pred = m.__dict__["predictor"]
+    gpu_pred.set_feature(out["sam"], (24, 32))
+    cpu_pred.set_feature(out["sam"].cpu(), (24, 32))
+    got = gpu_pred.predict(pts, [1] * len(pts), return_logits=True)
+    want = cpu_pred.predict(pts, [1] * len(pts), return_logits=True)
+    for a, b, what in zip(got, want, ("logits", "iou", "low")):
+        scale = float(b.abs().max()) + 1e-6
+        assert float((a.cpu() - b).abs().max()) <= 5e-3 * scale + 1e-5, what  # measured on B200: 7e-4 (TF32 transposed convs)
+    masks, _, _ = gpu_pred.predict(pts, [1] * len(pts))
+    differs = (out["masked_rgb"] - masked_image(masks[0, 0], out["rgb"])).abs().amax(dim=-1) > 1e-6
+    assert float(differs.float().mean()) < 1e-3  # the same mask up to sign flips of ~0 logits between two launches
