@@ -72,6 +72,48 @@ def click_points_reference(heat, image_width, image_height):
     return ns["clip_points"]
 
 
+def build_reference_clipseg(seed=0):
+    """The reference's ``CLIPDensePredT(version="ViT-B/16", reduce_dim=64)`` (sam_model.py:216) with OpenAI's ``clip``
+    package - absent here - stubbed out: its CLIP towers are only touched by the image / text branches, never by the
+    ``inp_feature`` branch with a tensor conditional that is pinned here."""
+    import types
+
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    if "clip" not in sys.modules:
+        class _NoClip(torch.nn.Module):
+            def __init__(self):
+                super().__init__()
+                self.visual = torch.nn.Identity()
+
+        stub = types.ModuleType("clip")
+        stub.load = lambda version, device="cpu", jit=False: (_NoClip(), None)
+        stub.tokenize = lambda *a, **k: (_ for _ in ()).throw(RuntimeError("no CLIP text tower in this container"))
+        sys.modules["clip"] = stub
+    from samnerf.clipseg.models.clipseg import CLIPDensePredT
+
+    model = CLIPDensePredT(version="ViT-B/16", reduce_dim=64)
+    model.load_state_dict(seeded_state({k: tuple(v.shape) for k, v in model.state_dict().items()}, seed), strict=True)
+    return model.eval()
+
+
+def seeded_state(shapes, seed: int):
+    """A state dict drawn from one seeded generator in sorted-key order (weights of the ClipSeg fixture: 1.1 M values that
+    the test regenerates instead of storing; layer norms near identity, everything else small and non-zero)."""
+    g = torch.Generator().manual_seed(seed)
+    out = {}
+    for k in sorted(shapes):
+        t = 0.08 * torch.randn(shapes[k], generator=g)
+        out[k] = t + 1.0 if (k.endswith("norm1.weight") or k.endswith("norm2.weight")) else t
+    return out
+
+
+def clipseg_inputs():
+    """Rendered-ClipSeg-map stand-in ``[32,32,192]`` and text-embedding stand-in ``[1,512]`` of the fixture (seeded)."""
+    g = torch.Generator().manual_seed(31)
+    return 0.3 * torch.randn(32, 32, 192, generator=g), torch.randn(1, 512, generator=g)
+
+
 def click_heat() -> torch.Tensor:
     """The heat map of the click fixture (the test regenerates it from the same seed instead of storing 1 MB):
     512 / 16 = 32 x 32 blocks - the reference's topk(k=1000) needs at least 1000 of them."""
@@ -98,6 +140,17 @@ def main():
             tag = f"{name}.{'multi' if multi else 'single'}"
             out[tag + ".logits"], out[tag + ".iou"], out[tag + ".low"] = masks.numpy(), iou.numpy(), low.numpy()
     out["clicks.points"] = click_points_reference(click_heat(), 1297, 840)
+    # ClipSeg decoder: the reference's module on a rendered-map stand-in, through the call of sam_model.py:487-499
+    clipseg = build_reference_clipseg(seed=21)  # the test rebuilds these weights with seeded_state(..., 21)
+    cmap, cond = clipseg_inputs()
+    acts = []
+    for _i in range(3):
+        _c = cmap[..., 64 * _i: 64 * (_i + 1)].reshape(-1, 64).unsqueeze(dim=1)
+        acts.append(torch.cat([_c.mean(dim=0, keepdim=True), _c], dim=0))
+    with torch.no_grad():
+        logits = clipseg(None, inp_feature={"activations": acts, "visual_q": None, "transformed_image_size": (32, 32)},
+                         conditional=cond)[0][0][0]
+    out["clipseg.logits_every_3rd"] = logits[::3, ::3].numpy()  # every token's 16 x 16 block is sampled ~28 times
     path = os.path.join(GOLDEN, "sam_decoder.npz")
     np.savez_compressed(path, **out)
     print(len(out), "arrays,", os.path.getsize(path), "bytes")

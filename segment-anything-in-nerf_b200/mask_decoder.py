@@ -16,8 +16,13 @@ reference's parameter names so that ``load_state_dict(strict=True)`` accepts the
 entries of a SAM checkpoint (``sam_vit_h_4b8939.pth``) unchanged; pinned by ``tests/golden/sam_decoder.npz`` (a
 reduced-width instance of the reference's own modules, weights + inputs + outputs) and, in the build container, against
 the reference's modules at full width (``tests/test_mask_decoder.py``).  The prompt encoder implements what the reference
-calls it with - point prompts; box and mask prompts raise.  The ClipSeg decoder (``CLIPDensePredT``,
-samnerf/clipseg/models/clipseg.py) needs OpenAI's ``clip`` package for its text tower and is not built.
+calls it with - point prompts; box and mask prompts raise.
+
+``ClipSegDecoder`` is the part of ``CLIPDensePredT`` (samnerf/clipseg/models/clipseg.py:301-500) that runs behind the
+rendered 32 x 32 x 192 ClipSeg map - the reference's own ``inp_feature`` branch (:453-497): FiLM conditioning, three
+transformer blocks over the rendered activations, the 16 x 16 transposed convolution - with the same parameter names, so
+``rd64-uni.pth`` loads.  The text prompt enters as its CLIP embedding (``cond [1,512]``, which the reference's
+``get_cond_vec`` accepts as well, :238-239); the CLIP text tower itself is OpenAI's ``clip`` package and not part of this.
 """
 from __future__ import annotations
 
@@ -317,6 +322,57 @@ def generate_masked_img(predictor: SamMaskPredictor, points, labels, image: torc
     """``generate_masked_img`` (sam_utils.py:45-54): one mask for all prompts, blended over the rendered rgb."""
     masks, _, _ = predictor.predict(points, labels, multimask_output=False)
     return masked_image(masks[0, 0], image, rgba)
+
+
+class ClipSegDecoder(nn.Module):
+    """``CLIPDensePredT(version="ViT-B/16", reduce_dim=64)`` (sam_model.py:216) without its CLIP towers: what
+    ``self.clipseg(None, inp_feature=..., conditional=...)`` computes (sam_model.py:487-499).  ``reduce`` / ``reduces`` are
+    part of the checkpoint layout (the rendered activations are already reduced, so they are not applied here either)."""
+
+    def __init__(self, reduce_dim: int = 64, n_heads: int = 4, depth: int = 3, cond_dim: int = 512, clip_width: int = 768,
+                 patch: int = 16, cond_layer: int = 0):
+        super().__init__()
+        self.film_mul, self.film_add = nn.Linear(cond_dim, reduce_dim), nn.Linear(cond_dim, reduce_dim)
+        self.reduce = nn.Linear(clip_width, reduce_dim)
+        self.reduces = nn.ModuleList([nn.Linear(clip_width, reduce_dim) for _ in range(depth)])
+        self.blocks = nn.ModuleList([nn.TransformerEncoderLayer(d_model=reduce_dim, nhead=n_heads) for _ in range(depth)])
+        self.trans_conv = nn.ConvTranspose2d(reduce_dim, 1, (patch, patch), stride=(patch, patch))
+        self.cond_layer = cond_layer
+
+    def forward(self, activations: Sequence[torch.Tensor], cond: torch.Tensor) -> torch.Tensor:
+        """``activations``: three ``[1 + T, 1, reduce_dim]`` token tensors (``prompts.clipseg_activations`` of the rendered
+        map, CLS slot first); ``cond [1, cond_dim]``.  Returns the ``[sqrt(T) * patch, sqrt(T) * patch]`` logit map."""
+        a = None
+        for i, (act, block) in enumerate(zip(activations, self.blocks)):
+            a = act if a is None else act + a
+            if i == self.cond_layer:
+                a = self.film_mul(cond) * a + self.film_add(cond)
+            a = block(a)
+        a = a[1:].permute(1, 2, 0)  # drop the CLS token -> [1, C, T]
+        side = int(math.sqrt(a.shape[2]))
+        return self.trans_conv(a.reshape(1, a.shape[1], side, side))[0, 0]
+
+    @classmethod
+    def from_checkpoint(cls, path_or_state, device="cpu") -> "ClipSegDecoder":
+        """``rd64-uni.pth`` (sam_model.py:217-220, loaded non-strictly over the CLIP-carrying model in the reference): here
+        every decoder key must be present, and keys of the CLIP towers, if any, are ignored."""
+        state = torch.load(path_or_state, map_location="cpu") if isinstance(path_or_state, (str, bytes)) else path_or_state
+        me = cls()
+        own = set(me.state_dict())
+        me.load_state_dict({k: v for k, v in state.items() if k in own}, strict=True)
+        return me.to(device).eval()
+
+
+def clipseg_heat_and_clicks(decoder: ClipSegDecoder, clipseg_map: torch.Tensor, cond: torch.Tensor, image_width: int,
+                            image_height: int):
+    """Rendered ``clipseg[32,32,192]`` + text embedding -> (``clipseg_feature [512,512,1]``, click prompts ``[n,2]``):
+    sam_model.py:487-512."""
+    from .prompts import clipseg_activations
+
+    dev = decoder.trans_conv.weight.device
+    with torch.no_grad():
+        heat = decoder(clipseg_activations(clipseg_map.to(dev, torch.float32)), cond.to(dev, torch.float32)).sigmoid()
+    return heat.unsqueeze(dim=-1), clipseg_click_points(heat, image_width, image_height)
 
 
 def clipseg_click_points(heat: torch.Tensor, image_width: int, image_height: int, k: int = 1000, thresh: float = 0.7,

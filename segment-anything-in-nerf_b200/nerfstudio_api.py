@@ -876,10 +876,10 @@ class SAMModel(torch.nn.Module):
                 for i in range(0, len(cb), chunk):
                     feats.append(self.forward(cb[i:i + chunk], get_feature=["clipseg"])["clipseg"])
                 outputs["clipseg"] = torch.cat(feats).view(32, 32, -1)
-        self._handle_prompts(outputs, points, intrin, c2w)
+        self._handle_prompts(outputs, points, intrin, c2w, text_prompt)
         return outputs
 
-    def _handle_prompts(self, outputs: Dict[str, torch.Tensor], points, intrin, c2w) -> None:
+    def _handle_prompts(self, outputs: Dict[str, torch.Tensor], points, intrin, c2w, text_prompt=None) -> None:
         """The prompt bookkeeping of sam_model.py:426-475 up to the point where the 2-D decoders take over: new clicks are
         lifted to 3-D once (at the rendered depth minus ``TOR``) and remembered in ``self.prompts``; every frame the
         remembered prompts are projected into the current view and the ones inside the image become
@@ -891,8 +891,10 @@ class SAMModel(torch.nn.Module):
         outputs["masked_rgb"] = outputs["rgb"]
         if "sam" in outputs:
             outputs["sam_embedding"] = P.pad_feature_map(outputs["sam"])
+        self._decode_clipseg(outputs, text_prompt)
         if points is None:
             self.prompts = None
+            self._decode_mask(outputs)  # ClipSeg clicks alone can prompt the mask (sam_model.py:509-516)
             return
         assert intrin is not None and c2w is not None
         intrin, c2w = torch.as_tensor(intrin, dtype=torch.float32).cpu(), torch.as_tensor(c2w, dtype=torch.float32).cpu()
@@ -907,7 +909,7 @@ class SAMModel(torch.nn.Module):
         if getattr(self, "prompts", None) is not None:
             h, w = outputs["rgb"].shape[:2]
             outputs["prompt_points"] = P.prompts_in_image(self.prompts, intrin, c2w, w, h)
-            self._decode_mask(outputs)
+        self._decode_mask(outputs)
 
     def attach_mask_decoder(self, predictor) -> None:
         """Give the model SAM's prompt encoder + mask decoder (``mask_decoder.SamMaskPredictor``, or a SAM checkpoint path /
@@ -920,6 +922,40 @@ class SAMModel(torch.nn.Module):
             predictor = SamMaskPredictor.from_sam_checkpoint(predictor, device=self.renderer.device)
         self.__dict__["predictor"] = predictor
 
+    def attach_clipseg_decoder(self, decoder, text_encoder=None) -> None:
+        """Give the model the ClipSeg decoder behind the rendered ClipSeg map (``mask_decoder.ClipSegDecoder``, or the path /
+        state dict of ``rd64-uni.pth``, sam_model.py:216-222).  ``text_prompt`` of the whole-image entry points is then
+        either the prompt's CLIP embedding ``[1,512]`` or - with ``text_encoder``, a callable ``str -> [1,512]`` such as
+        ``lambda s: clip_model.encode_text(clip.tokenize([s]))`` - the string itself; the CLIP text tower is OpenAI's ``clip``
+        package and not part of this repository.  Kept out of the module tree like ``self.clipseg`` weights are kept out of
+        the reference's checkpoints."""
+        from .mask_decoder import ClipSegDecoder
+
+        if decoder is not None and not isinstance(decoder, ClipSegDecoder):
+            decoder = ClipSegDecoder.from_checkpoint(decoder, device=self.renderer.device)
+        self.__dict__["clipseg_decoder"] = decoder
+        self.__dict__["text_encoder"] = text_encoder
+
+    def _decode_clipseg(self, outputs: Dict[str, torch.Tensor], text_prompt) -> None:
+        """sam_model.py:487-512: rendered ClipSeg map + text prompt -> ``outputs["clipseg_feature"]`` (the 512 x 512 heat map)
+        and ``outputs["clipseg_points"]`` (click prompts in image pixels, fed to the mask decoder with the user's clicks)."""
+        from .mask_decoder import clipseg_heat_and_clicks
+
+        dec = self.__dict__.get("clipseg_decoder")
+        if dec is None or "clipseg" not in outputs or text_prompt is None:
+            return
+        if isinstance(text_prompt, str):
+            enc = self.__dict__.get("text_encoder")
+            if enc is None:
+                raise RuntimeError("a text prompt needs CLIP's text tower: pass the prompt's 512-d CLIP embedding as text_prompt, "
+                                   "or attach_clipseg_decoder(decoder, text_encoder=...)")
+            text_prompt = enc(text_prompt)
+        cond = torch.as_tensor(text_prompt, dtype=torch.float32).reshape(1, -1)
+        h, w = outputs["rgb"].shape[:2]
+        heat, clicks = clipseg_heat_and_clicks(dec, outputs["clipseg"], cond, w, h)
+        outputs["clipseg_feature"] = heat.to(outputs["rgb"].device)
+        outputs["clipseg_points"] = torch.from_numpy(clicks)
+
     def _decode_mask(self, outputs: Dict[str, torch.Tensor]) -> None:
         """``predictor.set_feature(outputs["sam"])`` + ``generate_masked_img(predictor, prompts, 1s, rgb)`` for the prompts
         that fall inside this view (sam_model.py:485-486,514-527).  Without an attached decoder, without a rendered SAM
@@ -929,16 +965,22 @@ class SAMModel(torch.nn.Module):
         from .mask_decoder import generate_masked_img
 
         pred = self.__dict__.get("predictor")
-        pts = outputs.get("prompt_points")
-        if pred is None or "sam" not in outputs or pts is None or len(pts) == 0:
+        if pred is None or "sam" not in outputs:
             return
+        pts = [p.cpu().numpy().astype("float32") for p in (outputs.get("prompt_points"), outputs.get("clipseg_points"))
+               if p is not None and len(p) > 0]  # the user's clicks first, then ClipSeg's (sam_model.py:513-514)
+        if not pts:
+            return
+        import numpy as np
+
+        pts = np.concatenate(pts, axis=0)
         h, w = outputs["rgb"].shape[:2]
         pred.set_feature(outputs["sam"], (h, w))
         rgb = outputs["rgb"].to(pred.device)
-        outputs["masked_rgb"] = generate_masked_img(pred, pts.cpu().numpy(), [1] * len(pts), rgb).to(outputs["rgb"].device)
+        outputs["masked_rgb"] = generate_masked_img(pred, pts, [1] * len(pts), rgb).to(outputs["rgb"].device)
 
     @torch.no_grad()
-    def get_outputs_for_camera(self, camera: Camera, points=None, fast: bool = False) -> Dict[str, torch.Tensor]:
+    def get_outputs_for_camera(self, camera: Camera, points=None, fast: bool = False, text_prompt=None) -> Dict[str, torch.Tensor]:
         """``get_outputs_for_camera_ray_bundle(cameras.generate_rays(i, keep_shape=True))`` without the ray bundle
         (SURVEY.md 8 f-2): the three loops of sam_model.py:354-406 each become one ``snrf_render_camera`` call that
         generates its rays on the device - LOOP A every pixel, LOOP B the ``fh*p x fw*p`` strided sub-grid in
@@ -963,5 +1005,5 @@ class SAMModel(torch.nn.Module):
             points = [[0, 0]] * int(self.prompts.shape[0]) if getattr(self, "prompts", None) is not None else None
         intrin = torch.tensor([[camera.fx, 0.0, camera.cx], [0.0, camera.fy, camera.cy], [0.0, 0.0, 1.0]])
         self._handle_prompts(outputs, points, intrin if points is not None else None,
-                             camera.camera_to_world if points is not None else None)
+                             camera.camera_to_world if points is not None else None, text_prompt)
         return outputs

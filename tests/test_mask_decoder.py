@@ -196,3 +196,78 @@ def test_gpu_rendered_map_through_the_decoder():
     masks, _, _ = gpu_pred.predict(pts, [1] * len(pts))
     differs = (out["masked_rgb"] - masked_image(masks[0, 0], out["rgb"])).abs().amax(dim=-1) > 1e-6
     assert float(differs.float().mean()) < 1e-3  # the same mask up to sign flips of ~0 logits between two launches
+
+
+def test_clipseg_decoder_matches_reference_golden():
+    """``ClipSegDecoder`` on the fixture of oracle/make_decoder_golden.py: the reference's ``CLIPDensePredT`` (CLIP towers
+    stubbed: the ``inp_feature`` branch never touches them) with seeded weights, a rendered-map stand-in and a text
+    embedding, through the call of sam_model.py:487-499.  The weights are regenerated from the seed, loaded by NAME."""
+    from oracle.make_decoder_golden import clipseg_inputs, seeded_state
+    from samnerf_b200.mask_decoder import ClipSegDecoder, clipseg_heat_and_clicks
+
+    z = np.load(os.path.join(GOLDEN, "sam_decoder.npz"))
+    dec = ClipSegDecoder()
+    state = seeded_state({k: tuple(v.shape) for k, v in dec.state_dict().items()}, 21)
+    dec = ClipSegDecoder.from_checkpoint({**state, "clip_model.visual.proj": torch.zeros(768, 512)})  # tower keys are ignored
+    cmap, cond = clipseg_inputs()
+    heat, clicks = clipseg_heat_and_clicks(dec, cmap, cond, 1297, 840)
+    assert heat.shape == (512, 512, 1)
+    want = torch.from_numpy(z["clipseg.logits_every_3rd"]).sigmoid()
+    _close(heat[::3, ::3, 0], want, "clipseg heat map")
+    assert np.array_equal(clicks, clipseg_click_points(heat[..., 0], 1297, 840)) and clicks.shape[1] == 2
+    with pytest.raises(RuntimeError):
+        ClipSegDecoder.from_checkpoint({k: v for k, v in state.items() if not k.startswith("film_mul")})
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF, "samnerf", "clipseg", "models", "clipseg.py")),
+                    reason="the reference tree only exists in the build container")
+def test_clipseg_decoder_has_the_reference_modules_parameter_tree():
+    """Key names and shapes of the reference's ``CLIPDensePredT(version="ViT-B/16", reduce_dim=64)`` minus its CLIP towers
+    (what ``rd64-uni.pth`` holds) == ``ClipSegDecoder().state_dict()``, and the seeded fixture weights are the same tensors."""
+    from oracle.make_decoder_golden import build_reference_clipseg
+    from samnerf_b200.mask_decoder import ClipSegDecoder
+
+    ref = {k: v for k, v in build_reference_clipseg(seed=21).state_dict().items() if not k.startswith(("clip_model.", "model."))}
+    mine = ClipSegDecoder().state_dict()
+    assert {k: tuple(v.shape) for k, v in ref.items()} == {k: tuple(v.shape) for k, v in mine.items()}
+
+
+def test_model_text_prompt_through_clipseg_to_the_mask(monkeypatch):
+    """sam_model.py:487-527 end to end on the shim: rendered ClipSeg map + text embedding -> ``clipseg_feature`` heat map ->
+    ClipSeg click points -> (with the user's clicks) SAM mask decoder -> ``masked_rgb``.  A string prompt needs a text
+    encoder; without the decoders nothing changes."""
+    import samnerf_b200.nerfstudio_api as api
+    from fake_renderer import FakeRenderer
+    from helpers import model_pair
+    from oracle.make_decoder_golden import seeded_state
+    from samnerf_b200.mask_decoder import ClipSegDecoder
+    from samnerf_b200.synthetic import look_at, pinhole_rays
+
+    monkeypatch.setattr(api, "Renderer", FakeRenderer)
+    cfg, params, _ = model_pair("tiny", "scene", 6, True, 1)
+    m = api.SAMModel(cfg)
+    m.load_state_dict(params)
+    keys_before = set(m.state_dict())
+    torch.manual_seed(0)
+    m.attach_mask_decoder(SamMaskPredictor().eval())
+    dec = ClipSegDecoder()
+    state = seeded_state({k: tuple(v.shape) for k, v in dec.state_dict().items()}, 21)
+    state["trans_conv.bias"] = state["trans_conv.bias"] + 8.0  # hot everywhere: every block passes the 0.7 threshold
+    m.attach_clipseg_decoder(state)
+    assert set(m.state_dict()) == keys_before
+    H, W, f = 8, 12, 12.0
+    o, d = pinhole_rays(H, W, f, f, look_at((1.1, 0.6, 0.45)))
+    bundle = api.RayBundle(origins=o, directions=d, pixel_area=torch.ones(H, W, 1), camera_indices=torch.zeros(H, W, 1, dtype=torch.long))
+    cond = torch.randn(1, 512, generator=torch.Generator().manual_seed(2))
+    plain = m.get_outputs_for_camera_ray_bundle(bundle)
+    assert "clipseg_feature" not in plain and plain["masked_rgb"] is plain["rgb"]
+    out = m.get_outputs_for_camera_ray_bundle(bundle, text_prompt=cond)
+    assert out["clipseg_feature"].shape == (512, 512, 1) and float(out["clipseg_feature"].min()) > 0.7
+    assert out["clipseg_points"].shape == (1000, 2)
+    assert float(out["clipseg_points"][:, 0].max()) < W and float(out["clipseg_points"][:, 1].max()) < H
+    assert out["masked_rgb"] is not out["rgb"] and out["masked_rgb"].shape == out["rgb"].shape
+    with pytest.raises(RuntimeError, match="text tower"):
+        m.get_outputs_for_camera_ray_bundle(bundle, text_prompt="a chair")
+    m.attach_clipseg_decoder(state, text_encoder=lambda s: cond)
+    again = m.get_outputs_for_camera_ray_bundle(bundle, text_prompt="a chair")
+    assert torch.equal(again["clipseg_feature"], out["clipseg_feature"]) and torch.equal(again["masked_rgb"], out["masked_rgb"])
